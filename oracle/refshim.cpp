@@ -1,0 +1,168 @@
+// TEST INFRASTRUCTURE ONLY -- never imported, linked or executed by the product path.
+//
+// C-ABI shim over the UNMODIFIED reference headers under $(REF)/include (they are included
+// where they lie; nothing is copied).  The reference exports only CPIndex through pybind11
+// (src/bindings.cpp:115-240); the kernel-level functions of the query hot path are C++
+// templates with no binding, so the parity tests reach them through this file:
+//
+//   refshim_encode_queries   -> RaBitQEncoder<D>::encode_query_raw      (encoder/rabitq_encoder.hpp:73-79,197-209)
+//   refshim_rotate           -> RaBitQEncoderBase::rotate_raw_vector    (encoder/rabitq_encoder.hpp:81-86)
+//   refshim_fastscan         -> fastscan::compute_inner_products / compute_nbit_inner_products /
+//                               compute_msb_only_inner_products          (distance/fastscan_kernel.hpp:17-87,197-217,349-368)
+//   refshim_convert          -> fastscan::convert_to_distances_with_bounds / convert_msb_to_lower_bounds /
+//                               convert_nbit_to_distances_with_bounds    (distance/fastscan_kernel.hpp:89-194,371-425,220-346)
+//   refshim_dot / refshim_l2 -> dot_product_simd<D> / l2_distance_simd<D> (core/memory.hpp:65-96)
+//
+// Built by oracle/Makefile into oracle/_ref/libcphnsw_refshim.so (git-ignored).
+#include <cphnsw/core/codes.hpp>
+#include <cphnsw/core/memory.hpp>
+#include <cphnsw/core/util.hpp>
+#include <cphnsw/distance/fastscan_kernel.hpp>
+#include <cphnsw/distance/fastscan_layout.hpp>
+#include <cphnsw/encoder/rabitq_encoder.hpp>
+
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+using namespace cphnsw;
+
+#define FOR_EACH_D(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
+
+namespace {
+
+template <size_t D>
+int encode_queries_t(uint32_t dim, uint64_t nq, const float* q, uint8_t* lut, float* coeffs) {
+    RaBitQEncoder<D> enc(dim, constants::kDefaultRotationSeed);
+    std::vector<float> padded(D);
+    for (uint64_t i = 0; i < nq; ++i) {
+        // Index::search pads to D floats before encoding (api/hnsw_index.hpp:174-182)
+        std::memcpy(padded.data(), q + i * dim, dim * sizeof(float));
+        std::memset(padded.data() + dim, 0, (D - dim) * sizeof(float));
+        RaBitQQuery<D> rq = enc.encode_query_raw(padded.data());
+        std::memcpy(lut + i * (D / 4) * 16, rq.lut, (D / 4) * 16);
+        coeffs[3 * i + 0] = rq.coeff_fastscan;
+        coeffs[3 * i + 1] = rq.coeff_popcount;
+        coeffs[3 * i + 2] = rq.coeff_constant;
+    }
+    return 0;
+}
+
+template <size_t D>
+int rotate_t(uint32_t dim, uint64_t nq, const float* q, float* out) {
+    RaBitQEncoder<D> enc(dim, constants::kDefaultRotationSeed);
+    for (uint64_t i = 0; i < nq; ++i) enc.rotate_raw_vector(q + i * dim, out + i * D);
+    return 0;
+}
+
+template <size_t D, size_t B>
+int fastscan_t(const uint8_t* lut, const uint8_t* planes, uint32_t* nbit, uint32_t* msb, uint32_t* msb2) {
+    alignas(64) uint8_t lut_local[D / 4][16];
+    std::memcpy(lut_local, lut, sizeof(lut_local));
+    if constexpr (B == 1) {
+        FastScanCodeBlock<D, 32> blk;
+        std::memcpy(blk.packed, planes, sizeof(blk.packed));
+        fastscan::compute_inner_products<D>(lut_local, blk, nbit);
+        std::memcpy(msb, nbit, 32 * sizeof(uint32_t));
+        std::memcpy(msb2, nbit, 32 * sizeof(uint32_t));
+    } else {
+        NbitFastScanCodeBlock<D, B, 32> blk;
+        static_assert(sizeof(blk) == B * 4 * D, "plane layout");
+        std::memcpy(&blk, planes, sizeof(blk));
+        fastscan::compute_nbit_inner_products<D, B>(lut_local, blk, nbit, msb);
+        fastscan::compute_msb_only_inner_products<D, B>(lut_local, blk, msb2);
+    }
+    return 0;
+}
+
+struct QParams { float A, Bc, C, a, b, floor, slack; };
+
+template <size_t D, size_t B>
+int convert_t(const QParams& p, const uint32_t* nbit, const uint32_t* msb, const uint32_t* msb2,
+              const float* nop, const float* ip_qo, const float* ip_cp,
+              const uint16_t* pop, const uint16_t* wpop, uint32_t count, float dqp,
+              float* est, float* lower, float* msb_lower) {
+    RaBitQQuery<D> q;
+    q.coeff_fastscan = p.A; q.coeff_popcount = p.Bc; q.coeff_constant = p.C;
+    q.affine_a = p.a; q.affine_b = p.b; q.ip_qo_floor = p.floor; q.dot_slack = p.slack;
+    if constexpr (B == 1) {
+        fastscan::convert_to_distances_with_bounds<D>(q, nbit, nop, ip_qo, ip_cp, pop, count, est, lower, dqp);
+        std::memcpy(msb_lower, lower, count * sizeof(float));
+    } else {
+        fastscan::convert_msb_to_lower_bounds<D, B>(q, msb2, nop, ip_qo, ip_cp, pop, count, msb_lower, dqp);
+        fastscan::convert_nbit_to_distances_with_bounds<D, B>(q, nbit, msb, nop, ip_qo, ip_cp, pop, wpop,
+                                                               count, est, lower, dqp);
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int refshim_encode_queries(uint32_t dim, uint64_t nq, const float* q, uint8_t* lut, float* coeffs) {
+    size_t pd = next_power_of_two(dim);
+    switch (pd) {
+#define X(DD) case DD: return encode_queries_t<DD>(dim, nq, q, lut, coeffs);
+        FOR_EACH_D(X)
+#undef X
+    }
+    return -1;
+}
+
+int refshim_rotate(uint32_t dim, uint64_t nq, const float* q, float* out) {
+    size_t pd = next_power_of_two(dim);
+    switch (pd) {
+#define X(DD) case DD: return rotate_t<DD>(dim, nq, q, out);
+        FOR_EACH_D(X)
+#undef X
+    }
+    return -1;
+}
+
+int refshim_fastscan(uint32_t D, uint32_t B, const uint8_t* lut, const uint8_t* planes,
+                     uint32_t* nbit, uint32_t* msb, uint32_t* msb2) {
+#define X(DD) if (D == DD) { \
+        if (B == 1) return fastscan_t<DD, 1>(lut, planes, nbit, msb, msb2); \
+        if (B == 2) return fastscan_t<DD, 2>(lut, planes, nbit, msb, msb2); \
+        if (B == 4) return fastscan_t<DD, 4>(lut, planes, nbit, msb, msb2); }
+    FOR_EACH_D(X)
+#undef X
+    return -1;
+}
+
+// params = {coeff_fastscan, coeff_popcount, coeff_constant, affine_a, affine_b, ip_qo_floor, dot_slack}
+int refshim_convert(uint32_t D, uint32_t B, const float* params,
+                    const uint32_t* nbit, const uint32_t* msb, const uint32_t* msb2,
+                    const float* nop, const float* ip_qo, const float* ip_cp,
+                    const uint16_t* pop, const uint16_t* wpop, uint32_t count, float dqp,
+                    float* est, float* lower, float* msb_lower) {
+    QParams p{params[0], params[1], params[2], params[3], params[4], params[5], params[6]};
+#define X(DD) if (D == DD) { \
+        if (B == 1) return convert_t<DD, 1>(p, nbit, msb, msb2, nop, ip_qo, ip_cp, pop, wpop, count, dqp, est, lower, msb_lower); \
+        if (B == 2) return convert_t<DD, 2>(p, nbit, msb, msb2, nop, ip_qo, ip_cp, pop, wpop, count, dqp, est, lower, msb_lower); \
+        if (B == 4) return convert_t<DD, 4>(p, nbit, msb, msb2, nop, ip_qo, ip_cp, pop, wpop, count, dqp, est, lower, msb_lower); }
+    FOR_EACH_D(X)
+#undef X
+    return -1;
+}
+
+float refshim_dot(uint32_t D, const float* a, const float* b) {
+    switch (D) {
+#define X(DD) case DD: return dot_product_simd<DD>(a, b);
+        FOR_EACH_D(X)
+#undef X
+    }
+    return -1.0f;
+}
+
+float refshim_l2(uint32_t D, const float* a, const float* b) {
+    switch (D) {
+#define X(DD) case DD: return l2_distance_simd<DD>(a, b);
+        FOR_EACH_D(X)
+#undef X
+    }
+    return -1.0f;
+}
+
+}  // extern "C"
