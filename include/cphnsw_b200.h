@@ -1,0 +1,155 @@
+/* cphnsw_b200 -- C ABI of the B200-native CP-HNSW query path.
+ *
+ * This is the drop-in boundary for the query-time hot path of the reference
+ * (indrajeetadityaroy9/rabitq-ann-search).  The reference exposes that path only through the
+ * pybind11 class CPIndex (src/bindings.cpp:115-240, over PyIndexBase :21-37); a maintainer
+ * binds the functions below beside it (INTEGRATION.md shows the stub).  Plain pointers and
+ * sizes only: no C++ types, no torch types, no exceptions cross this boundary.  Every function
+ * returns 0 on success or a negative CPHNSW_B200_E* code; cphnsw_b200_last_error() gives the
+ * message.  There is no CPU fallback: without a CUDA device every call fails.
+ *
+ * Pointers whose name starts with d_ are device addresses (e.g. torch.Tensor.data_ptr());
+ * all others are host addresses.  `stream` is a cudaStream_t passed as void* (NULL = default).
+ */
+#ifndef CPHNSW_B200_H
+#define CPHNSW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPHNSW_B200_OK 0
+#define CPHNSW_B200_EINVAL (-1)    /* bad argument (std::invalid_argument -> ValueError)   */
+#define CPHNSW_B200_ERUNTIME (-2)  /* bad file / state   (std::runtime_error  -> RuntimeError) */
+#define CPHNSW_B200_ECUDA (-3)     /* CUDA runtime error                                    */
+#define CPHNSW_B200_ENOMEM (-4)
+
+typedef struct cphnsw_b200_index cphnsw_b200_index;
+
+/* Host view of a finalized reference index, field for field what Index<D,32,BitWidth> holds
+ * after finalize()/load() (api/hnsw_index.hpp:33-58,445-466; graph/rabitq_graph.hpp:286-290),
+ * i.e. also what its save file v2 stores (api/hnsw_index.hpp:217-303).  All ids are the
+ * reference's internal (BFS-reordered) ids. */
+typedef struct {
+    uint32_t D;          /* padded dimension (power of two, 16..2048) */
+    uint32_t bits;       /* BitWidth: 1, 2 or 4 */
+    uint32_t dim;        /* user dimension */
+    uint64_t n;
+    const uint8_t* search_data;  /* [n][rec_size] VertexSearchData<D,32,bits> records */
+    uint64_t rec_size;           /* sizeof(VertexSearchData) */
+    uint32_t nb_off;             /* offsetof(VertexSearchData, neighbors) = sizeof(code) */
+    const float* raw;            /* [n][D] zero-padded raw vectors */
+    const float* norm_sq;        /* [n] */
+    const float* centroid;       /* [dim] (only the exhaustive-scan mode reads it) */
+    const uint8_t* calibration;  /* CalibrationSnapshot, 248 bytes (api/hnsw_index.hpp:33-58) */
+    int32_t max_level;
+    uint32_t entry_point;        /* upper-layer entry point (== graph entry after load) */
+    uint32_t graph_entry_point;  /* layer-0 hub, used when max_level == 0 */
+    uint64_t rotation_seed;
+    uint32_t n_layers;                   /* upper layers, level L at index L-1 */
+    const uint32_t* const* layer_nodes;  /* [n_layers][layer_sizes[l]] sorted node ids */
+    const uint32_t* const* layer_offs;   /* [n_layers][layer_sizes[l]+1] CSR offsets */
+    const uint32_t* const* layer_nbrs;   /* [n_layers][...] neighbour node ids */
+    const uint32_t* layer_sizes;
+} cphnsw_b200_host_index;
+
+typedef struct {
+    uint32_t D, bits, dim;
+    uint64_t n;
+    int32_t max_level;
+    uint32_t entry_point;
+    uint32_t n_layers;
+    uint32_t block_stride;      /* bytes per re-laid-out neighbour block in HBM */
+    uint64_t device_bytes;      /* HBM held by the index */
+    float affine_a, affine_b, ip_qo_floor;
+    float search_gamma, gamma_max, gamma_beta;
+    uint64_t gamma_warmup;
+    int32_t num_slack_levels;
+    float slack_levels[32];
+} cphnsw_b200_info;
+
+/* Per-batch counters of the last search (sums over queries; max_beam is a max). */
+typedef struct {
+    uint64_t pops, expansions, exact_calls, beam_pushes, max_beam, nn_pushes;
+    uint64_t lb_skips, gamma_terms, msb_skipped, estimated, descent_dists;
+    uint64_t overflow_retries;  /* queries re-run with a larger frontier arena */
+} cphnsw_b200_stats;
+
+/* ---- lifetime: replaces PyIndexWrapper's unique_ptr<Index<...>> (src/bindings.cpp:39-75) ---- */
+int cphnsw_b200_create(int device, cphnsw_b200_index** out);
+void cphnsw_b200_destroy(cphnsw_b200_index* ix);
+const char* cphnsw_b200_last_error(const cphnsw_b200_index* ix); /* ix may be NULL: create() errors */
+
+/* ---- index hand-off ---------------------------------------------------------------------- */
+/* Parse a save file v2 written by CPIndex.save (api/hnsw_index.hpp:217-303), validate it like
+ * Index::load (:305-443: magic, version, R=32, bits, D = next_pow2(dim), truncation), re-lay it
+ * out and upload it. */
+int cphnsw_b200_load(cphnsw_b200_index* ix, const char* path);
+/* Same from an in-memory view (what a binding beside src/bindings.cpp would pass). */
+int cphnsw_b200_upload(cphnsw_b200_index* ix, const cphnsw_b200_host_index* host);
+int cphnsw_b200_get_info(const cphnsw_b200_index* ix, cphnsw_b200_info* out);
+
+/* ---- the hot path: replaces PyIndexBase::search_raw looped by search_batch
+ *      (src/bindings.cpp:60-63,177-218 -> Index::search api/hnsw_index.hpp:168-211) ----------- */
+/* Host buffers: queries [nq][dim] f32, ids [nq][k] i64, dists [nq][k] f32; rows padded with
+ * -1 / FLT_MAX exactly like bindings.cpp:201-210.  k == 0 behaves as the reference does
+ * (searches with k = 1, writes nothing). */
+int cphnsw_b200_search_batch(cphnsw_b200_index* ix, const float* queries, uint64_t nq, uint64_t k,
+                             int64_t* ids, float* dists);
+/* Device buffers, asynchronous on `stream` unless a frontier arena overflows (then it
+ * synchronises and re-runs the affected queries). */
+int cphnsw_b200_search_batch_device(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq,
+                                    uint64_t k, int64_t* d_ids, float* d_dists, void* stream);
+/* Counters of the last search_batch* call (synchronises). */
+int cphnsw_b200_last_stats(cphnsw_b200_index* ix, cphnsw_b200_stats* out);
+/* Tuning knobs that do not change results: warps in flight and frontier arena size. */
+int cphnsw_b200_set_option(cphnsw_b200_index* ix, const char* name, int64_t value);
+
+/* ---- kernel-level hooks (parity tests and micro-benchmarks) --------------------------------- */
+/* K1: replaces RaBitQEncoder::encode_query_raw (encoder/rabitq_encoder.hpp:73-79,197-209) after
+ * the zero-padding of Index::search (api/hnsw_index.hpp:174-180).  Any output may be NULL.
+ * d_lut [nq][D/4][16] u8, d_coeffs [nq][3] f32, d_rotated [nq][D] f32 (scaled rotated query),
+ * d_uplanes [nq][4][max(D,128)/32] u32 (bit t of the 4-bit query values, the kernels' own form).
+ * center != 0 subtracts the index centroid first (exhaustive-scan mode only). */
+int cphnsw_b200_prepare_queries(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq, int center,
+                                uint8_t* d_lut, float* d_coeffs, float* d_rotated,
+                                uint32_t* d_uplanes, void* stream);
+/* K2: replaces fastscan::compute_inner_products / compute_nbit_inner_products /
+ * compute_msb_only_inner_products and the three convert_* epilogues
+ * (distance/fastscan_kernel.hpp:17-87,197-217,349-368 and :89-194,220-346,371-425) over the
+ * neighbour blocks of `nblocks` vertices.  Block i uses query d_query_of_block[i] (or query 0
+ * when NULL) of the nq queries prepared by K1 (d_uplanes, d_coeffs), dist_qp_sq d_dqp[i] and the
+ * slack level d_slack_level[i] (or level 0 when NULL).  d_vertex_ids NULL = vertices
+ * first_vertex .. first_vertex+nblocks-1.  Outputs are [nblocks][32]; any may be NULL. */
+int cphnsw_b200_fastscan_blocks(cphnsw_b200_index* ix, const uint32_t* d_uplanes, const float* d_coeffs,
+                                uint64_t nq, const uint32_t* d_query_of_block,
+                                const uint32_t* d_vertex_ids, uint64_t first_vertex, uint64_t nblocks,
+                                const float* d_dqp, const int32_t* d_slack_level,
+                                uint32_t* d_nbit, uint32_t* d_msb, uint32_t* d_msb2,
+                                float* d_est, float* d_lower, float* d_msb_lower, void* stream);
+/* K4 primitive: replaces the exact_l2 lambda (search/rabitq_search.hpp:88-93, dot_product_simd
+ * core/memory.hpp:81-96): out[q][j] = max(|q|^2 + norm_sq[id] - 2<q,x_id>, 0), ids [nq][m]. */
+int cphnsw_b200_exact_l2(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq,
+                         const uint32_t* d_ids, uint64_t m, float* d_out, void* stream);
+/* K3 prologue: replaces greedy_search_layer over the upper layers (api/hnsw_index.hpp:195-202,
+ * 617-638): layer-0 entry point per query. */
+int cphnsw_b200_greedy_descent(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq,
+                               uint32_t* d_entry, void* stream);
+
+/* ---- exhaustive batched scan (bits == 1 indexes; composed from reference primitives, the
+ *      reference has no such mode: see DESIGN.md) over internal ids [id_begin, id_end) -------- */
+int cphnsw_b200_exhaustive_search(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq,
+                                  uint64_t k, uint64_t kprime, uint64_t id_begin, uint64_t id_end,
+                                  int64_t* d_ids, float* d_dists, void* stream);
+/* Estimator only: integer sums [nq][id_end-id_begin] u32 and estimates f32 (either may be NULL). */
+int cphnsw_b200_exhaustive_estimates(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq,
+                                     uint64_t id_begin, uint64_t id_end,
+                                     uint32_t* d_sums, float* d_est, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,157 @@
+"""Kernel-level hooks of the C ABI as torch-tensor functions (parity tests, micro-benchmarks).
+
+Each function launches exactly one of the library's kernels on tensors that already live on the
+index's GPU; torch is only the buffer allocator here.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _capi
+
+
+def _dev(ix):
+    return torch.device("cuda", ix._device)
+
+
+def _stream(ix):
+    return torch.cuda.current_stream(_dev(ix)).cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def prepare_queries(ix, queries: torch.Tensor, center: bool = False):
+    """K1.  Returns dict(lut u8 [nq,D/4,16], coeffs f32 [nq,3], rotated f32 [nq,D], uplanes i32 [nq,4,W])."""
+    info = ix.info()
+    D, nq = info["D"], queries.shape[0]
+    W = max(D, 128) // 32
+    q = queries.to(_dev(ix), torch.float32).contiguous()
+    out = {
+        "lut": torch.empty((nq, D // 4, 16), dtype=torch.uint8, device=q.device),
+        "coeffs": torch.empty((nq, 3), dtype=torch.float32, device=q.device),
+        "rotated": torch.empty((nq, D), dtype=torch.float32, device=q.device),
+        "uplanes": torch.empty((nq, 4, W), dtype=torch.int32, device=q.device),
+    }
+    _capi.check(ix.handle, ix._lib.cphnsw_b200_prepare_queries(
+        ix.handle, q.data_ptr(), nq, int(center), out["lut"].data_ptr(), out["coeffs"].data_ptr(),
+        out["rotated"].data_ptr(), out["uplanes"].data_ptr(), _stream(ix)))
+    return out
+
+
+def fastscan_blocks(ix, uplanes, coeffs, dqp, vertex_ids=None, first_vertex=0, nblocks=None,
+                    query_of_block=None, slack_level=None, want=("nbit", "msb", "msb2", "est", "lower", "msb_lower")):
+    """K2 over the neighbour blocks of `vertex_ids` (or a contiguous range).  Outputs are [nblocks, 32]."""
+    dev = _dev(ix)
+    if vertex_ids is not None:
+        vertex_ids = vertex_ids.to(dev, torch.int32).contiguous()
+        nblocks = vertex_ids.numel()
+    dqp = dqp.to(dev, torch.float32).contiguous()
+    assert dqp.numel() == nblocks
+    if query_of_block is not None:
+        query_of_block = query_of_block.to(dev, torch.int32).contiguous()
+    if slack_level is not None:
+        slack_level = slack_level.to(dev, torch.int32).contiguous()
+    out = {}
+    for name in ("nbit", "msb", "msb2"):
+        out[name] = torch.empty((nblocks, 32), dtype=torch.int32, device=dev) if name in want else None
+    for name in ("est", "lower", "msb_lower"):
+        out[name] = torch.empty((nblocks, 32), dtype=torch.float32, device=dev) if name in want else None
+    _capi.check(ix.handle, ix._lib.cphnsw_b200_fastscan_blocks(
+        ix.handle, uplanes.data_ptr(), coeffs.data_ptr(), uplanes.shape[0], _ptr(query_of_block), _ptr(vertex_ids),
+        first_vertex, nblocks, dqp.data_ptr(), _ptr(slack_level), _ptr(out["nbit"]), _ptr(out["msb"]),
+        _ptr(out["msb2"]), _ptr(out["est"]), _ptr(out["lower"]), _ptr(out["msb_lower"]), _stream(ix)))
+    return {k: v for k, v in out.items() if v is not None}
+
+
+def exact_l2(ix, queries: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    """K4 primitive: exact distances of ids [nq, m] to queries [nq, dim]."""
+    dev = _dev(ix)
+    q = queries.to(dev, torch.float32).contiguous()
+    ids = ids.to(dev, torch.int32).contiguous()
+    out = torch.empty(ids.shape, dtype=torch.float32, device=dev)
+    _capi.check(ix.handle, ix._lib.cphnsw_b200_exact_l2(
+        ix.handle, q.data_ptr(), q.shape[0], ids.data_ptr(), ids.shape[1], out.data_ptr(), _stream(ix)))
+    return out
+
+
+def greedy_descent(ix, queries: torch.Tensor) -> torch.Tensor:
+    """K3 prologue: layer-0 entry point per query."""
+    dev = _dev(ix)
+    q = queries.to(dev, torch.float32).contiguous()
+    out = torch.empty((q.shape[0],), dtype=torch.int32, device=dev)
+    _capi.check(ix.handle, ix._lib.cphnsw_b200_greedy_descent(ix.handle, q.data_ptr(), q.shape[0], out.data_ptr(), _stream(ix)))
+    return out
+
+
+def exhaustive_estimates(ix, queries: torch.Tensor, id_begin: int = 0, id_end: int | None = None):
+    dev = _dev(ix)
+    q = queries.to(dev, torch.float32).contiguous()
+    id_end = ix.size if id_end is None else id_end
+    m = id_end - id_begin
+    sums = torch.empty((q.shape[0], m), dtype=torch.int32, device=dev)
+    est = torch.empty((q.shape[0], m), dtype=torch.float32, device=dev)
+    _capi.check(ix.handle, ix._lib.cphnsw_b200_exhaustive_estimates(
+        ix.handle, q.data_ptr(), q.shape[0], id_begin, id_end, sums.data_ptr(), est.data_ptr(), _stream(ix)))
+    return sums, est
+
+
+def exhaustive_search(ix, queries: torch.Tensor, k: int, kprime: int, id_begin: int = 0, id_end: int | None = None):
+    dev = _dev(ix)
+    q = queries.to(dev, torch.float32).contiguous()
+    id_end = ix.size if id_end is None else id_end
+    ids = torch.empty((q.shape[0], k), dtype=torch.int64, device=dev)
+    dists = torch.empty((q.shape[0], k), dtype=torch.float32, device=dev)
+    _capi.check(ix.handle, ix._lib.cphnsw_b200_exhaustive_search(
+        ix.handle, q.data_ptr(), q.shape[0], k, kprime, id_begin, id_end, ids.data_ptr(), dists.data_ptr(), _stream(ix)))
+    return ids, dists
+
+
+def upload_arrays(ix, *, D, bits, dim, search_data, raw, norm_sq, calibration, centroid=None, max_level=0,
+                  entry_point=0, graph_entry_point=0, rotation_seed=42, layers=()):
+    """cphnsw_b200_upload from numpy arrays laid out like the reference's in-memory index.
+
+    search_data: uint8 [n, rec_size] VertexSearchData records; raw: float32 [n, D]; calibration: the
+    248-byte CalibrationSnapshot; layers: sequence of (nodes, offsets, neighbours) uint32 arrays.
+    """
+    import ctypes as C
+
+    import numpy as np
+
+    n = search_data.shape[0]
+    sd = np.ascontiguousarray(search_data, np.uint8)
+    raw = np.ascontiguousarray(raw, np.float32)
+    ns = np.ascontiguousarray(norm_sq, np.float32)
+    cal = np.ascontiguousarray(np.frombuffer(bytes(calibration), np.uint8))
+    cen = np.ascontiguousarray(np.zeros(dim, np.float32) if centroid is None else centroid, np.float32)
+    words = (D + 63) // 64
+    storage = -(-(8 * words * bits) // 64) * 64
+    nb_off = -(-(storage + 8) // 64) * 64
+    h = _capi.HostIndex()
+    h.D, h.bits, h.dim, h.n = D, bits, dim, n
+    h.search_data, h.rec_size, h.nb_off = sd.ctypes.data, sd.shape[1], nb_off
+    h.raw, h.norm_sq, h.centroid, h.calibration = raw.ctypes.data, ns.ctypes.data, cen.ctypes.data, cal.ctypes.data
+    h.max_level, h.entry_point, h.graph_entry_point, h.rotation_seed = max_level, entry_point, graph_entry_point, rotation_seed
+    nl = len(layers)
+    h.n_layers = nl
+    u32p = C.POINTER(C.c_uint32)
+    keep = []
+    arrs = [(u32p * max(nl, 1))() for _ in range(3)]
+    sizes = np.zeros(max(nl, 1), np.uint32)
+    for i, (nodes, offs, nbrs) in enumerate(layers):
+        nodes = np.ascontiguousarray(nodes, np.uint32)
+        offs = np.ascontiguousarray(offs, np.uint32)
+        nbrs = np.ascontiguousarray(nbrs if len(nbrs) else np.zeros(1, np.uint32), np.uint32)
+        keep += [nodes, offs, nbrs]
+        for a, x in zip(arrs, (nodes, offs, nbrs)):
+            a[i] = x.ctypes.data_as(u32p)
+        sizes[i] = nodes.size
+    h.layer_nodes, h.layer_offs, h.layer_nbrs = (C.cast(a, C.POINTER(u32p)) for a in arrs)
+    h.layer_sizes = sizes.ctypes.data_as(u32p)
+    _capi.check(ix.handle, ix._lib.cphnsw_b200_upload(ix.handle, C.byref(h)))
+    info = _capi.Info()
+    _capi.check(ix.handle, ix._lib.cphnsw_b200_get_info(ix.handle, C.byref(info)))
+    ix._info = info
+    ix._finalized = True
+    ix._source_path = None

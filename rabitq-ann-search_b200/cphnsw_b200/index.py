@@ -1,0 +1,229 @@
+"""`CPIndex` -- the reference's Python index class (src/bindings.cpp:115-240) with the query path
+on a B200.
+
+Same surface: ``CPIndex(dim, bits=1)``, ``build``, ``finalize``, ``search``, ``search_batch``,
+``save``, ``load``, properties ``size``, ``dim``, ``is_finalized``; same argument meaning, return
+shapes, padding (-1 / FLT_MAX) and exception types.  Index construction and calibration are not
+part of this library: ``build`` / ``finalize`` / ``save`` call the reference's own module
+(``cphnsw``: whichever one is importable, or the one given to :func:`set_host_module`), and the
+finalized index is handed to the device through the reference's save-file format.  ``load`` and
+all searches need only this library.  Searches never run on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import tempfile
+
+import numpy as np
+
+from . import _capi
+
+_host_module = None
+_FLT_MAX = np.finfo(np.float32).max
+_SUPPORTED_D = (16, 32, 64, 128, 256, 512, 1024, 2048)
+
+
+def set_host_module(mod) -> None:
+    """Use `mod` (an imported reference ``cphnsw`` package) for build / finalize / save."""
+    global _host_module
+    _host_module = mod
+
+
+def _host():
+    global _host_module
+    if _host_module is None:
+        try:
+            import cphnsw  # the reference package, wherever the user installed it
+        except ImportError as e:  # pragma: no cover - depends on the environment
+            raise RuntimeError(
+                "build/finalize/save are performed by the reference's cphnsw module, which is not "
+                "importable here; install it or call cphnsw_b200.set_host_module()") from e
+        _host_module = cphnsw
+    return _host_module
+
+
+def _next_pow2(v: int) -> int:
+    p = 1
+    while p < v:
+        p <<= 1
+    return p
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.split(".")[0] == "torch"
+
+
+class CPIndex:
+    """Drop-in for ``cphnsw.CPIndex`` whose ``search`` / ``search_batch`` run on the GPU."""
+
+    def __init__(self, dim: int, bits: int = 1, device: int | None = None):
+        dim = int(dim)
+        bits = int(bits)
+        # the factory's checks and messages (src/bindings.cpp:77-113)
+        if dim <= 0 or _next_pow2(dim) not in _SUPPORTED_D:
+            raise ValueError(
+                f"Unsupported dimension {dim} (padded to {_next_pow2(max(dim, 1))}). Supported padded dims: "
+                "16, 32, 64, 128, 256, 512, 1024, 2048.")
+        if bits not in (1, 2, 4):
+            raise ValueError(f"Unsupported bits={bits}. Supported: 1, 2, 4.")
+        self._dim, self._bits = dim, bits
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0")) if "CPHNSW_B200_DEVICE" not in os.environ \
+                else int(os.environ["CPHNSW_B200_DEVICE"])
+        self._device = device
+        self._lib = _capi.lib()
+        h = C.c_void_p()
+        rc = self._lib.cphnsw_b200_create(device, C.byref(h))
+        if rc != _capi.OK:
+            _capi.check(None, rc)
+        self._h = h
+        self._host_index = None   # reference CPIndex (only when built here)
+        self._source_path = None  # save file the device copy came from
+        self._finalized = False
+        self._info = None
+        self._tmp = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.cphnsw_b200_destroy(self._h)
+                self._h = None
+            if getattr(self, "_tmp", None):
+                self._tmp.cleanup()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+    # ---- construction: the reference does it ---------------------------------------------------
+    def build(self, vectors) -> None:
+        v = np.asarray(vectors)
+        if v.ndim != 2 or v.shape[1] != self._dim:
+            raise ValueError("vectors must be a (n, dim) float32 array")
+        v = np.ascontiguousarray(v, dtype=np.float32)
+        self._host_index = _host().CPIndex(dim=self._dim, bits=self._bits)
+        self._finalized = False
+        self._host_index.build(v)
+
+    def finalize(self) -> None:
+        if self._host_index is None:
+            raise RuntimeError("Finalize called without a pending build.")
+        self._host_index.finalize()
+        # hand-off through the reference's own serialisation (api/hnsw_index.hpp:217-303)
+        self._tmp = tempfile.TemporaryDirectory(prefix="cphnsw_b200_")
+        path = os.path.join(self._tmp.name, "index.bin")
+        self._host_index.save(path)
+        self._load_device(path)
+
+    def save(self, path) -> None:
+        if not self._finalized:
+            raise RuntimeError("Index must be finalized before saving.")
+        if self._host_index is not None:
+            self._host_index.save(str(path))
+        elif os.path.abspath(str(path)) != os.path.abspath(self._source_path):
+            shutil.copyfile(self._source_path, str(path))
+
+    def load(self, path) -> None:
+        self._host_index = None
+        self._load_device(str(path))
+
+    def _load_device(self, path: str) -> None:
+        _capi.check(self._h, self._lib.cphnsw_b200_load(self._h, path.encode()))
+        info = _capi.Info()
+        _capi.check(self._h, self._lib.cphnsw_b200_get_info(self._h, C.byref(info)))
+        if info.dim != self._dim or info.bits != self._bits:
+            raise RuntimeError(
+                f"Parameter mismatch: file has dim={info.dim}, bits={info.bits}; index was created with "
+                f"dim={self._dim}, bits={self._bits}.")
+        self._info = info
+        self._source_path = path
+        self._finalized = True
+
+    # ---- the hot path --------------------------------------------------------------------------
+    def search(self, query, k: int = 10):
+        q = np.asarray(query.detach().cpu() if _is_torch(query) else query)
+        if q.ndim != 1 or q.shape[0] != self._dim:
+            raise ValueError("query must be 1D and match index dimension")
+        kk = max(int(k), 1)   # Index::search searches with max(k,1) and returns what it found
+        ids, dists = self.search_batch(q[None, :], kk)
+        m = int((ids[0] >= 0).sum())
+        return ids[0, :m].copy(), dists[0, :m].copy()
+
+    def search_batch(self, queries, k: int = 10):
+        """(ids int64 [nq,k], distances float32 [nq,k]); rows padded with -1 / FLT_MAX.
+
+        numpy (or CPU torch) input -> numpy output, host<->device copies inside the call.
+        CUDA torch tensor input -> CUDA torch tensors, no host round trip.
+        """
+        k = int(k)
+        if k < 0:
+            raise ValueError("k must be non-negative")
+        if _is_torch(queries) and queries.is_cuda:
+            return self._search_batch_cuda(queries, k)
+        q = np.asarray(queries.detach() if _is_torch(queries) else queries)
+        if q.ndim != 2 or q.shape[1] != self._dim:
+            raise ValueError("queries must be a (n, dim) array")
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        nq = q.shape[0]
+        ids = np.empty((nq, k), np.int64)
+        dists = np.empty((nq, k), np.float32)
+        self._require_finalized()
+        _capi.check(self._h, self._lib.cphnsw_b200_search_batch(
+            self._h, q.ctypes.data, nq, k, ids.ctypes.data, dists.ctypes.data))
+        return ids, dists
+
+    def _search_batch_cuda(self, queries, k: int):
+        import torch
+
+        if queries.dim() != 2 or queries.shape[1] != self._dim:
+            raise ValueError("queries must be a (n, dim) array")
+        if queries.device.index != self._device:
+            raise ValueError(f"queries live on cuda:{queries.device.index}, the index on cuda:{self._device}")
+        q = queries.detach().to(torch.float32).contiguous()
+        nq = q.shape[0]
+        ids = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        dists = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+        self._require_finalized()
+        stream = torch.cuda.current_stream(q.device).cuda_stream
+        _capi.check(self._h, self._lib.cphnsw_b200_search_batch_device(
+            self._h, q.data_ptr(), nq, k, ids.data_ptr(), dists.data_ptr(), stream))
+        return ids, dists
+
+    def _require_finalized(self):
+        if not self._finalized:
+            raise RuntimeError("Index must be finalized (or loaded) before searching on the device.")
+
+    # ---- introspection -------------------------------------------------------------------------
+    @property
+    def size(self) -> int:
+        if self._info is not None:
+            return int(self._info.n)
+        return int(self._host_index.size) if self._host_index is not None else 0
+
+    @property
+    def dim(self) -> int:
+        return self._dim
+
+    @property
+    def is_finalized(self) -> bool:
+        return self._finalized
+
+    @property
+    def handle(self):
+        """Opaque native handle (for the kernel-level hooks in cphnsw_b200.hooks)."""
+        return self._h
+
+    def info(self) -> dict:
+        self._require_finalized()
+        i = self._info
+        d = {n: getattr(i, n) for n, _ in i._fields_ if n != "slack_levels"}
+        d["slack_levels"] = [float(x) for x in i.slack_levels][: max(i.num_slack_levels, 0)]
+        return d
+
+    def last_stats(self) -> dict:
+        st = _capi.Stats()
+        _capi.check(self._h, self._lib.cphnsw_b200_last_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def set_option(self, name: str, value: int) -> None:
+        _capi.check(self._h, self._lib.cphnsw_b200_set_option(self._h, name.encode(), int(value)))

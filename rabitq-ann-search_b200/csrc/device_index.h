@@ -1,0 +1,116 @@
+// Device-side view of a finalized CP-HNSW index as this library lays it out in HBM, plus the
+// host-side owner that builds it.  See DESIGN.md "Data layout in HBM".
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/cphnsw_b200.h"
+
+namespace cpb {
+
+constexpr uint32_t kInvalid = 0xFFFFFFFFu;
+constexpr int kMaxLevels = 24;
+constexpr uint32_t kR = 32;  // fixed layer-0 degree (src/bindings.cpp:42)
+
+// CalibrationSnapshot fields the query path consumes (api/hnsw_index.hpp:33-58)
+struct Calib {
+    float affine_a, affine_b, ip_qo_floor;
+    float slack[32];
+    int32_t num_slack;
+    float gamma, gamma_max, gamma_beta;
+    uint64_t gamma_warmup;
+};
+
+// One upper HNSW layer as slot-addressed CSR.  A "slot" is the position of a node in the layer's
+// sorted node list; neighbour lists carry both the node id (for the distance) and the
+// neighbour's own slot, so the greedy descent never searches (find_edge, hnsw_index.hpp:468-474,
+// becomes a table walk).  down[s] = slot of node[s] one level below (level 1: the node id).
+struct Level {
+    const uint32_t* node;
+    const uint32_t* offs;
+    const uint32_t* nbr_node;
+    const uint32_t* nbr_slot;  // kInvalid when the neighbour has no edge record at this level
+    const uint32_t* down;      // kInvalid when absent below
+    uint32_t size;
+};
+
+// Neighbour block of one vertex in HBM (block_stride bytes, 128-B aligned):
+//   [plane b][chunk c][slot v] uint4   code bits of dims 128c..128c+127 of neighbour v, plane b
+//                                      (bit j of word w <-> dim 128c+32w+j); planes MSB first
+//   aux_off + 0    ids   u32[32]
+//   aux_off + 128  nop   f32[32]
+//   aux_off + 256  ip_qo f32[32]
+//   aux_off + 384  ip_cp f32[32]
+//   aux_off + 512  pops  u32[32]   lo16 = popcounts (plane-0 popcount), hi16 = weighted_popcounts
+//   aux_off + 640  count u32
+struct DevIndex {
+    uint32_t D, B, dim;
+    uint32_t nch;  // 128-dim chunks per code plane = max(D,128)/128
+    uint32_t T;    // D/8: length of one exact-L2 accumulator chain
+    uint64_t n;
+    const uint8_t* blocks;
+    uint32_t block_stride, aux_off;
+    // raw vectors, accumulator-major: rawT[id][l*T + t] = raw[id][8t + l]  (l = 0..7)
+    const float* rawT;
+    const float* norm_sq;
+    const float* signs;     // [3][D]
+    const float* centroid;  // [dim]
+    int32_t max_level;
+    uint32_t entry_point;        // node id
+    uint32_t entry_slot;         // its slot in level max_level (kInvalid if it has no record)
+    uint32_t graph_entry_point;  // used when max_level == 0
+    uint32_t n_levels;
+    Level levels[kMaxLevels];  // level L at [L-1]
+    // per-vertex 1-bit codes for the exhaustive scan (B == 1 only)
+    const uint32_t* flat_codes;  // [n][nch*4]
+    const float* flat_nop;
+    const float* flat_ipqo;
+    const uint16_t* flat_pop;
+    Calib calib;
+};
+
+// prepared query state in HBM (written by K1, read by K2/K3/K5)
+struct QueryState {
+    float* qT;          // [nq][D] padded raw query, accumulator-major
+    uint32_t* uplanes;  // [nq][4][nch*4]
+    float* coeffs;      // [nq][4] A, Bc, C, |q|^2
+};
+
+struct Stats {
+    unsigned long long pops, expansions, exact_calls, beam_pushes, max_beam, nn_pushes;
+    unsigned long long lb_skips, gamma_terms, msb_skipped, estimated, descent_dists;
+};
+
+}  // namespace cpb
+
+struct cphnsw_b200_index {
+    int device = 0;
+    bool loaded = false;
+    std::string err;
+    cpb::DevIndex dev{};
+    uint64_t device_bytes = 0;
+    std::vector<void*> allocs;  // everything dev points to
+    int num_sms = 148;
+    // options (do not change results)
+    int64_t warps_per_cta = 8;
+    int64_t ctas_per_sm = 4;
+    int64_t beam_capacity = 1 << 15;  // frontier entries per in-flight query (first attempt)
+    // scratch, grown on demand
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void* bitmaps = nullptr;   // zero between searches; slot i at i * bitmap_words
+    size_t bitmaps_bytes = 0;
+    void* qstate = nullptr;
+    size_t qstate_bytes = 0;
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+    void* h_stage = nullptr;  // pinned
+    size_t h_stage_bytes = 0;
+    cpb::Stats* d_stats = nullptr;
+    uint32_t* d_counters = nullptr;  // [0] work counter, [1] overflow count
+    cphnsw_b200_stats last_stats{};
+    cudaStream_t own_stream = nullptr;
+};

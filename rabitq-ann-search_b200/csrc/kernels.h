@@ -1,0 +1,86 @@
+// Launchers of the sm_100a kernels (one translation unit each).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_index.h"
+
+namespace cpb {
+
+constexpr uint32_t kCoeffStride = 8;  // A, Bc, C, |q|^2, |q-c|^2, pad
+
+// ---- K1 query preparation (query_prep.cu) ------------------------------------------------
+struct PrepOut {
+    uint8_t* lut;       // [nq][D/4][16]           (reference form; parity hook only)
+    float* coeffs;      // [nq][kCoeffStride]
+    float* rotated;     // [nq][D]
+    uint32_t* uplanes;  // [nq][4][nch*4]
+    float* qT;          // [nq][D] accumulator-major padded raw query
+};
+cudaError_t launch_query_prep(const DevIndex& ix, const float* d_queries, uint32_t nq, int center,
+                              const PrepOut& out, cudaStream_t stream);
+
+// ---- K2 FastScan over neighbour blocks (fastscan_blocks.cu) --------------------------------
+struct FastScanArgs {
+    const uint32_t* uplanes;  // [nq][4][nch*4]
+    const float* coeffs;      // [nq][kCoeffStride]
+    uint32_t nq;
+    const uint32_t* query_of_block;  // may be NULL
+    const uint32_t* vertex_ids;      // may be NULL
+    uint64_t first_vertex, nblocks;
+    const float* dqp;                // [nblocks]
+    const int32_t* slack_level;      // may be NULL
+    uint32_t *nbit, *msb, *msb2;     // [nblocks][32], may be NULL
+    float *est, *lower, *msb_lower;  // [nblocks][32], may be NULL
+};
+cudaError_t launch_fastscan_blocks(const DevIndex& ix, const FastScanArgs& a, int num_sms, cudaStream_t stream);
+
+// ---- K3 (+K4 fused) layer-0 Distance-Adaptive Beam Search (search.cu) --------------------------
+struct SearchArgs {
+    uint32_t nq;               // work items
+    const uint32_t* query_list;  // NULL = identity; else work item i is query query_list[i]
+    uint32_t k;                // max(user k, 1)
+    uint32_t kout;             // user k (row stride of the outputs)
+    int64_t* ids;              // [*][kout]
+    float* dists;              // [*][kout]
+    const float* qT;           // prepared queries
+    const uint32_t* uplanes;
+    const float* coeffs;
+    uint8_t* scratch;          // per-slot arenas (frontier heap, large result lists): may hold garbage
+    size_t slot_stride;        // bytes per slot
+    size_t heap_off, nn_off;   // inside a slot
+    uint32_t beam_capacity;    // frontier entries per slot
+    uint32_t* bitmaps;         // per-slot "estimated" bitmaps: all-zero between queries
+    uint32_t bitmap_words, chunk_words;
+    uint32_t* counters;        // [0] work counter, [1] number of overflowed queries
+    uint32_t* overflow_list;   // queries whose frontier overflowed (to be re-run)
+    Stats* stats;              // may be NULL
+    uint32_t* entry_out;       // descent-only mode: layer-0 entry point per query (else NULL)
+};
+struct SearchLaunch { int ctas, warps_per_cta; size_t smem_per_cta; };
+size_t search_smem_per_warp(const DevIndex& ix, uint32_t k);
+cudaError_t launch_search(const DevIndex& ix, const SearchArgs& a, int ctas, int warps_per_cta, cudaStream_t stream);
+
+// ---- K4 primitive: exact distances of listed ids (search.cu) ----------------------------------
+cudaError_t launch_exact_l2(const DevIndex& ix, const float* qT, const float* coeffs, uint32_t nq,
+                            const uint32_t* ids, uint32_t m, float* out, cudaStream_t stream);
+
+// ---- index re-layout (relayout.cu) -------------------------------------------------------------
+cudaError_t launch_relayout_blocks(const DevIndex& ix, const uint8_t* d_records, uint64_t rec_size, uint32_t nb_off,
+                                   uint64_t first, uint32_t count, cudaStream_t stream);
+cudaError_t launch_relayout_raw(const DevIndex& ix, const float* d_raw, uint64_t first, uint32_t count,
+                                cudaStream_t stream);
+
+// ---- K5 exhaustive scan (exhaustive.cu) ---------------------------------------------------------
+struct ExhaustiveArgs {
+    const uint32_t* uplanes; const float* coeffs; const float* qT;
+    uint32_t nq; uint64_t id_begin, id_end;
+    uint32_t k, kprime;
+    uint32_t* sums; float* est;       // optional dense outputs [nq][id_end-id_begin]
+    int64_t* ids; float* dists;       // [nq][k]
+    void* workspace; size_t workspace_bytes;
+};
+size_t exhaustive_workspace_bytes(const DevIndex& ix, uint32_t nq, uint64_t m, uint32_t kprime);
+cudaError_t launch_exhaustive(const DevIndex& ix, const ExhaustiveArgs& a, int num_sms, cudaStream_t stream);
+
+}  // namespace cpb
