@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- QPS of the CP-HNSW query path (RaBitQ FastScan estimate + beam search + exact-L2 rerank).
+
+    python bench.py --gpus N --steps K --warmup W                 # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the reference's CPU path (oracle/_ref)
+
+One step = one search_batch over the workload's query batch (BASELINE.json configs[1]: 1M x 128,
+4-bit codes, 10k queries, k = 10).  The index is built ONCE by the reference's own build code
+(oracle/_ref/refbuild, see its header for why the stock finalize() cannot do 1M) and both arms load
+that same file; it is looked up in bench_cache/ (prebuilt, travels with the tree), then in
+/tmp/cphnsw_b200_bench_cache/, and built on the spot otherwise.  N > 1: one process per GPU, index
+replicated, each rank searches its own 10k queries (weak scaling, no data-path collective).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "rabitq-ann-search_b200"))
+TMP_CACHE = Path("/tmp/cphnsw_b200_bench_cache")
+FLT_MAX = np.finfo(np.float32).max
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------------
+def synthetic(n, dim, seed, clusters=0, sigma_c=4.0):
+    rng = np.random.default_rng(seed)
+    if clusters:
+        centers = rng.standard_normal((clusters, dim)).astype(np.float32) * np.float32(sigma_c)
+        return (centers[rng.integers(0, clusters, n)] + rng.standard_normal((n, dim)).astype(np.float32)).astype(np.float32)
+    return rng.standard_normal((n, dim)).astype(np.float32)
+
+
+def make_queries(args, rank):
+    if args.clusters:
+        centers = np.random.default_rng(args.seed).standard_normal((args.clusters, args.dim)).astype(np.float32) * np.float32(4.0)
+        rng = np.random.default_rng(99 + rank)
+        return (centers[rng.integers(0, args.clusters, args.nq)] + rng.standard_normal((args.nq, args.dim)).astype(np.float32)).astype(np.float32)
+    return np.random.default_rng(99 + rank).standard_normal((args.nq, args.dim)).astype(np.float32)
+
+
+def index_name(args):
+    dist = f"cl{args.clusters}" if args.clusters else "iid"
+    return f"c2_{args.n}x{args.dim}_b{args.bits}_{dist}_seed{args.seed}.bin"
+
+
+def obtain_index(args, rank, world):
+    """Path of the finalized index file, building it with the reference's own code if nobody has yet."""
+    name = index_name(args)
+    for d, src in ((ROOT / "bench_cache", "prebuilt (bench_cache/, built by oracle/_ref/refbuild)"), (TMP_CACHE, "cached in /tmp")):
+        if (d / name).exists():
+            return d / name, src
+    TMP_CACHE.mkdir(parents=True, exist_ok=True)
+    path = TMP_CACHE / name
+    if rank == 0:
+        refbuild = ROOT / "oracle" / "_ref" / "refbuild"
+        if not refbuild.exists():
+            raise SystemExit("no index file and no oracle/_ref/refbuild to build one (run __graft_entry__.build() where /root/reference exists)")
+        log(f"[bench] building {name} with the reference's build code ({os.cpu_count()} cores) ...")
+        vec = TMP_CACHE / (name + ".f32")
+        synthetic(args.n, args.dim, args.seed, args.clusters).tofile(vec)
+        t = time.time()
+        tmp = str(path) + ".part"
+        subprocess.run([str(refbuild), str(args.dim), str(args.bits), str(args.n), str(vec), tmp], check=True)
+        os.replace(tmp, path)
+        vec.unlink()
+        log(f"[bench] index built in {time.time() - t:.0f} s")
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    return path, "built on this box by oracle/_ref/refbuild"
+
+
+def parse_save_header(path):
+    with open(path, "rb") as f:
+        h = f.read(68)
+    u32 = lambda o: int.from_bytes(h[o:o + 4], "little")  # noqa: E731
+    return {"D": u32(12), "bits": u32(20), "dim": u32(24), "n": int.from_bytes(h[28:36], "little")}
+
+
+def raw_vectors(path):
+    """Raw vectors in internal-id order straight from the save file -- for ground truth."""
+    h = parse_save_header(path)
+    off = 68 + 248 + 72 + 4 * h["dim"] + 8 * h["n"]
+    return np.memmap(path, np.float32, "r", off, (h["n"], h["D"]))
+
+
+def recall_at_k(ids, gt):
+    """Reference definition (cphnsw/eval.py:23-28): |set(result) & set(truth)| / k, averaged."""
+    k = gt.shape[1]
+    hit = 0
+    for r, g in zip(ids, gt):
+        hit += len(set(r[:k].tolist()) & set(g.tolist()))
+    return hit / (len(ids) * k)
+
+
+def ground_truth(path, q, k, device):
+    import torch
+
+    base = raw_vectors(path)
+    dim = q.shape[1]
+    qt = torch.from_numpy(q).to(device)
+    best_d = torch.full((q.shape[0], k), float("inf"), device=device)
+    best_i = torch.zeros((q.shape[0], k), dtype=torch.int64, device=device)
+    step = 262144
+    for s in range(0, base.shape[0], step):
+        b = torch.from_numpy(np.ascontiguousarray(base[s:s + step, :dim])).to(device)
+        d = (qt * qt).sum(1, keepdim=True) - 2.0 * (qt @ b.T) + (b * b).sum(1)[None, :]
+        dd, ii = torch.topk(d, k, dim=1, largest=False)
+        cat_d = torch.cat([best_d, dd], 1)
+        cat_i = torch.cat([best_i, ii + s], 1)
+        best_d, sel = torch.topk(cat_d, k, dim=1, largest=False)
+        best_i = torch.gather(cat_i, 1, sel)
+    return best_i.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the unmodified reference's search_batch on the host cores
+# ---------------------------------------------------------------------------------------------------
+def reference_module():
+    ref_dir = ROOT / "oracle" / "_ref"
+    if not any((ref_dir / "cphnsw").glob("_core*.so")):
+        return None
+    sys.path.insert(0, str(ref_dir))
+    import cphnsw
+
+    return cphnsw
+
+
+def time_reference(args, path, q, budget_s, steps, warmup):
+    """QPS of the stock reference CPIndex.search_batch (all host cores) on a bounded sample of q."""
+    cph = reference_module()
+    if cph is None:
+        return None
+    cores = os.cpu_count()
+    idx = cph.CPIndex(dim=args.dim, bits=args.bits)
+    t = time.time()
+    idx.load(str(path))
+    log(f"[bench] reference loaded the index in {time.time() - t:.1f} s")
+    probe = min(len(q), 4 * cores)
+    t = time.perf_counter()
+    idx.search_batch(q[:probe], args.k)
+    per_q = (time.perf_counter() - t) / probe
+    m = int(min(len(q), max(probe, budget_s / max(per_q, 1e-9) / max(steps + warmup, 1))))
+    sample = q[:m]
+    for _ in range(warmup):
+        idx.search_batch(sample, args.k)
+    times = []
+    for _ in range(steps):
+        t = time.perf_counter()
+        ids, _ = idx.search_batch(sample, args.k)
+        times.append(time.perf_counter() - t)
+    total = sum(times)
+    return {"value": m * steps / total, "unit": "queries/s", "cores": cores, "kind": "reference",
+            "sample": f"first {m} of the {len(q)} queries x {steps} steps, CPIndex.search_batch from oracle/_ref (unmodified reference, OMP all cores)",
+            "ms_per_step": 1e3 * total / steps, "ids": ids, "m": m}
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--bits", type=int, default=4)
+    ap.add_argument("--nq", type=int, default=10_000)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--clusters", type=int, default=0)
+    ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-recall", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = (f"{args.n}x{args.dim} synthetic {'clustered(%d)' % args.clusters if args.clusters else 'iid N(0,1)'}, "
+                f"{args.bits}-bit RaBitQ CP-HNSW graph search, {args.nq} queries/GPU, k={args.k}")
+    metric = "QPS (search_batch queries/s; recall@10 of the reference on the same index reported beside it)"
+
+    # ---------------- reference arm: rank 0 alone, CPU only --------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        path, src = obtain_index(args, 0, 1)
+        q = make_queries(args, 0)
+        r = time_reference(args, path, q, budget_s=90.0, steps=args.steps, warmup=args.warmup)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/cphnsw/_core*.so (the compiled reference) is not in the tree"}))
+            return
+        line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8 LUT sums + f32", "data": "synthetic",
+                "config": {"workload": workload, "index_source": src, "index_file": index_name(args)},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ---------------- this repo's CUDA path ------------------------------------------------------------
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the query path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import cphnsw_b200
+
+    path, src = obtain_index(args, rank, world)
+    ix = cphnsw_b200.CPIndex(args.dim, args.bits, device=local)
+    t = time.time()
+    ix.load(str(path))
+    info = ix.info()
+    log(f"[bench] rank {rank}: index on cuda:{local} in {time.time() - t:.1f} s, {info['device_bytes'] / 2**30:.2f} GiB")
+    q = make_queries(args, rank)
+    q_dev = torch.from_numpy(q).cuda()
+    q_pin = torch.from_numpy(q).pin_memory()
+    ids_pin = torch.empty((args.nq, args.k), dtype=torch.int64).pin_memory()
+    dist_pin = torch.empty((args.nq, args.k), dtype=torch.float32).pin_memory()
+    lib, h = ix._lib, ix.handle
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t_ = torch.tensor([x], dtype=torch.float64, device="cuda")
+        torch.distributed.all_reduce(t_, op=torch.distributed.ReduceOp.MAX)
+        return float(t_.item())
+
+    # -- one untimed pass with the counters on (expansions etc. for the roofline), then the fast path ---
+    ix.set_option("collect_stats", 1)
+    ix.search_batch(q_dev, args.k)
+    st = ix.last_stats()
+    ix.set_option("collect_stats", 0)
+
+    # -- value: device-resident queries, CUDA events on the launching stream ------------------------
+    for _ in range(args.warmup):
+        ix.search_batch(q_dev, args.k)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms, prep_ms, retries = [], [], 0
+    barrier()
+    with ClockSampler(local) as clocks:
+        time.sleep(1.0)   # let nvidia-smi finish attaching before the timed region
+        ev0.record()
+        for _ in range(args.steps):
+            ids_dev, dists_dev = ix.search_batch(q_dev, args.k)
+            tm = ix.last_timings()
+            kernel_ms.append(tm["search_ms"]); prep_ms.append(tm["prep_ms"])
+        ev1.record()
+        barrier()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    retries = st["overflow_retries"]
+    value = world * args.nq * args.steps / (dev_ms / 1e3)
+
+    # -- e2e: the public host-buffer call (pinned host memory in, pinned host memory out) ---------------
+    import ctypes as C  # noqa: F401
+
+    def e2e_step():
+        rc = lib.cphnsw_b200_search_batch(h, q_pin.data_ptr(), args.nq, args.k, ids_pin.data_ptr(), dist_pin.data_ptr())
+        if rc:
+            raise RuntimeError(lib.cphnsw_b200_last_error(h).decode())
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * args.nq * args.steps / e2e_s
+    assert np.array_equal(ids_pin.numpy(), ids_dev.cpu().numpy()), "host-buffer and device-buffer paths disagree"
+
+    # -- roofline of the dominant kernel (K3 search): algorithmic bytes / its own event-timed duration -----
+    D, B = info["D"], info["bits"]
+    block_bytes = 4 * D * B + 32 * 12 + 32 * 2 * (2 if B > 1 else 1) + 32 * 4 + 4
+    vec_bytes = 4 * D + 4
+    ref_exact_calls = st["nn_pushes"] + args.nq        # every exact_l2 of the reference feeds nn.push, plus the entry point
+    algo_bytes = st["expansions"] * block_bytes + ref_exact_calls * vec_bytes
+    k_ms = float(np.mean(kernel_ms))
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = algo_bytes / (k_ms / 1e3) / 1e9
+    traffic = None
+    tfile = ROOT / "profiles" / "search_kernel_traffic.json"
+    if tfile.exists():
+        try:
+            traffic = json.loads(tfile.read_text()).get("dram_bytes_per_launch")
+        except ValueError:
+            pass
+    roofline = {"bound": "hbm", "kernel": f"search_kernel<{B}> (K3: descent + beam search + fused exact-L2 rerank)", "achieved": achieved, "peak": peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s", "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": k_ms, "prep_kernel_ms": float(np.mean(prep_ms)),
+                "expansions_per_query": st["expansions"] / args.nq, "bytes_per_expansion": block_bytes + vec_bytes}
+
+    line = {"metric": metric, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 popcount sums + f32", "data": "synthetic",
+            "config": {"workload": workload, "index_source": src, "index_file": index_name(args), "parallelism": f"query-sharded x{world}, index replicated",
+                       "l2": f"no flush needed: random reads over a {info['device_bytes'] / 2**30:.1f} GiB index (>> 126 MB L2)",
+                       "overflow_reruns_last_step": retries},
+            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": args.nq * args.dim * 4, "d2h_bytes_per_step": args.nq * args.k * 12,
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": (2 + (1 if retries else 0)) * args.steps, "roofline": roofline, "clocks": clocks.summary(),
+            "search_stats_per_query": {k: v / args.nq for k, v in st.items() if k not in ("max_beam", "overflow_retries")} | {"max_beam": st["max_beam"]}}
+
+    if rank == 0:
+        ids_np = ids_dev.cpu().numpy()
+        if not args.no_recall:
+            gt = ground_truth(path, q, args.k, torch.device("cuda", local))
+            line["recall_at_10"] = recall_at_k(ids_np, gt)
+            line["unique_ids_per_row"] = float(np.mean([len(set(r.tolist())) for r in ids_np]))
+        if world == 1 and not args.no_cpu_baseline:
+            r = time_reference(args, path, q, budget_s=args.cpu_budget, steps=1, warmup=0)
+            if r is not None:
+                line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                same = np.array_equal(np.sort(r["ids"], 1), np.sort(ids_np[:r["m"]], 1))
+                line["cpu_baseline"]["ids_identical_to_gpu"] = bool(same)
+                if not args.no_recall:
+                    line["cpu_baseline"]["recall_at_10"] = recall_at_k(r["ids"], gt[:r["m"]])
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

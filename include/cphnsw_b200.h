@@ -105,6 +105,10 @@ int cphnsw_b200_search_batch_device(cphnsw_b200_index* ix, const float* d_querie
                                     uint64_t k, int64_t* d_ids, float* d_dists, void* stream);
 /* Counters of the last search_batch* call (synchronises). */
 int cphnsw_b200_last_stats(cphnsw_b200_index* ix, cphnsw_b200_stats* out);
+/* Device time of the kernels of the last search_batch* call, from CUDA events on the launching
+ * stream: K1 (query preparation) and K3 (descent + beam search + rerank; summed over the re-run
+ * if a frontier overflowed). */
+int cphnsw_b200_last_timings(cphnsw_b200_index* ix, float* prep_ms, float* search_ms);
 /* Tuning knobs that do not change results: warps in flight and frontier arena size. */
 int cphnsw_b200_set_option(cphnsw_b200_index* ix, const char* name, int64_t value);
 

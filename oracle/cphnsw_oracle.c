@@ -218,6 +218,18 @@ static inline float scalar_ip_est(float A, float Bc, float C, float fs, float pc
     return fmaf(t, a, b);
 }
 
+/* The plane-0 (lower-bound) chain inside the N-bit scalar tail (:339-342) is contracted the other way
+ * round by the same compiler: t = B*pc; t = fma(A,fs,t); t += C  (pinned by oracle/probe_contraction.c). */
+static inline float scalar_ip_est_msbtail(float A, float Bc, float C, float fs, float pc, float ipcp,
+                                          float q, float a, float b) {
+    float t = Bc * pc;
+    t = fmaf(A, fs, t);
+    t = t + C;
+    t = t - ipcp;
+    t = t / q;
+    return fmaf(t, a, b);
+}
+
 static inline float scalar_lower(float e, float slack, float sqrt_dqp, float nop, float dqp) {
     float cu = (e + slack) / sqrt_dqp;
     if (cu < -1.0f) cu = -1.0f;
@@ -294,7 +306,7 @@ void cpo_convert_nbit(uint32_t B, const float p[7], const uint32_t* nbit, const 
         float d = fmaf(-(nop[i] + nop[i]), e, fmaf(nop[i], nop[i], dqp));
         est[i] = d < 0.0f ? 0.0f : d;
         if (!(q > 1e-10f)) { lower[i] = 0.0f; continue; }
-        float em = scalar_ip_est(A_m, B_m, C, (float)msb[i], (float)pop[i], ip_cp[i], q, a, b);
+        float em = scalar_ip_est_msbtail(A_m, B_m, C, (float)msb[i], (float)pop[i], ip_cp[i], q, a, b);
         lower[i] = scalar_lower(em, slack, sqrt_dqp, nop[i], dqp);
     }
 }

@@ -59,6 +59,7 @@ SYMBOLS = {
     "cphnsw_b200_search_batch": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P, _P]),
     "cphnsw_b200_search_batch_device": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P, _P, _P]),
     "cphnsw_b200_last_stats": (C.c_int, [_P, C.POINTER(Stats)]),
+    "cphnsw_b200_last_timings": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "cphnsw_b200_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "cphnsw_b200_prepare_queries": (C.c_int, [_P, _P, C.c_uint64, C.c_int, _P, _P, _P, _P, _P]),
     "cphnsw_b200_fastscan_blocks": (C.c_int, [_P, _P, _P, C.c_uint64, _P, _P, C.c_uint64, C.c_uint64, _P, _P,

@@ -225,5 +225,11 @@ class CPIndex:
         _capi.check(self._h, self._lib.cphnsw_b200_last_stats(self._h, C.byref(st)))
         return st.as_dict()
 
+    def last_timings(self) -> dict:
+        """Device milliseconds of the last search's kernels (CUDA events on the launching stream)."""
+        a, b = C.c_float(0), C.c_float(0)
+        _capi.check(self._h, self._lib.cphnsw_b200_last_timings(self._h, C.byref(a), C.byref(b)))
+        return {"prep_ms": a.value, "search_ms": b.value}
+
     def set_option(self, name: str, value: int) -> None:
         _capi.check(self._h, self._lib.cphnsw_b200_set_option(self._h, name.encode(), int(value)))

@@ -154,7 +154,8 @@ int cphnsw_b200_create(int device, cphnsw_b200_index** out) {
     ix->num_sms = prop.multiProcessorCount;
     if (cudaMalloc(reinterpret_cast<void**>(&ix->d_stats), sizeof(Stats)) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&ix->d_counters), 16) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        [&] { for (auto& e : ix->ev) if (cudaEventCreate(&e) != cudaSuccess) return true; return false; }()) {
         delete ix;
         return fail(nullptr, CPHNSW_B200_ECUDA, "could not allocate control buffers");
     }
@@ -173,6 +174,7 @@ void cphnsw_b200_destroy(cphnsw_b200_index* ix) {
     if (ix->d_stats) cudaFree(ix->d_stats);
     if (ix->d_counters) cudaFree(ix->d_counters);
     if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
+    for (auto& e : ix->ev) if (e) cudaEventDestroy(e);
     delete ix;
 }
 
@@ -183,6 +185,7 @@ int cphnsw_b200_set_option(cphnsw_b200_index* ix, const char* name, int64_t valu
     const std::string n(name);
     if (n == "warps_per_cta") { if (value < 1 || value > 8) return fail(ix, CPHNSW_B200_EINVAL, "warps_per_cta must be 1..8"); ix->warps_per_cta = value; }
     else if (n == "ctas_per_sm") { if (value < 1 || value > 32) return fail(ix, CPHNSW_B200_EINVAL, "ctas_per_sm must be 1..32"); ix->ctas_per_sm = value; }
+    else if (n == "collect_stats") ix->collect_stats = value ? 1 : 0;
     else if (n == "beam_capacity") { if (value < 64) return fail(ix, CPHNSW_B200_EINVAL, "beam_capacity must be >= 64"); ix->beam_capacity = value; }
     else return fail(ix, CPHNSW_B200_EINVAL, "unknown option " + n);
     return 0;
@@ -277,6 +280,7 @@ int cphnsw_b200_upload(cphnsw_b200_index* ix, const cphnsw_b200_host_index* h) {
 
     // records and raw vectors: copy as they are, re-lay out on the device
     ix->dev = d;
+    CUDA_TRY(ix, cudaMemset(ix->d_counters, 0, 16));
     const size_t chunk_bytes = (size_t)256 << 20;
     void* stage = nullptr;
     CUDA_TRY(ix, cudaMalloc(&stage, chunk_bytes));
@@ -286,7 +290,7 @@ int cphnsw_b200_upload(cphnsw_b200_index* ix, const cphnsw_b200_host_index* h) {
         for (uint64_t first = 0; first < d.n; first += per) {
             const uint32_t cnt = (uint32_t)std::min<uint64_t>(per, d.n - first);
             cudaError_t e = cudaMemcpy(stage, h->search_data + first * h->rec_size, (size_t)cnt * h->rec_size, cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) e = launch_relayout_blocks(d, static_cast<const uint8_t*>(stage), h->rec_size, h->nb_off, first, cnt, 0);
+            if (e == cudaSuccess) e = launch_relayout_blocks(d, static_cast<const uint8_t*>(stage), h->rec_size, h->nb_off, first, cnt, ix->d_counters + 2, 0);
             if (e == cudaSuccess) e = cudaDeviceSynchronize();
             if (e != cudaSuccess) return cleanup(fail(ix, CPHNSW_B200_ECUDA, std::string("re-layout of neighbour blocks: ") + cudaGetErrorString(e)));
         }
@@ -300,6 +304,10 @@ int cphnsw_b200_upload(cphnsw_b200_index* ix, const cphnsw_b200_host_index* h) {
         }
     }
     cudaFree(stage);
+    uint32_t problems[4] = {0, 0, 0, 0};
+    CUDA_TRY(ix, cudaMemcpy(problems, ix->d_counters, 16, cudaMemcpyDeviceToHost));
+    if (problems[3]) { release_index(ix); return fail(ix, CPHNSW_B200_ERUNTIME, "Index is corrupt: neighbour id out of range in " + std::to_string(problems[3]) + " blocks."); }
+    ix->dev.dup_neighbors = problems[2];
     ix->loaded = true;
     return 0;
 }
@@ -407,13 +415,22 @@ static int run_search(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq
     if (rc) return rc;
     PrepOut po{};
     po.coeffs = qs.coeffs; po.uplanes = qs.uplanes; po.qT = qs.qT;
+    CUDA_TRY(ix, cudaEventRecord(ix->ev[0], stream));
     CUDA_TRY(ix, launch_query_prep(d, d_queries, (uint32_t)nq, 0, po, stream));
+    CUDA_TRY(ix, cudaEventRecord(ix->ev[1], stream));
 
-    // launch geometry: persistent grid, one warp per in-flight query
+    // launch geometry: persistent grid, one warp per in-flight query; as much of the frontier heap in
+    // shared memory as still lets the requested number of warps reside
+    const bool stats = ix->collect_stats != 0;
     int warps = (int)ix->warps_per_cta;
-    const size_t smem_warp = search_smem_per_warp(d, k);
-    while (warps > 1 && smem_warp * warps > 200 * 1024) --warps;
-    int ctas = ix->num_sms * (int)ix->ctas_per_sm;
+    uint32_t heap_cache = 255;
+    const size_t smem_budget = 220 * 1024;
+    if (search_smem_per_warp(d, k, heap_cache) * warps * (size_t)ix->ctas_per_sm > smem_budget) heap_cache = 63;
+    while (warps > 1 && search_smem_per_warp(d, k, heap_cache) * warps > smem_budget) --warps;
+    int per_sm = search_max_ctas_per_sm(d, k, heap_cache, warps, stats);
+    if (per_sm <= 0) return fail(ix, CPHNSW_B200_ECUDA, "search kernel cannot be resident (shared memory / registers)");
+    per_sm = std::min<int>(per_sm, (int)ix->ctas_per_sm);
+    int ctas = ix->num_sms * per_sm;
     const int need = (int)((nq + warps - 1) / warps);
     if (ctas > need) ctas = need;
 
@@ -424,10 +441,11 @@ static int run_search(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq
         a.chunk_words = chunk;
         a.bitmap_words = chunk * 256;
         size_t off = 0;
-        a.heap_off = off; off += ((size_t)(cap + 1) * 16 + 127) & ~(size_t)127;
+        a.heap_off = off; off += ((size_t)(cap + 2) * 12 + 127) & ~(size_t)127;
         a.nn_off = off; if (k > 128) off += ((size_t)k * 8 + 127) & ~(size_t)127;
         a.slot_stride = off;
         a.beam_capacity = cap;
+        a.heap_cache = heap_cache;
     };
 
     SearchArgs a{};
@@ -449,7 +467,9 @@ static int run_search(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq
     a.stats = ix->d_stats;
     CUDA_TRY(ix, cudaMemsetAsync(ix->d_counters, 0, 16, stream));
     CUDA_TRY(ix, cudaMemsetAsync(ix->d_stats, 0, sizeof(Stats), stream));
-    CUDA_TRY(ix, launch_search(d, a, ctas, warps, stream));
+    CUDA_TRY(ix, cudaEventRecord(ix->ev[2], stream));
+    CUDA_TRY(ix, launch_search(d, a, ctas, warps, stats, stream));
+    CUDA_TRY(ix, cudaEventRecord(ix->ev[3], stream));
 
     // frontier overflow: re-run those queries with an arena that cannot overflow (each id enters
     // the frontier at most once, so n entries always suffice)
@@ -457,6 +477,8 @@ static int run_search(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq
     CUDA_TRY(ix, cudaMemcpyAsync(counters, ix->d_counters, 16, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(ix, cudaStreamSynchronize(stream));
     ix->last_stats.overflow_retries = 0;
+    cudaEventElapsedTime(&ix->prep_ms, ix->ev[0], ix->ev[1]);
+    cudaEventElapsedTime(&ix->search_ms, ix->ev[2], ix->ev[3]);
     if (counters[1] > 0) {
         const uint32_t nover = counters[1];
         std::vector<uint32_t> list(nover);
@@ -482,13 +504,18 @@ static int run_search(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq
         cudaMemcpy(d_list, list.data(), (size_t)nover * 4, cudaMemcpyHostToDevice);
         b.query_list = d_list; b.nq = nover;
         cudaMemsetAsync(ix->d_counters, 0, 16, stream);
-        cudaError_t e = launch_search(d, b, rctas, rwarps, stream);
+        cudaEventRecord(ix->ev[4], stream);
+        cudaError_t e = launch_search(d, b, rctas, rwarps, stats, stream);
+        cudaEventRecord(ix->ev[5], stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(counters, ix->d_counters, 16, cudaMemcpyDeviceToHost, stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
         cudaFree(d_list);
         if (e != cudaSuccess) return fail(ix, CPHNSW_B200_ECUDA, std::string("overflow re-run: ") + cudaGetErrorString(e));
         if (counters[1] != 0) return fail(ix, CPHNSW_B200_ERUNTIME, "internal error: frontier overflow with a full-size arena");
         ix->last_stats.overflow_retries = nover;
+        float rerun_ms = 0.0f;
+        cudaEventElapsedTime(&rerun_ms, ix->ev[4], ix->ev[5]);
+        ix->search_ms += rerun_ms;
     }
     return 0;
 }
@@ -525,6 +552,13 @@ int cphnsw_b200_search_batch(cphnsw_b200_index* ix, const float* queries, uint64
         CUDA_TRY(ix, cudaMemcpyAsync(dists, d_d, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
     }
     CUDA_TRY(ix, cudaStreamSynchronize(st));
+    return 0;
+}
+
+int cphnsw_b200_last_timings(cphnsw_b200_index* ix, float* prep_ms, float* search_ms) {
+    if (!ix) return CPHNSW_B200_EINVAL;
+    if (prep_ms) *prep_ms = ix->prep_ms;
+    if (search_ms) *search_ms = ix->search_ms;
     return 0;
 }
 

@@ -53,6 +53,7 @@ struct DevIndex {
     uint64_t n;
     const uint8_t* blocks;
     uint32_t block_stride, aux_off;
+    uint32_t dup_neighbors;  // != 0: some block lists a neighbour id twice (never seen from the reference's builder)
     // raw vectors, accumulator-major: rawT[id][l*T + t] = raw[id][8t + l]  (l = 0..7)
     const float* rawT;
     const float* norm_sq;
@@ -98,6 +99,7 @@ struct cphnsw_b200_index {
     int64_t warps_per_cta = 8;
     int64_t ctas_per_sm = 4;
     int64_t beam_capacity = 1 << 15;  // frontier entries per in-flight query (first attempt)
+    int64_t collect_stats = 0;        // per-batch counters (costs registers: off on the fast path)
     // scratch, grown on demand
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -113,4 +115,6 @@ struct cphnsw_b200_index {
     uint32_t* d_counters = nullptr;  // [0] work counter, [1] overflow count
     cphnsw_b200_stats last_stats{};
     cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev[6] = {};  // prep begin/end, search begin/end, re-run begin/end
+    float prep_ms = 0.0f, search_ms = 0.0f;
 };

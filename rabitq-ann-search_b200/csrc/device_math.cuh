@@ -111,6 +111,18 @@ __device__ __forceinline__ float scalar_ip_est(float A, float Bc, float C, float
     return __fmaf_rn(t, a, b);
 }
 
+// ...except the plane-0 chain inside the N-bit scalar tail (:339-342), which the same compiler
+// contracts the other way round: t = B*pc; t = fma(A,fs,t); t += C  (pinned by oracle/probe_contraction.c)
+__device__ __forceinline__ float scalar_ip_est_msbtail(float A, float Bc, float C, float fs, float pc, float ipcp,
+                                                       float q, float a, float b) {
+    float t = __fmul_rn(Bc, pc);
+    t = __fmaf_rn(A, fs, t);
+    t = __fadd_rn(t, C);
+    t = __fsub_rn(t, ipcp);
+    t = __fdiv_rn(t, q);
+    return __fmaf_rn(t, a, b);
+}
+
 __device__ __forceinline__ float scalar_lower(float e, float slack, float sqrt_dqp, float nop, float dqp) {
     float cu = __fdiv_rn(__fadd_rn(e, slack), sqrt_dqp);
     if (cu < -1.0f) cu = -1.0f;
@@ -131,7 +143,7 @@ __device__ __forceinline__ void lane_scalar(float A_e, float B_e, float fs_e, fl
     const float d = __fmaf_rn(-__fadd_rn(nop, nop), e, __fmaf_rn(nop, nop, dqp));
     est = d < 0.0f ? 0.0f : d;
     if (!good) { lower = 0.0f; return; }
-    const float el = same ? e : scalar_ip_est(A_l, B_l, p.C, fs_l, pc_l, ipcp, q, p.a, p.b);
+    const float el = same ? e : scalar_ip_est_msbtail(A_l, B_l, p.C, fs_l, pc_l, ipcp, q, p.a, p.b);
     lower = scalar_lower(el, p.slack, sqrt_dqp, nop, dqp);
 }
 

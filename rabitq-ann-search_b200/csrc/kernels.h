@@ -50,6 +50,7 @@ struct SearchArgs {
     size_t slot_stride;        // bytes per slot
     size_t heap_off, nn_off;   // inside a slot
     uint32_t beam_capacity;    // frontier entries per slot
+    uint32_t heap_cache;       // frontier entries kept in shared memory (63 or 255: whole tree levels)
     uint32_t* bitmaps;         // per-slot "estimated" bitmaps: all-zero between queries
     uint32_t bitmap_words, chunk_words;
     uint32_t* counters;        // [0] work counter, [1] number of overflowed queries
@@ -57,17 +58,19 @@ struct SearchArgs {
     Stats* stats;              // may be NULL
     uint32_t* entry_out;       // descent-only mode: layer-0 entry point per query (else NULL)
 };
-struct SearchLaunch { int ctas, warps_per_cta; size_t smem_per_cta; };
-size_t search_smem_per_warp(const DevIndex& ix, uint32_t k);
-cudaError_t launch_search(const DevIndex& ix, const SearchArgs& a, int ctas, int warps_per_cta, cudaStream_t stream);
+size_t search_smem_per_warp(const DevIndex& ix, uint32_t k, uint32_t heap_cache);
+int search_max_ctas_per_sm(const DevIndex& ix, uint32_t k, uint32_t heap_cache, int warps_per_cta, bool stats);
+cudaError_t launch_search(const DevIndex& ix, const SearchArgs& a, int ctas, int warps_per_cta, bool stats,
+                          cudaStream_t stream);
 
 // ---- K4 primitive: exact distances of listed ids (search.cu) ----------------------------------
 cudaError_t launch_exact_l2(const DevIndex& ix, const float* qT, const float* coeffs, uint32_t nq,
                             const uint32_t* ids, uint32_t m, float* out, cudaStream_t stream);
 
 // ---- index re-layout (relayout.cu) -------------------------------------------------------------
+// d_problems[0] += blocks holding one neighbour id twice, d_problems[1] += blocks with an id >= n
 cudaError_t launch_relayout_blocks(const DevIndex& ix, const uint8_t* d_records, uint64_t rec_size, uint32_t nb_off,
-                                   uint64_t first, uint32_t count, cudaStream_t stream);
+                                   uint64_t first, uint32_t count, uint32_t* d_problems, cudaStream_t stream);
 cudaError_t launch_relayout_raw(const DevIndex& ix, const float* d_raw, uint64_t first, uint32_t count,
                                 cudaStream_t stream);
 

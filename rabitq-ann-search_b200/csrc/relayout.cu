@@ -14,7 +14,7 @@ namespace cpb {
 // one CTA (128 threads) per vertex
 __global__ void __launch_bounds__(128) relayout_blocks_kernel(const DevIndex ix, const uint8_t* __restrict__ rec,
                                                               uint64_t rec_size, uint32_t nb_off, uint64_t first,
-                                                              uint32_t count) {
+                                                              uint32_t count, uint32_t* __restrict__ problems) {
     const uint32_t v = blockIdx.x;
     if (v >= count) return;
     const uint32_t D = ix.D, B = ix.B, nch = ix.nch;
@@ -45,7 +45,15 @@ __global__ void __launch_bounds__(128) relayout_blocks_kernel(const DevIndex ix,
         const uint32_t pop = reinterpret_cast<const uint16_t*>(s_pop)[l];
         const uint32_t wpop = nbit ? reinterpret_cast<const uint16_t*>(s_wpop)[l] : 0u;
         reinterpret_cast<uint32_t*>(aux + 512)[l] = pop | (wpop << 16);
-        if (l == 0) reinterpret_cast<uint32_t*>(aux + 640)[0] = reinterpret_cast<const uint32_t*>(s_ids + 128)[0];
+        const uint32_t cnt = reinterpret_cast<const uint32_t*>(s_ids + 128)[0];
+        if (l == 0) reinterpret_cast<uint32_t*>(aux + 640)[0] = cnt < 32 ? cnt : 32;
+        // sanity of the graph: ids in range, and whether any id repeats inside the block
+        const uint32_t id = reinterpret_cast<const uint32_t*>(s_ids)[l];
+        const bool valid = l < cnt;
+        const unsigned peers = __match_any_sync(kFull, valid ? id : (kInvalid - l));
+        const bool dup = __any_sync(kFull, valid && (peers & (peers - 1)) != 0);
+        const bool oob = __any_sync(kFull, valid && id >= ix.n);
+        if (l == 0) { if (dup) atomicAdd(problems, 1u); if (oob) atomicAdd(problems + 1, 1u); }
     }
     // per-vertex 1-bit code (RaBitQCode<D>: signs @0, nop, ip_qo after the 64-B aligned sign words)
     if (B == 1 && ix.flat_codes && threadIdx.x >= 32 && threadIdx.x < 64) {
@@ -83,9 +91,9 @@ __global__ void relayout_raw_kernel(const DevIndex ix, const float* __restrict__
 }
 
 cudaError_t launch_relayout_blocks(const DevIndex& ix, const uint8_t* d_records, uint64_t rec_size, uint32_t nb_off,
-                                   uint64_t first, uint32_t count, cudaStream_t stream) {
+                                   uint64_t first, uint32_t count, uint32_t* d_problems, cudaStream_t stream) {
     if (count == 0) return cudaSuccess;
-    relayout_blocks_kernel<<<count, 128, 0, stream>>>(ix, d_records, rec_size, nb_off, first, count);
+    relayout_blocks_kernel<<<count, 128, 0, stream>>>(ix, d_records, rec_size, nb_off, first, count, d_problems);
     return cudaGetLastError();
 }
 

@@ -10,16 +10,28 @@
 // atomic counter because work per query varies by 100x.  Inside a query the reference loop is
 // strictly sequential (every decision reads the live k-th distance), so the parallel axes are:
 // lane = neighbour slot for the 32-code FastScan block and its epilogue, 4 groups x 8 lanes =
-// 4 exact distances at a time in the reference's 8-accumulator order, and thousands of queries
-// in flight to cover HBM latency.
+// 4 exact distances at a time in the reference's 8-accumulator order, lane = tree node for the
+// frontier heap, and thousands of queries in flight to cover HBM latency.
 //
-// Per-warp state: query (accumulator-major), query bit-planes, result list and the top of the
-// frontier heap live in shared memory; the rest of the frontier heap and the "estimated" bitmap
-// live in a per-slot HBM arena.  The frontier is the reference's binary heap, restated move for
-// move (libstdc++ __push_heap/__adjust_heap) because equal estimates are common in large
-// frontiers and their pop order decides the traversal.  The "visited" set of the reference is
-// elided: an id enters the frontier only right after its first "estimated" mark, hence at most
-// once, so is_visited() can never be true.
+// Per-warp state: query (accumulator-major), query bit-planes, result list and the top levels of
+// the frontier heap live in shared memory; the rest of the frontier and the "estimated" bitmap
+// live in a per-slot HBM arena.
+//
+// Frontier.  The reference's frontier is std::priority_queue, i.e. libstdc++'s binary heap;
+// equal estimates are common in large frontiers (a frontier of 10^4 floats in [200,300] has a few
+// colliding pairs) and their pop order steers the traversal, so the heap is kept node for node
+// identical to what __push_heap/__adjust_heap would build -- but executed by the whole warp:
+//   push: the ancestors of the new leaf are an arithmetic sequence; lane l loads ancestor l, one
+//         ballot finds how far the new entry rises, the displaced ancestors move down in parallel.
+//   pop : __adjust_heap walks to a leaf always taking the child its comparator prefers (right,
+//         unless right > left) and then sifts the former last entry v back up.  On a valid heap
+//         the keys along that walk are non-decreasing, so v ends exactly below the last walk node
+//         whose key is <= v's, and everything deeper returns to where it was.  Hence: descend only
+//         while key(preferred child) <= key(v).  The walk is done five levels per step: the 31
+//         sibling pairs under the hole are loaded one per lane, two ballots (which sibling, does it
+//         still move) give every lane the whole 5-level path, and the moves happen in parallel.
+// The "visited" set of the reference is elided: an id enters the frontier only right after its
+// first "estimated" mark, hence at most once, so is_visited() can never be true.
 #include <float.h>
 
 #include "device_math.cuh"
@@ -27,12 +39,12 @@
 
 namespace cpb {
 
-constexpr uint32_t kHeapCache = 64;   // frontier entries [0, kHeapCache) live in shared memory
-constexpr uint32_t kNNSmem = 128;     // result lists up to this k live in shared memory
+constexpr uint32_t kNNSmem = 128;  // result lists up to this k live in shared memory
 
-__host__ __device__ inline size_t smem_per_warp(uint32_t T, uint32_t nch, uint32_t k) {
-    size_t s = (size_t)8 * (T + 4) * 4 + (size_t)nch * 64 + (size_t)kHeapCache * 16 + 32;
-    if (k <= kNNSmem) s += (size_t)kNNSmem * 8;
+__host__ __device__ inline uint32_t nn_smem_entries(uint32_t k) { return k <= kNNSmem ? ((k + 31u) & ~31u) : 0u; }
+
+__host__ __device__ inline size_t smem_per_warp(uint32_t T, uint32_t nch, uint32_t k, uint32_t hc) {
+    size_t s = (size_t)8 * (T + 4) * 4 + (size_t)nch * 64 + (size_t)(hc + 1) * 12 + 32 + (size_t)nn_smem_entries(k) * 8;
     return (s + 15) & ~(size_t)15;
 }
 
@@ -40,55 +52,91 @@ struct WarpCtx {
     // shared memory
     float* qrow;      // this lane's accumulator row of the query
     const uint4* uq;  // query bit-planes
-    uint4* hs;        // frontier cache
+    float* ks;        // frontier keys   [0, hc)
+    uint2* ps;        // frontier payload {lower bound bits, id}
     uint32_t* dirty;  // 256-bit summary of touched bitmap chunks
     // arena
-    uint4* hg;        // frontier, physical index = logical + 1 (children share a 32-B sector)
+    float* kg;        // frontier keys, physical index = logical + 1 (sibling pairs 8-B aligned)
+    uint2* pg;
     uint32_t* bitmap;
     float* nn_d;
     uint32_t* nn_i;
-    uint32_t lane;
+    uint32_t lane, hc;
 };
 
-__device__ __forceinline__ uint4 hget(const WarpCtx& w, uint32_t i) { return i < kHeapCache ? w.hs[i] : w.hg[i + 1]; }
-__device__ __forceinline__ void hset(const WarpCtx& w, uint32_t i, const uint4& e) {
-    if (i < kHeapCache) w.hs[i] = e; else w.hg[i + 1] = e;
-}
-__device__ __forceinline__ float key(const uint4& e) { return __uint_as_float(e.x); }
-
-// std::__push_heap with comp(a,b) = a.est > b.est (min-heap on the estimate)
-__device__ __forceinline__ void heap_sift_up(const WarpCtx& w, uint32_t hole, const uint4& v) {
-    const float vk = key(v);
-    while (hole > 0) {
-        const uint32_t parent = (hole - 1) >> 1;
-        const uint4 pe = hget(w, parent);
-        if (!(key(pe) > vk)) break;
-        hset(w, hole, pe);
-        hole = parent;
-    }
-    hset(w, hole, v);
+__device__ __forceinline__ float kget(const WarpCtx& w, uint32_t i) { return i < w.hc ? w.ks[i] : w.kg[i + 1]; }
+__device__ __forceinline__ uint2 pget(const WarpCtx& w, uint32_t i) { return i < w.hc ? w.ps[i] : w.pg[i + 1]; }
+__device__ __forceinline__ void eset(const WarpCtx& w, uint32_t i, float key, uint2 pay) {
+    if (i < w.hc) { w.ks[i] = key; w.ps[i] = pay; } else { w.kg[i + 1] = key; w.pg[i + 1] = pay; }
 }
 
-// std::pop_heap + pop_back on a heap of n entries (lane 0 only)
+// std::push_heap of (vk, vp) onto a heap of n entries, comp(a,b) = a.est > b.est.  Warp-cooperative.
+__device__ __forceinline__ void heap_push(const WarpCtx& w, uint32_t n, float vk, uint2 vp) {
+    const uint32_t m = n + 1;                      // 1-based index of the new leaf
+    const uint32_t depth = 31u - __clz(m);         // number of ancestors
+    const uint32_t l = w.lane;
+    const uint32_t anc = l < depth ? (m >> (l + 1)) - 1 : 0u;   // ancestor l (l = 0: parent)
+    float ka = 0.0f;
+    if (l < depth) ka = kget(w, anc);
+    const unsigned up = __ballot_sync(kFull, l < depth && ka > vk);
+    const uint32_t cnt = __ffs(~up) - 1;           // the new entry passes ancestors 0 .. cnt-1
+    uint2 pa = make_uint2(0, 0);
+    if (l < cnt) pa = pget(w, anc);
+    __syncwarp();
+    if (l < cnt) eset(w, (m >> l) - 1, ka, pa);    // ancestor l moves to where ancestor l-1 (or the leaf) was
+    if (l == cnt) eset(w, (m >> cnt) - 1, vk, vp);
+    __syncwarp();
+}
+
+// std::pop_heap + pop_back on a heap of n >= 1 entries.  Warp-cooperative.
 __device__ __forceinline__ void heap_pop(const WarpCtx& w, uint32_t n) {
     if (n <= 1) return;
-    const uint4 v = hget(w, n - 1);
-    const int len = (int)n - 1;
-    int hole = 0, child = 0;
-    while (child < (len - 1) / 2) {
-        child = 2 * (child + 1);
-        uint4 r = hget(w, child);
-        const uint4 l = hget(w, child - 1);
-        if (key(r) > key(l)) { child--; r = l; }
-        hset(w, hole, r);
-        hole = child;
+    const uint32_t len = n - 1;                    // entries 0 .. len-1 remain, the hole starts at the root
+    const float vk = kget(w, len);
+    const uint2 vp = pget(w, len);
+    const uint32_t L = w.lane;
+    const uint32_t d = 32u - __clz(L + 1);         // lane L holds sibling pair j of level d below the hole (L < 31)
+    const uint32_t j = L + 1 - (1u << (d - 1));
+    uint32_t hole = 0;
+    for (;;) {
+        const uint64_t left64 = (((uint64_t)hole + 1) << d) - 1 + 2 * j;
+        const uint32_t left = (uint32_t)left64;
+        const bool hl = L < 31 && left64 < len, hr = L < 31 && left64 + 1 < len;
+        const float kl = hl ? kget(w, left) : 0.0f, kr = hr ? kget(w, left + 1) : 0.0f;
+        const bool right = hr && !(kr > kl);       // __adjust_heap: the right child unless right > left
+        const float ck = right ? kr : kl;
+        const unsigned rmask = __ballot_sync(kFull, right);
+        const unsigned omask = __ballot_sync(kFull, hl && ck <= vk);   // this pair's preferred child moves up
+        // every lane walks the (at most) five levels
+        uint32_t node[6];
+        node[0] = hole;
+        uint32_t jj = 0, moves = 0;
+#pragma unroll
+        for (uint32_t lv = 1; lv <= 5; ++lv) {
+            const uint32_t pl = (1u << (lv - 1)) - 1 + jj;
+            const bool go = moves == lv - 1 && ((omask >> pl) & 1u);
+            const uint32_t r = (rmask >> pl) & 1u;
+            node[lv] = ((hole + 1) << lv) - 1 + 2 * jj + r;
+            if (go) { moves = lv; jj = 2 * jj + r; }
+        }
+        // lane t < moves moves node[t+1] into node[t]
+        uint32_t src = 0, dst = 0;
+#pragma unroll
+        for (uint32_t t = 0; t < 5; ++t) if (L == t) { dst = node[t]; src = node[t + 1]; }
+        float mk = 0.0f;
+        uint2 mp = make_uint2(0, 0);
+        if (L < moves) { mk = kget(w, src); mp = pget(w, src); }
+        __syncwarp();
+        if (L < moves) eset(w, dst, mk, mp);
+        uint32_t nh = hole;
+#pragma unroll
+        for (uint32_t t = 1; t <= 5; ++t) if (moves == t) nh = node[t];
+        hole = nh;
+        if (moves < 5) break;
+        __syncwarp();
     }
-    if ((len & 1) == 0 && child == (len - 2) / 2) {
-        child = 2 * (child + 1);
-        hset(w, hole, hget(w, child - 1));
-        hole = child - 1;
-    }
-    heap_sift_up(w, (uint32_t)hole, v);
+    if (L == 0) eset(w, hole, vk, vp);
+    __syncwarp();
 }
 
 // BoundedMaxHeap::push (search/rabitq_search.hpp:26-35) on an ascending list: accept while not
@@ -104,7 +152,7 @@ __device__ __forceinline__ void nn_push(const WarpCtx& w, uint32_t& m, uint32_t 
         const bool have0 = i < m, havem = i >= 1 && (i - 1) < m;
         if (have0) d0 = w.nn_d[i];
         if (havem) { dm = w.nn_d[i - 1]; im = w.nn_i[i - 1]; }
-        const bool le0 = have0 && d0 <= dist;            // old[i] stays in place
+        const bool le0 = have0 && d0 <= dist;              // old[i] stays in place
         const bool lem = i == 0 || (havem && dm <= dist);  // old[i-1] stays in place
         __syncwarp();
         if (i < newm && !le0) {
@@ -112,7 +160,7 @@ __device__ __forceinline__ void nn_push(const WarpCtx& w, uint32_t& m, uint32_t 
             else { w.nn_d[i] = dm; w.nn_i[i] = im; }
         }
         __syncwarp();
-        if (__all_sync(kFull, le0 || i >= newm)) break;  // nothing below this chunk moves
+        if (__all_sync(kFull, le0 || i >= newm)) break;         // nothing below this chunk moves
         if (__any_sync(kFull, i < newm && !le0 && lem)) break;  // insertion point passed
     }
     m = newm;
@@ -129,7 +177,7 @@ __device__ __forceinline__ float exact_group(const DevIndex& ix, const WarpCtx& 
 // exact distances of the lanes named in `mask` (each lane's own `nid`), four per round; the
 // result lands in that lane's return value.
 __device__ __forceinline__ float exact_for_lanes(const DevIndex& ix, const WarpCtx& w, unsigned mask, uint32_t nid,
-                                                 float qn, unsigned long long& calls) {
+                                                 float qn) {
     float mine = 0.0f;
     const uint32_t g = w.lane >> 3;
     while (mask) {
@@ -144,13 +192,14 @@ __device__ __forceinline__ float exact_for_lanes(const DevIndex& ix, const WarpC
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float v = __shfl_sync(kFull, d, j * 8);
-            if (src[j] >= 0) { ++calls; if ((int)w.lane == src[j]) mine = v; }
+            if ((int)w.lane == src[j]) mine = v;
         }
     }
     return mine;
 }
 
 // greedy_search_layer over levels max_level..1 (api/hnsw_index.hpp:195-202, 617-638)
+template <bool STATS>
 __device__ __forceinline__ uint32_t greedy_descent(const DevIndex& ix, const WarpCtx& w, unsigned long long& ndist) {
     if (ix.max_level <= 0) return ix.graph_entry_point;
     const uint32_t g = w.lane >> 3, l = w.lane & 7u;
@@ -158,7 +207,7 @@ __device__ __forceinline__ uint32_t greedy_descent(const DevIndex& ix, const War
     for (int L = ix.max_level; L >= 1; --L) {
         const bool have_level = (uint32_t)L <= ix.n_levels;
         float best = group_chain<true>(ix.rawT + (size_t)node * ix.D + (size_t)l * ix.T, w.qrow, ix.T, true);
-        ++ndist;
+        if (STATS) ++ndist;
         uint32_t best_id = node, best_slot = slot;
         bool improved = have_level;
         while (improved) {
@@ -176,7 +225,7 @@ __device__ __forceinline__ uint32_t greedy_descent(const DevIndex& ix, const War
                     const float dt = __shfl_sync(kFull, d, t * 8);
                     const uint32_t nt = __shfl_sync(kFull, nb, t * 8), st = __shfl_sync(kFull, ns, t * 8);
                     if (j + t < e) {
-                        ++ndist;
+                        if (STATS) ++ndist;
                         if (dt < best) { best = dt; best_id = nt; best_slot = st; improved = true; }
                     }
                 }
@@ -188,32 +237,36 @@ __device__ __forceinline__ uint32_t greedy_descent(const DevIndex& ix, const War
     return node;
 }
 
-template <int B>
-__global__ void __launch_bounds__(256, 2) search_kernel(const DevIndex ix, const SearchArgs a) {
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int B, bool STATS>
+__global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const SearchArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const uint32_t D = ix.D, T = ix.T, nch = ix.nch, Tp = T + 4;
     const uint32_t k = a.k;
-    const bool nn_in_smem = k <= kNNSmem;
 
     // ---- carve shared memory -------------------------------------------------------------------
-    const size_t per_warp = smem_per_warp(T, nch, k);
+    const size_t per_warp = smem_per_warp(T, nch, k, a.heap_cache);
     uint8_t* sm = smem_raw + (size_t)warp * per_warp;
     WarpCtx w;
     w.lane = lane;
+    w.hc = a.heap_cache;
     float* qs = reinterpret_cast<float*>(sm);                     sm += (size_t)8 * Tp * 4;
     uint4* uqs = reinterpret_cast<uint4*>(sm);                    sm += (size_t)nch * 64;
-    w.hs = reinterpret_cast<uint4*>(sm);                          sm += (size_t)kHeapCache * 16;
+    w.ps = reinterpret_cast<uint2*>(sm);                          sm += (size_t)(a.heap_cache + 1) * 8;
+    w.ks = reinterpret_cast<float*>(sm);                          sm += (size_t)(a.heap_cache + 1) * 4;
     w.dirty = reinterpret_cast<uint32_t*>(sm);                    sm += 32;
     w.qrow = qs + (size_t)(lane & 7u) * Tp;
     w.uq = uqs;
     const uint32_t slot = blockIdx.x * nwarps + warp;
     uint8_t* arena = a.scratch + (size_t)slot * a.slot_stride;
-    w.hg = reinterpret_cast<uint4*>(arena + a.heap_off);
+    w.pg = reinterpret_cast<uint2*>(arena + a.heap_off);
+    w.kg = reinterpret_cast<float*>(arena + a.heap_off + ((size_t)a.beam_capacity + 2) * 8);
     w.bitmap = a.bitmaps + (size_t)slot * a.bitmap_words;
-    if (nn_in_smem) {
+    if (k <= kNNSmem) {
         w.nn_d = reinterpret_cast<float*>(sm);
-        w.nn_i = reinterpret_cast<uint32_t*>(sm + (size_t)kNNSmem * 4);
+        w.nn_i = reinterpret_cast<uint32_t*>(sm + (size_t)nn_smem_entries(k) * 4);
     } else {
         w.nn_d = reinterpret_cast<float*>(arena + a.nn_off);
         w.nn_i = reinterpret_cast<uint32_t*>(arena + a.nn_off + (size_t)k * 4);
@@ -222,6 +275,7 @@ __global__ void __launch_bounds__(256, 2) search_kernel(const DevIndex ix, const
 
     const Calib& cal = ix.calib;
     Stats st{};
+    const uint32_t block_lines = (ix.aux_off + 644 + 127) >> 7;
 
     for (;;) {
         uint32_t wi = 0;
@@ -245,104 +299,118 @@ __global__ void __launch_bounds__(256, 2) search_kernel(const DevIndex ix, const
         const float qn = cf[3];
         __syncwarp();
 
-        const uint32_t ep = greedy_descent(ix, w, st.descent_dists);
+        const uint32_t ep = greedy_descent<STATS>(ix, w, st.descent_dists);
         if (a.entry_out) { if (lane == 0) a.entry_out[q] = ep; continue; }
 
         // ---- layer-0 search state (search/rabitq_search.hpp:77-97) ----------------------------
         uint32_t heap_n = 0, nn_m = 0;
         float gamma_q = cal.gamma;
         double ratio_sum = 0.0, ratio_sq_sum = 0.0;
-        unsigned long long ratio_count = 0;
+        uint32_t ratio_count = 0;
         int slack_batch_count = 0;
         bool overflow = false;
         uint32_t max_beam = 0;
 
         {
             const float d0 = exact_group(ix, w, ep, true, qn);
-            ++st.exact_calls;
+            if (STATS) { ++st.exact_calls; ++st.beam_pushes; ++st.estimated; }
             if (lane == 0) {
-                w.hs[0] = make_uint4(__float_as_uint(d0), __float_as_uint(0.0f), ep, 0u);
+                w.ks[0] = d0;
+                w.ps[0] = make_uint2(__float_as_uint(0.0f), ep);
                 atomicOr(&w.bitmap[ep >> 5], 1u << (ep & 31));
                 const uint32_t ch = (ep >> 5) / a.chunk_words;
                 w.dirty[ch >> 5] |= 1u << (ch & 31);
             }
-            heap_n = 1; ++st.beam_pushes; ++st.estimated;
+            heap_n = 1;
             __syncwarp();
         }
 
         while (heap_n > 0) {
             // ---- pop (:110-117).  is_visited() can never hit: see file header ---------------------
-            const uint4 top = w.hs[0];
-            const float cur_est = __uint_as_float(top.x), cur_lower = __uint_as_float(top.y);
-            const uint32_t cur = top.z;
-            if (lane == 0) heap_pop(w, heap_n);
-            --heap_n; ++st.pops;
-            __syncwarp();
-
+            const float cur_est = w.ks[0];
+            const uint2 top = w.ps[0];
+            const float cur_lower = __uint_as_float(top.x);
+            const uint32_t cur = top.y;
+            const uint8_t* blk = ix.blocks + (size_t)cur * ix.block_stride;
             const bool full0 = nn_m >= k;
             float worst = full0 ? w.nn_d[k - 1] : FLT_MAX;
-            if (full0 && cur_est >= __fmul_rn(gamma_q, worst)) { ++st.gamma_terms; break; }  // :120
-            if (full0 && cur_lower > worst) { ++st.lb_skips; continue; }                      // :122
+            const bool terminate = full0 && cur_est >= __fmul_rn(gamma_q, worst);   // :120
+            const bool lbskip = full0 && cur_lower > worst;                          // :122
+            if (!terminate && !lbskip) {
+                // start the HBM reads of this expansion before the heap work: block lines and raw vector
+                if (lane < block_lines) prefetch_l2(blk + (size_t)lane * 128);
+                else if (lane - block_lines < (D * 4 + 127) / 128) prefetch_l2(ix.rawT + (size_t)cur * D + (size_t)(lane - block_lines) * 32);
+            }
+            __syncwarp();
+            heap_pop(w, heap_n);
+            --heap_n;
+            if (STATS) ++st.pops;
+            if (terminate) { if (STATS) ++st.gamma_terms; break; }
+            if (lbskip) { if (STATS) ++st.lb_skips; continue; }
 
-            const float exact_dist = exact_group(ix, w, cur, true, qn);   // :130-133
-            ++st.exact_calls;
-            nn_push(w, nn_m, k, cur, exact_dist);
-            ++st.nn_pushes; ++st.expansions;
-
-            const uint8_t* blk = ix.blocks + (size_t)cur * ix.block_stride;
+            // neighbour ids first: their "estimated" probes travel while the distances are computed
             const uint8_t* aux = blk + ix.aux_off;
             const uint32_t count = __ldg(reinterpret_cast<const uint32_t*>(aux + 640));
-            if (count == 0) continue;
+            const uint32_t nid = __ldg(reinterpret_cast<const uint32_t*>(aux) + lane);
+            const bool valid = lane < count;
+            // ---- check_and_mark_estimated for all slots at once (:227); slots are distinct ids unless
+            //      the index says otherwise, then only the first of equal ids may be new
+            bool leader = valid;
+            if (ix.dup_neighbors) {
+                const unsigned peers = __match_any_sync(kFull, valid ? nid : (kInvalid - lane));
+                leader = valid && (uint32_t)(__ffs(peers) - 1) == lane;
+            }
+            uint32_t old = 0xFFFFFFFFu;
+            if (leader) old = atomicOr(&w.bitmap[nid >> 5], 1u << (nid & 31));
+
+            const float exact_dist = exact_group(ix, w, cur, true, qn);   // :130-133
+            nn_push(w, nn_m, k, cur, exact_dist);
+            if (STATS) { ++st.exact_calls; ++st.nn_pushes; ++st.expansions; }
+            // (count == 0 -> `continue` in the reference: no lane is valid, nothing below acts)
             const float dqp = exact_dist;
-            if (cal.num_slack > 0) {   // :141-145
+            if (cal.num_slack > 0 && count > 0) {   // :141-145
                 const int li = slack_batch_count < cal.num_slack - 1 ? slack_batch_count : cal.num_slack - 1;
                 qp.slack = cal.slack[li];
                 ++slack_batch_count;
             }
 
             // ---- FastScan over the 32-code block + epilogue (:150-207); lane = neighbour slot -----
-            const uint32_t nid = __ldg(reinterpret_cast<const uint32_t*>(aux) + lane);
-            const float nop = __ldg(reinterpret_cast<const float*>(aux + 128) + lane);
-            const float ipqo = __ldg(reinterpret_cast<const float*>(aux + 256) + lane);
-            const float ipcp = __ldg(reinterpret_cast<const float*>(aux + 384) + lane);
-            const uint32_t pops = __ldg(reinterpret_cast<const uint32_t*>(aux + 512) + lane);
-            uint32_t ps[B];
-            plane_sums<B>(reinterpret_cast<const uint4*>(blk), nch, lane, w.uq, ps);
-            uint32_t nbit, msb, msb2;
-            combine_planes<B>(ps, nbit, msb, msb2);
-            const bool valid = lane < count;
-            float est, lower;
-            if (B == 1) {
-                convert_1bit(qp, nbit, nop, ipqo, ipcp, pops & 0xFFFFu, lane, count, dqp, est, lower);
-            } else {
-                lower = convert_msb<B>(qp, msb2, nop, ipqo, ipcp, pops & 0xFFFFu, dqp);
-                const float threshold = nn_m ? w.nn_d[nn_m - 1] : FLT_MAX;   // nn.worst_distance()
-                const bool any = nn_m < k || __any_sync(kFull, valid && lower < threshold);
-                if (any) {
-                    convert_nbit<B>(qp, nbit, msb, nop, ipqo, ipcp, pops & 0xFFFFu, pops >> 16, lane, count, dqp, est,
-                                    lower);
+            float est = FLT_MAX, lower = 0.0f;
+            if (count > 0) {
+                const float nop = __ldg(reinterpret_cast<const float*>(aux + 128) + lane);
+                const float ipqo = __ldg(reinterpret_cast<const float*>(aux + 256) + lane);
+                const float ipcp = __ldg(reinterpret_cast<const float*>(aux + 384) + lane);
+                const uint32_t pops = __ldg(reinterpret_cast<const uint32_t*>(aux + 512) + lane);
+                uint32_t ps[B];
+                plane_sums<B>(reinterpret_cast<const uint4*>(blk), nch, lane, w.uq, ps);
+                uint32_t nbit, msb, msb2;
+                combine_planes<B>(ps, nbit, msb, msb2);
+                if (B == 1) {
+                    convert_1bit(qp, nbit, nop, ipqo, ipcp, pops & 0xFFFFu, lane, count, dqp, est, lower);
                 } else {
-                    ++st.msb_skipped;
-                    est = FLT_MAX;
+                    lower = convert_msb<B>(qp, msb2, nop, ipqo, ipcp, pops & 0xFFFFu, dqp);
+                    const float threshold = w.nn_d[nn_m - 1];   // nn.worst_distance(); nn is not empty here
+                    const bool any = nn_m < k || __any_sync(kFull, valid && lower < threshold);
+                    if (any) {
+                        convert_nbit<B>(qp, nbit, msb, nop, ipqo, ipcp, pops & 0xFFFFu, pops >> 16, lane, count, dqp,
+                                        est, lower);
+                    } else {
+                        if (STATS) ++st.msb_skipped;
+                        est = FLT_MAX;
+                    }
                 }
             }
 
-            // ---- check_and_mark_estimated for all slots at once (:227) -----------------------------
-            const unsigned peers = __match_any_sync(kFull, valid ? nid : (kInvalid - lane));
-            bool isnew = false;
-            if (valid && (uint32_t)(__ffs(peers) - 1) == lane) {
-                const uint32_t wd = nid >> 5, bit = 1u << (nid & 31);
-                const uint32_t old = atomicOr(&w.bitmap[wd], bit);
-                isnew = !(old & bit);
-                if (isnew) { const uint32_t ch = wd / a.chunk_words; atomicOr(&w.dirty[ch >> 5], 1u << (ch & 31)); }
-            }
+            const bool isnew = leader && !(old & (1u << (nid & 31)));
+            if (isnew) { const uint32_t ch = (nid >> 5) / a.chunk_words; atomicOr(&w.dirty[ch >> 5], 1u << (ch & 31)); }
             unsigned rem = __ballot_sync(kFull, isnew);
-            st.estimated += __popc(rem);
+            if (STATS) st.estimated += __popc(rem);
 
             // ---- the sequential neighbour loop (:218-273), batched between state changes -----------
             const bool warmup = nn_m < k;   // :210, fixed for the whole loop
             if (warmup) {
-                const float myex = exact_for_lanes(ix, w, rem, nid, qn, st.exact_calls);
+                const float myex = exact_for_lanes(ix, w, rem, nid, qn);
+                if (STATS) st.exact_calls += __popc(rem);
                 while (rem) {
                     const int j = __ffs(rem) - 1;
                     rem &= rem - 1;
@@ -350,20 +418,21 @@ __global__ void __launch_bounds__(256, 2) search_kernel(const DevIndex ix, const
                     const uint32_t id = __shfl_sync(kFull, nid, j);
                     const float dabs = nn_m >= k ? __fmul_rn(gamma_q, w.nn_d[k - 1]) : FLT_MAX;   // :230-232
                     nn_push(w, nn_m, k, id, ex);
-                    ++st.nn_pushes;
+                    if (STATS) ++st.nn_pushes;
                     if (ex < dabs) {
                         if (heap_n >= a.beam_capacity) { overflow = true; break; }
-                        if (lane == 0) heap_sift_up(w, heap_n, make_uint4(__float_as_uint(ex), __float_as_uint(ex), id, 0u));
-                        ++heap_n; ++st.beam_pushes;
-                        __syncwarp();
+                        heap_push(w, heap_n, ex, make_uint2(__float_as_uint(ex), id));
+                        ++heap_n;
+                        if (STATS) ++st.beam_pushes;
                     }
                 }
-            } else {
+            } else if (rem) {
                 worst = w.nn_d[k - 1];
                 // distances that may be needed: every new slot that passes both tests under the
                 // current k-th distance (the k-th distance only shrinks, so this is a superset)
                 const unsigned spec = __ballot_sync(kFull, isnew && !(lower >= worst) && est < worst);
-                const float myex = exact_for_lanes(ix, w, spec, nid, qn, st.exact_calls);
+                float myex = 0.0f;
+                if (spec) { myex = exact_for_lanes(ix, w, spec, nid, qn); if (STATS) st.exact_calls += __popc(spec); }
                 while (rem) {
                     const bool skip = lower >= worst;        // :246
                     const bool pex = !skip && est < worst;   // :248
@@ -375,13 +444,11 @@ __global__ void __launch_bounds__(256, 2) search_kernel(const DevIndex ix, const
                     while (pm) {
                         const int j = __ffs(pm) - 1;
                         pm &= pm - 1;
-                        const uint4 e = make_uint4(__float_as_uint(__shfl_sync(kFull, est, j)),
-                                                   __float_as_uint(__shfl_sync(kFull, lower, j)),
-                                                   __shfl_sync(kFull, nid, j), 0u);
                         if (heap_n >= a.beam_capacity) { overflow = true; break; }
-                        if (lane == 0) heap_sift_up(w, heap_n, e);
-                        ++heap_n; ++st.beam_pushes;
-                        __syncwarp();
+                        heap_push(w, heap_n, __shfl_sync(kFull, est, j),
+                                  make_uint2(__float_as_uint(__shfl_sync(kFull, lower, j)), __shfl_sync(kFull, nid, j)));
+                        ++heap_n;
+                        if (STATS) ++st.beam_pushes;
                     }
                     if (overflow) break;
                     rem &= ~batch;
@@ -391,19 +458,19 @@ __global__ void __launch_bounds__(256, 2) search_kernel(const DevIndex ix, const
                         const float lo = __shfl_sync(kFull, lower, first);
                         const uint32_t id = __shfl_sync(kFull, nid, first);
                         nn_push(w, nn_m, k, id, ex);
-                        ++st.nn_pushes;
+                        if (STATS) ++st.nn_pushes;
                         if (ex < dabs) {
                             if (heap_n >= a.beam_capacity) { overflow = true; break; }
-                            if (lane == 0) heap_sift_up(w, heap_n, make_uint4(__float_as_uint(ex), __float_as_uint(lo), id, 0u));
-                            ++heap_n; ++st.beam_pushes;
-                            __syncwarp();
+                            heap_push(w, heap_n, ex, make_uint2(__float_as_uint(lo), id));
+                            ++heap_n;
+                            if (STATS) ++st.beam_pushes;
                         }
                         if (ex > 1e-12f) {   // gamma_q adaptation (:255-267)
                             const double r = (double)__fdiv_rn(ed, ex);
                             ratio_sum = __dadd_rn(ratio_sum, r);
                             ratio_sq_sum = __fma_rn(r, r, ratio_sq_sum);
                             ++ratio_count;
-                            if (ratio_count >= cal.gamma_warmup) {
+                            if ((unsigned long long)ratio_count >= cal.gamma_warmup) {
                                 const double cnt = (double)ratio_count;
                                 const double r_mean = __ddiv_rn(ratio_sum, cnt);
                                 const double r_var = __fma_rn(-r_mean, r_mean, __ddiv_rn(ratio_sq_sum, cnt));
@@ -417,7 +484,7 @@ __global__ void __launch_bounds__(256, 2) search_kernel(const DevIndex ix, const
                 }
             }
             if (overflow) break;
-            if (heap_n > max_beam) max_beam = heap_n;
+            if (STATS && heap_n > max_beam) max_beam = heap_n;
         }
 
         // ---- results: extract_sorted (:37-40) then the padding of bindings.cpp:201-210 ------------
@@ -431,7 +498,7 @@ __global__ void __launch_bounds__(256, 2) search_kernel(const DevIndex ix, const
                 a.dists[(size_t)q * a.kout + j] = have ? w.nn_d[j] : FLT_MAX;
             }
         }
-        if ((unsigned long long)max_beam > st.max_beam) st.max_beam = max_beam;
+        if (STATS && (unsigned long long)max_beam > st.max_beam) st.max_beam = max_beam;
 
         // ---- clear the touched chunks of the estimated bitmap -------------------------------------
         __syncwarp();
@@ -440,8 +507,7 @@ __global__ void __launch_bounds__(256, 2) search_kernel(const DevIndex ix, const
             while (bits) {
                 const uint32_t ch = dw * 32 + (__ffs(bits) - 1);
                 bits &= bits - 1;
-                const uint32_t w0 = ch * a.chunk_words;
-                uint4* p = reinterpret_cast<uint4*>(w.bitmap + w0);
+                uint4* p = reinterpret_cast<uint4*>(w.bitmap + (size_t)ch * a.chunk_words);
                 for (uint32_t i = lane; i < a.chunk_words / 4; i += 32) p[i] = make_uint4(0, 0, 0, 0);
             }
         }
@@ -449,7 +515,7 @@ __global__ void __launch_bounds__(256, 2) search_kernel(const DevIndex ix, const
         if (lane < 8) w.dirty[lane] = 0;
     }
 
-    if (a.stats && lane == 0) {
+    if (STATS && a.stats && lane == 0) {
         atomicAdd(&a.stats->pops, st.pops);
         atomicAdd(&a.stats->expansions, st.expansions);
         atomicAdd(&a.stats->exact_calls, st.exact_calls);
@@ -464,12 +530,36 @@ __global__ void __launch_bounds__(256, 2) search_kernel(const DevIndex ix, const
     }
 }
 
-size_t search_smem_per_warp(const DevIndex& ix, uint32_t k) { return smem_per_warp(ix.T, ix.nch, k); }
+size_t search_smem_per_warp(const DevIndex& ix, uint32_t k, uint32_t heap_cache) {
+    return smem_per_warp(ix.T, ix.nch, k, heap_cache);
+}
 
-cudaError_t launch_search(const DevIndex& ix, const SearchArgs& a, int ctas, int warps_per_cta, cudaStream_t stream) {
-    const size_t smem = search_smem_per_warp(ix, a.k) * warps_per_cta;
-    void (*kern)(const DevIndex, const SearchArgs) =
-        ix.B == 1 ? search_kernel<1> : ix.B == 2 ? search_kernel<2> : search_kernel<4>;
+typedef void (*SearchKernel)(const DevIndex, const SearchArgs);
+
+static SearchKernel pick_kernel(uint32_t B, bool stats) {
+    if (stats) return B == 1 ? search_kernel<1, true> : B == 2 ? search_kernel<2, true> : search_kernel<4, true>;
+    return B == 1 ? search_kernel<1, false> : B == 2 ? search_kernel<2, false> : search_kernel<4, false>;
+}
+
+int search_max_ctas_per_sm(const DevIndex& ix, uint32_t k, uint32_t heap_cache, int warps_per_cta, bool stats) {
+    const size_t smem = search_smem_per_warp(ix, k, heap_cache) * warps_per_cta;
+    SearchKernel kern = pick_kernel(ix.B, stats);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, warps_per_cta * 32, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return nb;
+}
+
+cudaError_t launch_search(const DevIndex& ix, const SearchArgs& a, int ctas, int warps_per_cta, bool stats,
+                          cudaStream_t stream) {
+    const size_t smem = search_smem_per_warp(ix, a.k, a.heap_cache) * warps_per_cta;
+    SearchKernel kern = pick_kernel(ix.B, stats);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<ctas, warps_per_cta * 32, smem, stream>>>(ix, a);

@@ -172,6 +172,7 @@ def gpu_index_from(fab_or_path, dim=None, bits=None):
         sf = co.SaveFile(fab_or_path)
         ix = cphnsw_b200.CPIndex(sf.dim, sf.B)
         ix.load(str(fab_or_path))
+        ix.set_option("collect_stats", 1)
         return ix
     fab = fab_or_path
     ix = cphnsw_b200.CPIndex(fab.dim, fab.B)
@@ -179,6 +180,7 @@ def gpu_index_from(fab_or_path, dim=None, bits=None):
                         norm_sq=fab.norm_sq, calibration=fab.calibration, centroid=fab.centroid,
                         max_level=fab.max_level, entry_point=fab.entry_point, graph_entry_point=fab.entry_point,
                         rotation_seed=fab.rotation_seed, layers=fab.layers)
+    ix.set_option("collect_stats", 1)
     return ix
 
 
