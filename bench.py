@@ -75,7 +75,7 @@ def obtain_index(args, rank, world):
         synthetic(args.n, args.dim, args.seed, args.clusters).tofile(vec)
         t = time.time()
         tmp = str(path) + ".part"
-        subprocess.run([str(refbuild), str(args.dim), str(args.bits), str(args.n), str(vec), tmp], check=True)
+        subprocess.run([str(refbuild), str(args.dim), str(args.bits), str(args.n), str(vec), tmp], check=True, stdout=sys.stderr)
         os.replace(tmp, path)
         vec.unlink()
         log(f"[bench] index built in {time.time() - t:.0f} s")
@@ -119,7 +119,7 @@ def ground_truth(path, q, k, device):
     best_i = torch.zeros((q.shape[0], k), dtype=torch.int64, device=device)
     step = 262144
     for s in range(0, base.shape[0], step):
-        b = torch.from_numpy(np.ascontiguousarray(base[s:s + step, :dim])).to(device)
+        b = torch.from_numpy(np.array(base[s:s + step, :dim])).to(device)
         d = (qt * qt).sum(1, keepdim=True) - 2.0 * (qt @ b.T) + (b * b).sum(1)[None, :]
         dd, ii = torch.topk(d, k, dim=1, largest=False)
         cat_d = torch.cat([best_d, dd], 1)
@@ -230,6 +230,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-recall", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library tuning option name=value (does not change results)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -277,6 +278,9 @@ def main():
     ix.load(str(path))
     info = ix.info()
     log(f"[bench] rank {rank}: index on cuda:{local} in {time.time() - t:.1f} s, {info['device_bytes'] / 2**30:.2f} GiB")
+    for o in args.opt:
+        name, val = o.split("=")
+        ix.set_option(name, int(val))
     q = make_queries(args, rank)
     q_dev = torch.from_numpy(q).cuda()
     q_pin = torch.from_numpy(q).pin_memory()

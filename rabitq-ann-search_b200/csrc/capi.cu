@@ -423,11 +423,9 @@ static int run_search(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq
     // shared memory as still lets the requested number of warps reside
     const bool stats = ix->collect_stats != 0;
     int warps = (int)ix->warps_per_cta;
-    uint32_t heap_cache = 255;
     const size_t smem_budget = 220 * 1024;
-    if (search_smem_per_warp(d, k, heap_cache) * warps * (size_t)ix->ctas_per_sm > smem_budget) heap_cache = 63;
-    while (warps > 1 && search_smem_per_warp(d, k, heap_cache) * warps > smem_budget) --warps;
-    int per_sm = search_max_ctas_per_sm(d, k, heap_cache, warps, stats);
+    while (warps > 1 && search_smem_per_warp(d, k) * warps > smem_budget) --warps;
+    int per_sm = search_max_ctas_per_sm(d, k, warps, stats);
     if (per_sm <= 0) return fail(ix, CPHNSW_B200_ECUDA, "search kernel cannot be resident (shared memory / registers)");
     per_sm = std::min<int>(per_sm, (int)ix->ctas_per_sm);
     int ctas = ix->num_sms * per_sm;
@@ -436,16 +434,16 @@ static int run_search(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq
 
     auto layout = [&](uint32_t cap, SearchArgs& a) {
         const uint32_t words = (uint32_t)((d.n + 31) / 32);
-        uint32_t chunk = (words + 255) / 256;
-        chunk = (chunk + 31) / 32 * 32;
+        uint32_t chunk = 32, shift = 10;         // 32 chunks (one dirty bit each in a lane register),
+        while (chunk * 32 < words) { chunk <<= 1; ++shift; }   // power-of-two sized so id -> chunk is a shift
         a.chunk_words = chunk;
-        a.bitmap_words = chunk * 256;
+        a.chunk_shift = shift;
+        a.bitmap_words = chunk * 32;
         size_t off = 0;
         a.heap_off = off; off += ((size_t)(cap + 2) * 12 + 127) & ~(size_t)127;
         a.nn_off = off; if (k > 128) off += ((size_t)k * 8 + 127) & ~(size_t)127;
         a.slot_stride = off;
         a.beam_capacity = cap;
-        a.heap_cache = heap_cache;
     };
 
     SearchArgs a{};

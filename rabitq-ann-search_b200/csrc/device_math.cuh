@@ -148,11 +148,11 @@ __device__ __forceinline__ void lane_scalar(float A_e, float B_e, float fs_e, fl
 }
 
 // convert_to_distances_with_bounds<D> (:89-194) for lane `lane` of a block with `count` neighbours.
+// `sq` = __fsqrt_rn(dqp), computed once per block by the caller.
 __device__ __forceinline__ void convert_1bit(const QParams& p, uint32_t sum, float nop, float ipqo, float ipcp,
-                                             uint32_t pop, uint32_t lane, uint32_t count, float dqp, float& est,
-                                             float& lower) {
+                                             uint32_t pop, uint32_t lane, uint32_t count, float dqp, float sq,
+                                             float& est, float& lower) {
     if (dqp < 1e-12f) { est = __fmaf_rn(nop, nop, dqp); lower = 0.0f; return; }
-    const float sq = __fsqrt_rn(dqp);
     if (lane < (count & ~7u))
         lane_avx(p.A, p.Bc, (float)sum, (float)pop, 0, 0, 0, 0, true, p, sq, dqp, nop, ipqo, ipcp, est, lower);
     else
@@ -162,11 +162,10 @@ __device__ __forceinline__ void convert_1bit(const QParams& p, uint32_t sum, flo
 // convert_msb_to_lower_bounds<D,B> (:371-425): K_PARTIAL = 3 with the plane-0 popcount.
 template <int B>
 __device__ __forceinline__ float convert_msb(const QParams& p, uint32_t msb2, float nop, float ipqo, float ipcp,
-                                             uint32_t pop, float dqp) {
+                                             uint32_t pop, float dqp, float sq) {
     if (dqp < 1e-12f) return 0.0f;
-    const float inv_kp = __fdiv_rn(1.0f, (B < 2) ? 1.0f : 3.0f);
+    constexpr float inv_kp = 1.0f / ((B < 2) ? 1.0f : 3.0f);   // constexpr float inv_K = 1.0f / K_PARTIAL (:378-380)
     const float A = __fmul_rn(p.A, inv_kp), Bc = __fmul_rn(p.Bc, inv_kp);
-    const float sq = __fsqrt_rn(dqp);
     const float q = ipqo > p.floor_ ? ipqo : p.floor_;
     if (!(q > 1e-10f)) return 0.0f;
     const float e = scalar_ip_est(A, Bc, p.C, (float)msb2, (float)pop, ipcp, q, p.a, p.b);
@@ -177,11 +176,10 @@ __device__ __forceinline__ float convert_msb(const QParams& p, uint32_t msb2, fl
 template <int B>
 __device__ __forceinline__ void convert_nbit(const QParams& p, uint32_t nbit, uint32_t msb, float nop, float ipqo,
                                              float ipcp, uint32_t pop, uint32_t wpop, uint32_t lane, uint32_t count,
-                                             float dqp, float& est, float& lower) {
+                                             float dqp, float sq, float& est, float& lower) {
     if (dqp < 1e-12f) { est = __fmaf_rn(nop, nop, dqp); lower = 0.0f; return; }
-    const float inv_K = __fdiv_rn(1.0f, (float)((1u << B) - 1u));
+    constexpr float inv_K = 1.0f / (float)((1u << B) - 1u);   // constexpr float inv_K = 1.0f / K (:232-233)
     const float A_n = __fmul_rn(p.A, inv_K), B_n = __fmul_rn(p.Bc, inv_K);
-    const float sq = __fsqrt_rn(dqp);
     if (lane < (count & ~7u))
         lane_avx(A_n, B_n, (float)nbit, (float)wpop, p.A, p.Bc, (float)msb, (float)pop, false, p, sq, dqp, nop, ipqo,
                  ipcp, est, lower);

@@ -60,12 +60,13 @@ __global__ void __launch_bounds__(kFsWarps * 32) fastscan_blocks_kernel(const De
         uint32_t nbit, msb, msb2;
         combine_planes<B>(ps, nbit, msb, msb2);
         float est, lower, msb_lower;
+        const float sq = __fsqrt_rn(dqp);
         if (B == 1) {
-            convert_1bit(qp, nbit, nop, ipqo, ipcp, pops & 0xFFFFu, lane, count, dqp, est, lower);
+            convert_1bit(qp, nbit, nop, ipqo, ipcp, pops & 0xFFFFu, lane, count, dqp, sq, est, lower);
             msb_lower = lower;
         } else {
-            msb_lower = convert_msb<B>(qp, msb2, nop, ipqo, ipcp, pops & 0xFFFFu, dqp);
-            convert_nbit<B>(qp, nbit, msb, nop, ipqo, ipcp, pops & 0xFFFFu, pops >> 16, lane, count, dqp, est, lower);
+            msb_lower = convert_msb<B>(qp, msb2, nop, ipqo, ipcp, pops & 0xFFFFu, dqp, sq);
+            convert_nbit<B>(qp, nbit, msb, nop, ipqo, ipcp, pops & 0xFFFFu, pops >> 16, lane, count, dqp, sq, est, lower);
         }
         if (lane >= count) { est = FLT_MAX; lower = FLT_MAX; msb_lower = FLT_MAX; }
         const size_t o = (size_t)i * 32 + lane;

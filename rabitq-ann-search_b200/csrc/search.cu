@@ -40,11 +40,12 @@
 namespace cpb {
 
 constexpr uint32_t kNNSmem = 128;  // result lists up to this k live in shared memory
+constexpr uint32_t kHC = 63;       // frontier entries [0, 63) = tree levels 0..5 live in shared memory
 
 __host__ __device__ inline uint32_t nn_smem_entries(uint32_t k) { return k <= kNNSmem ? ((k + 31u) & ~31u) : 0u; }
 
-__host__ __device__ inline size_t smem_per_warp(uint32_t T, uint32_t nch, uint32_t k, uint32_t hc) {
-    size_t s = (size_t)8 * (T + 4) * 4 + (size_t)nch * 64 + (size_t)(hc + 1) * 12 + 32 + (size_t)nn_smem_entries(k) * 8;
+__host__ __device__ inline size_t smem_per_warp(uint32_t T, uint32_t nch, uint32_t k) {
+    size_t s = (size_t)8 * (T + 4) * 4 + (size_t)nch * 64 + (size_t)(kHC + 1) * 12 + (size_t)nn_smem_entries(k) * 8;
     return (s + 15) & ~(size_t)15;
 }
 
@@ -52,22 +53,40 @@ struct WarpCtx {
     // shared memory
     float* qrow;      // this lane's accumulator row of the query
     const uint4* uq;  // query bit-planes
-    float* ks;        // frontier keys   [0, hc)
+    float* ks;        // frontier keys   [0, kHC)
     uint2* ps;        // frontier payload {lower bound bits, id}
-    uint32_t* dirty;  // 256-bit summary of touched bitmap chunks
     // arena
     float* kg;        // frontier keys, physical index = logical + 1 (sibling pairs 8-B aligned)
     uint2* pg;
     uint32_t* bitmap;
     float* nn_d;
     uint32_t* nn_i;
-    uint32_t lane, hc;
+    uint32_t lane;
+    // lane constants of the frontier walk: lane L < 31 owns sibling pair L of the 5-level subtree under
+    // the hole (pair L = children of subtree node L, level dlev, index jpair in its level)
+    uint32_t dlev, jpair;
+    uint32_t anc_mask, anc_need;  // pairs above pair L on the way to the subtree root / which child they must pick
 };
 
-__device__ __forceinline__ float kget(const WarpCtx& w, uint32_t i) { return i < w.hc ? w.ks[i] : w.kg[i + 1]; }
-__device__ __forceinline__ uint2 pget(const WarpCtx& w, uint32_t i) { return i < w.hc ? w.ps[i] : w.pg[i + 1]; }
+__device__ __forceinline__ float kget(const WarpCtx& w, uint32_t i) { return i < kHC ? w.ks[i] : w.kg[i + 1]; }
+__device__ __forceinline__ uint2 pget(const WarpCtx& w, uint32_t i) { return i < kHC ? w.ps[i] : w.pg[i + 1]; }
 __device__ __forceinline__ void eset(const WarpCtx& w, uint32_t i, float key, uint2 pay) {
-    if (i < w.hc) { w.ks[i] = key; w.ps[i] = pay; } else { w.kg[i + 1] = key; w.pg[i + 1] = pay; }
+    if (i < kHC) { w.ks[i] = key; w.ps[i] = pay; } else { w.kg[i + 1] = key; w.pg[i + 1] = pay; }
+}
+
+__device__ __forceinline__ void init_walk_constants(WarpCtx& w) {
+    const uint32_t L = w.lane;
+    w.dlev = 32u - __clz(L + 1);
+    w.jpair = L + 1 - (1u << (w.dlev - 1));
+    uint32_t m = 0, need = 0, a = L;
+    while (a > 0 && L < 31) {
+        const uint32_t p = (a - 1) >> 1, r = (a - 1) & 1u;   // pair a hangs under child r of pair p
+        m |= 1u << p;
+        need |= r << p;
+        a = p;
+    }
+    w.anc_mask = m;
+    w.anc_need = need;
 }
 
 // std::push_heap of (vk, vp) onto a heap of n entries, comp(a,b) = a.est > b.est.  Warp-cooperative.
@@ -80,12 +99,44 @@ __device__ __forceinline__ void heap_push(const WarpCtx& w, uint32_t n, float vk
     if (l < depth) ka = kget(w, anc);
     const unsigned up = __ballot_sync(kFull, l < depth && ka > vk);
     const uint32_t cnt = __ffs(~up) - 1;           // the new entry passes ancestors 0 .. cnt-1
-    uint2 pa = make_uint2(0, 0);
-    if (l < cnt) pa = pget(w, anc);
+    if (cnt == 0) {                                 // the common case: it stays a leaf
+        if (l == 0) eset(w, n, vk, vp);
+    } else {
+        uint2 pa = make_uint2(0, 0);
+        if (l < cnt) pa = pget(w, anc);
+        __syncwarp();
+        if (l < cnt) eset(w, (m >> l) - 1, ka, pa);    // ancestor l moves to where ancestor l-1 (or the leaf) was
+        if (l == cnt) eset(w, (m >> cnt) - 1, vk, vp);
+    }
     __syncwarp();
-    if (l < cnt) eset(w, (m >> l) - 1, ka, pa);    // ancestor l moves to where ancestor l-1 (or the leaf) was
-    if (l == cnt) eset(w, (m >> cnt) - 1, vk, vp);
+}
+
+// One 5-level step of the pop walk under `hole`.  p = this lane's subtree node (parent of its sibling
+// pair), kl/kr = its pair's keys (0 where absent).  Returns the number of levels moved (5 = go on) and
+// updates hole.  SMEM: the whole step lives in shared memory (hole == 0).
+template <bool SMEM>
+__device__ __forceinline__ uint32_t pop_step(const WarpCtx& w, uint32_t& hole, uint32_t len, float vk) {
+    const uint32_t L = w.lane;
+    const uint32_t p = SMEM ? L : ((hole + 1) << (w.dlev - 1)) - 1 + w.jpair;
+    const uint32_t left = 2 * p + 1;
+    const bool hl = L < 31 && left < len, hr = L < 31 && left + 1 < len;
+    float kl = 0.0f, kr = 0.0f;
+    if (SMEM) { if (hl) kl = w.ks[left]; if (hr) kr = w.ks[left + 1]; }
+    else { if (hl) kl = w.kg[left + 1]; if (hr) kr = w.kg[left + 2]; }
+    const bool right = hr && !(kr > kl);           // __adjust_heap: the right child unless right > left
+    const bool ok = hl && (right ? kr : kl) <= vk;  // the preferred child still moves up
+    const unsigned rmask = __ballot_sync(kFull, right);
+    const unsigned omask = __ballot_sync(kFull, ok);
+    const bool mv = ok && (omask & w.anc_mask) == w.anc_mask && (rmask & w.anc_mask) == w.anc_need;
+    const unsigned M = __ballot_sync(kFull, mv);   // the pairs on the walk: one per level, top down
+    const uint32_t src = left + (right ? 1u : 0u);
+    float mk = 0.0f;
+    uint2 mp = make_uint2(0, 0);
+    if (mv) { if (SMEM) { mk = w.ks[src]; mp = w.ps[src]; } else { mk = w.kg[src + 1]; mp = w.pg[src + 1]; } }
     __syncwarp();
+    if (mv) { if (SMEM) { w.ks[p] = mk; w.ps[p] = mp; } else eset(w, p, mk, mp); }
+    if (M) hole = __shfl_sync(kFull, src, 31 - __clz(M));
+    return __popc(M);
 }
 
 // std::pop_heap + pop_back on a heap of n >= 1 entries.  Warp-cooperative.
@@ -94,48 +145,14 @@ __device__ __forceinline__ void heap_pop(const WarpCtx& w, uint32_t n) {
     const uint32_t len = n - 1;                    // entries 0 .. len-1 remain, the hole starts at the root
     const float vk = kget(w, len);
     const uint2 vp = pget(w, len);
-    const uint32_t L = w.lane;
-    const uint32_t d = 32u - __clz(L + 1);         // lane L holds sibling pair j of level d below the hole (L < 31)
-    const uint32_t j = L + 1 - (1u << (d - 1));
     uint32_t hole = 0;
-    for (;;) {
-        const uint64_t left64 = (((uint64_t)hole + 1) << d) - 1 + 2 * j;
-        const uint32_t left = (uint32_t)left64;
-        const bool hl = L < 31 && left64 < len, hr = L < 31 && left64 + 1 < len;
-        const float kl = hl ? kget(w, left) : 0.0f, kr = hr ? kget(w, left + 1) : 0.0f;
-        const bool right = hr && !(kr > kl);       // __adjust_heap: the right child unless right > left
-        const float ck = right ? kr : kl;
-        const unsigned rmask = __ballot_sync(kFull, right);
-        const unsigned omask = __ballot_sync(kFull, hl && ck <= vk);   // this pair's preferred child moves up
-        // every lane walks the (at most) five levels
-        uint32_t node[6];
-        node[0] = hole;
-        uint32_t jj = 0, moves = 0;
-#pragma unroll
-        for (uint32_t lv = 1; lv <= 5; ++lv) {
-            const uint32_t pl = (1u << (lv - 1)) - 1 + jj;
-            const bool go = moves == lv - 1 && ((omask >> pl) & 1u);
-            const uint32_t r = (rmask >> pl) & 1u;
-            node[lv] = ((hole + 1) << lv) - 1 + 2 * jj + r;
-            if (go) { moves = lv; jj = 2 * jj + r; }
-        }
-        // lane t < moves moves node[t+1] into node[t]
-        uint32_t src = 0, dst = 0;
-#pragma unroll
-        for (uint32_t t = 0; t < 5; ++t) if (L == t) { dst = node[t]; src = node[t + 1]; }
-        float mk = 0.0f;
-        uint2 mp = make_uint2(0, 0);
-        if (L < moves) { mk = kget(w, src); mp = pget(w, src); }
+    uint32_t moved = pop_step<true>(w, hole, len, vk);
+    while (moved == 5) {
         __syncwarp();
-        if (L < moves) eset(w, dst, mk, mp);
-        uint32_t nh = hole;
-#pragma unroll
-        for (uint32_t t = 1; t <= 5; ++t) if (moves == t) nh = node[t];
-        hole = nh;
-        if (moves < 5) break;
-        __syncwarp();
+        moved = pop_step<false>(w, hole, len, vk);
     }
-    if (L == 0) eset(w, hole, vk, vp);
+    __syncwarp();
+    if (w.lane == 0) eset(w, hole, vk, vp);
     __syncwarp();
 }
 
@@ -247,16 +264,15 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
     const uint32_t k = a.k;
 
     // ---- carve shared memory -------------------------------------------------------------------
-    const size_t per_warp = smem_per_warp(T, nch, k, a.heap_cache);
+    const size_t per_warp = smem_per_warp(T, nch, k);
     uint8_t* sm = smem_raw + (size_t)warp * per_warp;
     WarpCtx w;
     w.lane = lane;
-    w.hc = a.heap_cache;
+    init_walk_constants(w);
     float* qs = reinterpret_cast<float*>(sm);                     sm += (size_t)8 * Tp * 4;
     uint4* uqs = reinterpret_cast<uint4*>(sm);                    sm += (size_t)nch * 64;
-    w.ps = reinterpret_cast<uint2*>(sm);                          sm += (size_t)(a.heap_cache + 1) * 8;
-    w.ks = reinterpret_cast<float*>(sm);                          sm += (size_t)(a.heap_cache + 1) * 4;
-    w.dirty = reinterpret_cast<uint32_t*>(sm);                    sm += 32;
+    w.ps = reinterpret_cast<uint2*>(sm);                          sm += (size_t)(kHC + 1) * 8;
+    w.ks = reinterpret_cast<float*>(sm);                          sm += (size_t)(kHC + 1) * 4;
     w.qrow = qs + (size_t)(lane & 7u) * Tp;
     w.uq = uqs;
     const uint32_t slot = blockIdx.x * nwarps + warp;
@@ -271,8 +287,6 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
         w.nn_d = reinterpret_cast<float*>(arena + a.nn_off);
         w.nn_i = reinterpret_cast<uint32_t*>(arena + a.nn_off + (size_t)k * 4);
     }
-    if (lane < 8) w.dirty[lane] = 0;
-
     const Calib& cal = ix.calib;
     Stats st{};
     const uint32_t block_lines = (ix.aux_off + 644 + 127) >> 7;
@@ -310,6 +324,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
         int slack_batch_count = 0;
         bool overflow = false;
         uint32_t max_beam = 0;
+        uint32_t dirty = 0;   // this lane's share of the 32 bitmap chunks it has set bits in
 
         {
             const float d0 = exact_group(ix, w, ep, true, qn);
@@ -318,8 +333,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                 w.ks[0] = d0;
                 w.ps[0] = make_uint2(__float_as_uint(0.0f), ep);
                 atomicOr(&w.bitmap[ep >> 5], 1u << (ep & 31));
-                const uint32_t ch = (ep >> 5) / a.chunk_words;
-                w.dirty[ch >> 5] |= 1u << (ch & 31);
+                dirty |= 1u << (ep >> a.chunk_shift);
             }
             heap_n = 1;
             __syncwarp();
@@ -385,15 +399,16 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                 plane_sums<B>(reinterpret_cast<const uint4*>(blk), nch, lane, w.uq, ps);
                 uint32_t nbit, msb, msb2;
                 combine_planes<B>(ps, nbit, msb, msb2);
+                const float sq = __fsqrt_rn(dqp);
                 if (B == 1) {
-                    convert_1bit(qp, nbit, nop, ipqo, ipcp, pops & 0xFFFFu, lane, count, dqp, est, lower);
+                    convert_1bit(qp, nbit, nop, ipqo, ipcp, pops & 0xFFFFu, lane, count, dqp, sq, est, lower);
                 } else {
-                    lower = convert_msb<B>(qp, msb2, nop, ipqo, ipcp, pops & 0xFFFFu, dqp);
+                    lower = convert_msb<B>(qp, msb2, nop, ipqo, ipcp, pops & 0xFFFFu, dqp, sq);
                     const float threshold = w.nn_d[nn_m - 1];   // nn.worst_distance(); nn is not empty here
                     const bool any = nn_m < k || __any_sync(kFull, valid && lower < threshold);
                     if (any) {
                         convert_nbit<B>(qp, nbit, msb, nop, ipqo, ipcp, pops & 0xFFFFu, pops >> 16, lane, count, dqp,
-                                        est, lower);
+                                        sq, est, lower);
                     } else {
                         if (STATS) ++st.msb_skipped;
                         est = FLT_MAX;
@@ -402,7 +417,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             }
 
             const bool isnew = leader && !(old & (1u << (nid & 31)));
-            if (isnew) { const uint32_t ch = (nid >> 5) / a.chunk_words; atomicOr(&w.dirty[ch >> 5], 1u << (ch & 31)); }
+            if (isnew) dirty |= 1u << (nid >> a.chunk_shift);
             unsigned rem = __ballot_sync(kFull, isnew);
             if (STATS) st.estimated += __popc(rem);
 
@@ -500,19 +515,17 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
         }
         if (STATS && (unsigned long long)max_beam > st.max_beam) st.max_beam = max_beam;
 
-        // ---- clear the touched chunks of the estimated bitmap -------------------------------------
+        // ---- clear the touched chunks of the estimated bitmap (32 chunks; lanes OR their shares) ----------
         __syncwarp();
-        for (uint32_t dw = 0; dw < 8; ++dw) {
-            uint32_t bits = w.dirty[dw];
-            while (bits) {
-                const uint32_t ch = dw * 32 + (__ffs(bits) - 1);
-                bits &= bits - 1;
-                uint4* p = reinterpret_cast<uint4*>(w.bitmap + (size_t)ch * a.chunk_words);
-                for (uint32_t i = lane; i < a.chunk_words / 4; i += 32) p[i] = make_uint4(0, 0, 0, 0);
-            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dirty |= __shfl_xor_sync(kFull, dirty, o);
+        while (dirty) {
+            const uint32_t ch = __ffs(dirty) - 1;
+            dirty &= dirty - 1;
+            uint4* p = reinterpret_cast<uint4*>(w.bitmap + (size_t)ch * a.chunk_words);
+            for (uint32_t i = lane; i < a.chunk_words / 4; i += 32) p[i] = make_uint4(0, 0, 0, 0);
         }
         __syncwarp();
-        if (lane < 8) w.dirty[lane] = 0;
     }
 
     if (STATS && a.stats && lane == 0) {
@@ -530,9 +543,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
     }
 }
 
-size_t search_smem_per_warp(const DevIndex& ix, uint32_t k, uint32_t heap_cache) {
-    return smem_per_warp(ix.T, ix.nch, k, heap_cache);
-}
+size_t search_smem_per_warp(const DevIndex& ix, uint32_t k) { return smem_per_warp(ix.T, ix.nch, k); }
 
 typedef void (*SearchKernel)(const DevIndex, const SearchArgs);
 
@@ -541,8 +552,8 @@ static SearchKernel pick_kernel(uint32_t B, bool stats) {
     return B == 1 ? search_kernel<1, false> : B == 2 ? search_kernel<2, false> : search_kernel<4, false>;
 }
 
-int search_max_ctas_per_sm(const DevIndex& ix, uint32_t k, uint32_t heap_cache, int warps_per_cta, bool stats) {
-    const size_t smem = search_smem_per_warp(ix, k, heap_cache) * warps_per_cta;
+int search_max_ctas_per_sm(const DevIndex& ix, uint32_t k, int warps_per_cta, bool stats) {
+    const size_t smem = search_smem_per_warp(ix, k) * warps_per_cta;
     SearchKernel kern = pick_kernel(ix.B, stats);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
@@ -558,7 +569,7 @@ int search_max_ctas_per_sm(const DevIndex& ix, uint32_t k, uint32_t heap_cache, 
 
 cudaError_t launch_search(const DevIndex& ix, const SearchArgs& a, int ctas, int warps_per_cta, bool stats,
                           cudaStream_t stream) {
-    const size_t smem = search_smem_per_warp(ix, a.k, a.heap_cache) * warps_per_cta;
+    const size_t smem = search_smem_per_warp(ix, a.k) * warps_per_cta;
     SearchKernel kern = pick_kernel(ix.B, stats);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
