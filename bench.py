@@ -133,42 +133,53 @@ def ground_truth(path, q, k, device):
 # clocks
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons DURING the timed region, sampled in-process through NVML (spawning
+    nvidia-smi in a loop stalls the GPU for tens of ms per query and would distort the measurement)."""
 
-    def __init__(self, gpu):
-        self.gpu, self.rows, self.proc = gpu, [], None
+    def __init__(self, gpu, period=0.05):
+        self.gpu, self.period, self.rows, self.stop = gpu, period, [], False
+        self.t = None
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.t = threading.Thread(target=self._run, daemon=True)
             self.t.start()
-        except OSError:
-            self.proc = None
+        except Exception as e:  # noqa: BLE001
+            log(f"[bench] NVML clock sampling unavailable: {e}")
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self.stop:
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h),
+                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
 
     def __exit__(self, *a):
-        if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
+        self.stop = True
+        if self.t:
             self.t.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        seen = sorted(n for n, bit in names.items() if any(r[1] & bit for r in self.rows))
+        return {"sm_mhz": float(np.median([r[0] for r in self.rows])), "sm_max_mhz": float(self.max), "reasons": seen,
+                "samples": len(self.rows), "power_w_max": max(r[2] for r in self.rows)}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -306,22 +317,33 @@ def main():
     st = ix.last_stats()
     ix.set_option("collect_stats", 0)
 
-    # -- value: device-resident queries, CUDA events on the launching stream ------------------------
+    # -- value: device-resident queries and results, C-ABI device entry point, CUDA events on the launching stream
+    ids_dev = torch.empty((args.nq, args.k), dtype=torch.int64, device="cuda")
+    dists_dev = torch.empty((args.nq, args.k), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.Stream()
+
+    def dev_step():
+        rc = lib.cphnsw_b200_search_batch_device(h, q_dev.data_ptr(), args.nq, args.k, ids_dev.data_ptr(), dists_dev.data_ptr(), stream.cuda_stream)
+        if rc:
+            raise RuntimeError(lib.cphnsw_b200_last_error(h).decode())
+
     for _ in range(args.warmup):
-        ix.search_batch(q_dev, args.k)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms, prep_ms, retries = [], [], 0
+        dev_step()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    kernel_ms, prep_ms = [], []
     barrier()
     with ClockSampler(local) as clocks:
-        time.sleep(1.0)   # let nvidia-smi finish attaching before the timed region
-        ev0.record()
-        for _ in range(args.steps):
-            ids_dev, dists_dev = ix.search_batch(q_dev, args.k)
-            tm = ix.last_timings()
-            kernel_ms.append(tm["search_ms"]); prep_ms.append(tm["prep_ms"])
-        ev1.record()
+        time.sleep(0.2)
+        with torch.cuda.stream(stream):
+            evs[0].record()
+            for i in range(args.steps):
+                dev_step()
+                evs[i + 1].record()
+                tm = ix.last_timings()
+                kernel_ms.append(tm["search_ms"]); prep_ms.append(tm["prep_ms"])
         barrier()
-    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    dev_ms = max_over_ranks(evs[0].elapsed_time(evs[-1]))
     retries = st["overflow_retries"]
     value = world * args.nq * args.steps / (dev_ms / 1e3)
 
@@ -379,6 +401,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": args.nq * args.dim * 4, "d2h_bytes_per_step": args.nq * args.k * 12,
                     "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": (2 + (1 if retries else 0)) * args.steps, "roofline": roofline, "clocks": clocks.summary(),
+            "step_ms": [round(x, 3) for x in step_ms], "kernel_ms_per_step": [round(x, 3) for x in kernel_ms],
             "search_stats_per_query": {k: v / args.nq for k, v in st.items() if k not in ("max_beam", "overflow_retries")} | {"max_beam": st["max_beam"]}}
 
     if rank == 0:

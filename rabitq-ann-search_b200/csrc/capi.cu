@@ -440,7 +440,7 @@ static int run_search(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq
         a.chunk_shift = shift;
         a.bitmap_words = chunk * 32;
         size_t off = 0;
-        a.heap_off = off; off += ((size_t)(cap + 2) * 12 + 127) & ~(size_t)127;
+        a.heap_off = off; off += ((size_t)(cap + 2) * 16 + 127) & ~(size_t)127;
         a.nn_off = off; if (k > 128) off += ((size_t)k * 8 + 127) & ~(size_t)127;
         a.slot_stride = off;
         a.beam_capacity = cap;

@@ -37,7 +37,8 @@ __device__ __forceinline__ uint32_t weighted_popc(const uint4& w, const uint4& u
     return popc4(w, u0) + 2u * popc4(w, u1) + 4u * popc4(w, u2) + 8u * popc4(w, u3);
 }
 
-template <int B>
+// SMEM: `planes` is a staged copy of the block in shared memory, else the block in HBM.
+template <int B, bool SMEM = false>
 __device__ __forceinline__ void plane_sums(const uint4* __restrict__ planes, uint32_t nch, uint32_t lane,
                                            const uint4* __restrict__ uq, uint32_t (&ps)[B]) {
 #pragma unroll
@@ -46,7 +47,8 @@ __device__ __forceinline__ void plane_sums(const uint4* __restrict__ planes, uin
         const uint4 u0 = uq[0 * nch + c], u1 = uq[1 * nch + c], u2 = uq[2 * nch + c], u3 = uq[3 * nch + c];
 #pragma unroll
         for (int b = 0; b < B; ++b) {
-            const uint4 w = __ldg(planes + ((size_t)b * nch + c) * 32 + lane);
+            const uint4* wp = planes + ((size_t)b * nch + c) * 32 + lane;
+            const uint4 w = SMEM ? *wp : __ldg(wp);
             ps[b] += weighted_popc(w, u0, u1, u2, u3);
         }
     }
@@ -203,7 +205,8 @@ __device__ __forceinline__ float group_reduce8(float acc) {
     return acc;
 }
 
-template <bool L2>
+// XSMEM: xrow points into shared memory (a staged vector) instead of HBM.
+template <bool L2, bool XSMEM = false>
 __device__ __forceinline__ float group_chain(const float* __restrict__ xrow, const float* __restrict__ qrow,
                                              uint32_t T, bool active) {
     float acc = 0.0f;
@@ -214,7 +217,7 @@ __device__ __forceinline__ float group_chain(const float* __restrict__ xrow, con
             const uint32_t nv = T >> 2;
 #pragma unroll 4
             for (uint32_t j = 0; j < nv; ++j) {
-                const float4 x = __ldg(xp + j);
+                const float4 x = XSMEM ? xp[j] : __ldg(xp + j);
                 const float4 q = qp[j];
                 if (L2) {
                     float d;
@@ -231,7 +234,7 @@ __device__ __forceinline__ float group_chain(const float* __restrict__ xrow, con
             }
         } else {
             for (uint32_t t = 0; t < T; ++t) {
-                const float x = __ldg(xrow + t), q = qrow[t];
+                const float x = XSMEM ? xrow[t] : __ldg(xrow + t), q = qrow[t];
                 if (L2) { const float d = __fsub_rn(q, x); acc = __fmaf_rn(d, d, acc); }
                 else acc = __fmaf_rn(q, x, acc);
             }

@@ -30,6 +30,9 @@
 //         while key(preferred child) <= key(v).  The walk is done five levels per step: the 31
 //         sibling pairs under the hole are loaded one per lane, two ballots (which sibling, does it
 //         still move) give every lane the whole 5-level path, and the moves happen in parallel.
+// HBM reads of an expansion (the vertex's 32-code neighbour block and its raw vector) are staged into
+// shared memory by two bulk asynchronous copies (cp.async.bulk, the TMA engine) completing on a per-warp
+// mbarrier; they are issued as soon as the frontier top is known and fly while the heap is re-ordered.
 // The "visited" set of the reference is elided: an id enters the frontier only right after its
 // first "estimated" mark, hence at most once, so is_visited() can never be true.
 #include <float.h>
@@ -44,9 +47,15 @@ constexpr uint32_t kHC = 63;       // frontier entries [0, 63) = tree levels 0..
 
 __host__ __device__ inline uint32_t nn_smem_entries(uint32_t k) { return k <= kNNSmem ? ((k + 31u) & ~31u) : 0u; }
 
-__host__ __device__ inline size_t smem_per_warp(uint32_t T, uint32_t nch, uint32_t k) {
-    size_t s = (size_t)8 * (T + 4) * 4 + (size_t)nch * 64 + (size_t)(kHC + 1) * 12 + (size_t)nn_smem_entries(k) * 8;
-    return (s + 15) & ~(size_t)15;
+// bytes of a block that an expansion reads (codes + aux + count), rounded for the bulk copy
+__host__ __device__ inline uint32_t block_copy_bytes(uint32_t aux_off) { return (aux_off + 644u + 15u) & ~15u; }
+__host__ __device__ inline uint32_t stage_raw_off(uint32_t aux_off) { return (block_copy_bytes(aux_off) + 127u) & ~127u; }
+
+__host__ __device__ inline size_t smem_per_warp(uint32_t D, uint32_t B, uint32_t k) {
+    const uint32_t T = D / 8, nch = (D > 128 ? D : 128) / 128, aux_off = B * nch * 512;
+    size_t s = (size_t)stage_raw_off(aux_off) + (size_t)D * 4 + 16;   // staged block + raw vector + mbarrier
+    s += (size_t)8 * (T + 4) * 4 + (size_t)nch * 64 + (size_t)(kHC + 1) * 12 + (size_t)nn_smem_entries(k) * 8;
+    return (s + 127) & ~(size_t)127;
 }
 
 struct WarpCtx {
@@ -56,22 +65,28 @@ struct WarpCtx {
     float* ks;        // frontier keys   [0, kHC)
     uint2* ps;        // frontier payload {lower bound bits, id}
     // arena
-    float* kg;        // frontier keys, physical index = logical + 1 (sibling pairs 8-B aligned)
-    uint2* pg;
+    uint4* hg;        // frontier entries {key, lower, id, -} beyond kHC; physical index = logical + 1
+                      // (a sibling pair is one aligned 32-B sector)
     uint32_t* bitmap;
     float* nn_d;
     uint32_t* nn_i;
     uint32_t lane;
+    uint32_t D, T;    // padded dimension and D/8 (compile-time constants in the D = 128 instantiation)
     // lane constants of the frontier walk: lane L < 31 owns sibling pair L of the 5-level subtree under
     // the hole (pair L = children of subtree node L, level dlev, index jpair in its level)
     uint32_t dlev, jpair;
     uint32_t anc_mask, anc_need;  // pairs above pair L on the way to the subtree root / which child they must pick
 };
 
-__device__ __forceinline__ float kget(const WarpCtx& w, uint32_t i) { return i < kHC ? w.ks[i] : w.kg[i + 1]; }
-__device__ __forceinline__ uint2 pget(const WarpCtx& w, uint32_t i) { return i < kHC ? w.ps[i] : w.pg[i + 1]; }
+__device__ __forceinline__ float kget(const WarpCtx& w, uint32_t i) {
+    return i < kHC ? w.ks[i] : *reinterpret_cast<const float*>(w.hg + i + 1);
+}
+__device__ __forceinline__ void eget(const WarpCtx& w, uint32_t i, float& key, uint2& pay) {
+    if (i < kHC) { key = w.ks[i]; pay = w.ps[i]; }
+    else { const uint4 e = w.hg[i + 1]; key = __uint_as_float(e.x); pay = make_uint2(e.y, e.z); }
+}
 __device__ __forceinline__ void eset(const WarpCtx& w, uint32_t i, float key, uint2 pay) {
-    if (i < kHC) { w.ks[i] = key; w.ps[i] = pay; } else { w.kg[i + 1] = key; w.pg[i + 1] = pay; }
+    if (i < kHC) { w.ks[i] = key; w.ps[i] = pay; } else w.hg[i + 1] = make_uint4(__float_as_uint(key), pay.x, pay.y, 0u);
 }
 
 __device__ __forceinline__ void init_walk_constants(WarpCtx& w) {
@@ -90,7 +105,8 @@ __device__ __forceinline__ void init_walk_constants(WarpCtx& w) {
 }
 
 // std::push_heap of (vk, vp) onto a heap of n entries, comp(a,b) = a.est > b.est.  Warp-cooperative.
-__device__ __forceinline__ void heap_push(const WarpCtx& w, uint32_t n, float vk, uint2 vp) {
+// (lk, lp) track the entry at the last index (what the next pop re-inserts) without reading it back.
+__device__ __forceinline__ void heap_push(const WarpCtx& w, uint32_t n, float vk, uint2 vp, float& lk, uint2& lp) {
     const uint32_t m = n + 1;                      // 1-based index of the new leaf
     const uint32_t depth = 31u - __clz(m);         // number of ancestors
     const uint32_t l = w.lane;
@@ -101,12 +117,16 @@ __device__ __forceinline__ void heap_push(const WarpCtx& w, uint32_t n, float vk
     const uint32_t cnt = __ffs(~up) - 1;           // the new entry passes ancestors 0 .. cnt-1
     if (cnt == 0) {                                 // the common case: it stays a leaf
         if (l == 0) eset(w, n, vk, vp);
+        lk = vk; lp = vp;
     } else {
         uint2 pa = make_uint2(0, 0);
-        if (l < cnt) pa = pget(w, anc);
+        if (l < cnt) { float t; eget(w, anc, t, pa); }
         __syncwarp();
         if (l < cnt) eset(w, (m >> l) - 1, ka, pa);    // ancestor l moves to where ancestor l-1 (or the leaf) was
         if (l == cnt) eset(w, (m >> cnt) - 1, vk, vp);
+        lk = __shfl_sync(kFull, ka, 0);                 // the parent now sits in the leaf
+        lp.x = __shfl_sync(kFull, pa.x, 0);
+        lp.y = __shfl_sync(kFull, pa.y, 0);
     }
     __syncwarp();
 }
@@ -121,8 +141,12 @@ __device__ __forceinline__ uint32_t pop_step(const WarpCtx& w, uint32_t& hole, u
     const uint32_t left = 2 * p + 1;
     const bool hl = L < 31 && left < len, hr = L < 31 && left + 1 < len;
     float kl = 0.0f, kr = 0.0f;
+    uint4 el = make_uint4(0, 0, 0, 0), er = el;   // HBM part: whole entries, one 32-B sector per pair
     if (SMEM) { if (hl) kl = w.ks[left]; if (hr) kr = w.ks[left + 1]; }
-    else { if (hl) kl = w.kg[left + 1]; if (hr) kr = w.kg[left + 2]; }
+    else {
+        if (hl) { el = w.hg[left + 1]; kl = __uint_as_float(el.x); }
+        if (hr) { er = w.hg[left + 2]; kr = __uint_as_float(er.x); }
+    }
     const bool right = hr && !(kr > kl);           // __adjust_heap: the right child unless right > left
     const bool ok = hl && (right ? kr : kl) <= vk;  // the preferred child still moves up
     const unsigned rmask = __ballot_sync(kFull, right);
@@ -132,19 +156,20 @@ __device__ __forceinline__ uint32_t pop_step(const WarpCtx& w, uint32_t& hole, u
     const uint32_t src = left + (right ? 1u : 0u);
     float mk = 0.0f;
     uint2 mp = make_uint2(0, 0);
-    if (mv) { if (SMEM) { mk = w.ks[src]; mp = w.ps[src]; } else { mk = w.kg[src + 1]; mp = w.pg[src + 1]; } }
+    if (mv) {
+        if (SMEM) { mk = w.ks[src]; mp = w.ps[src]; }
+        else { mk = right ? kr : kl; mp = right ? make_uint2(er.y, er.z) : make_uint2(el.y, el.z); }
+    }
     __syncwarp();
     if (mv) { if (SMEM) { w.ks[p] = mk; w.ps[p] = mp; } else eset(w, p, mk, mp); }
     if (M) hole = __shfl_sync(kFull, src, 31 - __clz(M));
     return __popc(M);
 }
 
-// std::pop_heap + pop_back on a heap of n >= 1 entries.  Warp-cooperative.
-__device__ __forceinline__ void heap_pop(const WarpCtx& w, uint32_t n) {
+// std::pop_heap + pop_back on a heap of n >= 1 entries whose last entry is (vk, vp).  Warp-cooperative.
+__device__ __forceinline__ void heap_pop(const WarpCtx& w, uint32_t n, float vk, uint2 vp) {
     if (n <= 1) return;
     const uint32_t len = n - 1;                    // entries 0 .. len-1 remain, the hole starts at the root
-    const float vk = kget(w, len);
-    const uint2 vp = pget(w, len);
     uint32_t hole = 0;
     uint32_t moved = pop_step<true>(w, hole, len, vk);
     while (moved == 5) {
@@ -154,6 +179,28 @@ __device__ __forceinline__ void heap_pop(const WarpCtx& w, uint32_t n) {
     __syncwarp();
     if (w.lane == 0) eset(w, hole, vk, vp);
     __syncwarp();
+}
+
+// ---- bulk asynchronous copies (TMA engine) completing on an mbarrier ----------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    } while (!done);
 }
 
 // BoundedMaxHeap::push (search/rabitq_search.hpp:26-35) on an ascending list: accept while not
@@ -186,7 +233,7 @@ __device__ __forceinline__ void nn_push(const WarpCtx& w, uint32_t& m, uint32_t 
 __device__ __forceinline__ float exact_group(const DevIndex& ix, const WarpCtx& w, uint32_t id, bool active,
                                              float qn) {
     const uint32_t l = w.lane & 7u;
-    const float dot = group_chain<false>(ix.rawT + (size_t)id * ix.D + (size_t)l * ix.T, w.qrow, ix.T, active);
+    const float dot = group_chain<false>(ix.rawT + (size_t)id * w.D + (size_t)l * w.T, w.qrow, w.T, active);
     const float norm = active ? __ldg(ix.norm_sq + id) : 0.0f;
     return exact_from_dot(qn, norm, dot);
 }
@@ -223,7 +270,7 @@ __device__ __forceinline__ uint32_t greedy_descent(const DevIndex& ix, const War
     uint32_t node = ix.entry_point, slot = ix.entry_slot;
     for (int L = ix.max_level; L >= 1; --L) {
         const bool have_level = (uint32_t)L <= ix.n_levels;
-        float best = group_chain<true>(ix.rawT + (size_t)node * ix.D + (size_t)l * ix.T, w.qrow, ix.T, true);
+        float best = group_chain<true>(ix.rawT + (size_t)node * w.D + (size_t)l * w.T, w.qrow, w.T, true);
         if (STATS) ++ndist;
         uint32_t best_id = node, best_slot = slot;
         bool improved = have_level;
@@ -236,7 +283,7 @@ __device__ __forceinline__ uint32_t greedy_descent(const DevIndex& ix, const War
                 const bool act = j + g < e;
                 const uint32_t nb = act ? __ldg(lv.nbr_node + j + g) : 0;
                 const uint32_t ns = act ? __ldg(lv.nbr_slot + j + g) : kInvalid;
-                const float d = group_chain<true>(ix.rawT + (size_t)nb * ix.D + (size_t)l * ix.T, w.qrow, ix.T, act);
+                const float d = group_chain<true>(ix.rawT + (size_t)nb * w.D + (size_t)l * w.T, w.qrow, w.T, act);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const float dt = __shfl_sync(kFull, d, t * 8);
@@ -256,19 +303,27 @@ __device__ __forceinline__ uint32_t greedy_descent(const DevIndex& ix, const War
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-template <int B, bool STATS>
+// DT = 128: the padded dimension is the compile-time constant 128 (SIFT/Deep shapes: one 128-dim chunk per
+// code plane, 16-step distance chains, constant shared-memory offsets); DT = 0: any supported dimension.
+template <int B, bool STATS, int DT>
 __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const SearchArgs a) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const uint32_t D = ix.D, T = ix.T, nch = ix.nch, Tp = T + 4;
+    const uint32_t D = DT ? DT : ix.D, T = D / 8, nch = DT ? (DT > 128 ? DT : 128) / 128 : ix.nch, Tp = T + 4;
+    const uint32_t aux_off = B * nch * 512;
+    const uint32_t block_stride = DT ? ((aux_off + 644 + 127) & ~127u) : ix.block_stride;
     const uint32_t k = a.k;
 
     // ---- carve shared memory -------------------------------------------------------------------
-    const size_t per_warp = smem_per_warp(T, nch, k);
+    const size_t per_warp = smem_per_warp(D, B, k);
     uint8_t* sm = smem_raw + (size_t)warp * per_warp;
     WarpCtx w;
     w.lane = lane;
+    w.D = D; w.T = T;
     init_walk_constants(w);
+    const uint32_t blk_bytes = block_copy_bytes(aux_off), raw_off = stage_raw_off(aux_off);
+    uint8_t* stage = sm;                                          sm += (size_t)raw_off + (size_t)D * 4;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sm);             sm += 16;
     float* qs = reinterpret_cast<float*>(sm);                     sm += (size_t)8 * Tp * 4;
     uint4* uqs = reinterpret_cast<uint4*>(sm);                    sm += (size_t)nch * 64;
     w.ps = reinterpret_cast<uint2*>(sm);                          sm += (size_t)(kHC + 1) * 8;
@@ -277,8 +332,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
     w.uq = uqs;
     const uint32_t slot = blockIdx.x * nwarps + warp;
     uint8_t* arena = a.scratch + (size_t)slot * a.slot_stride;
-    w.pg = reinterpret_cast<uint2*>(arena + a.heap_off);
-    w.kg = reinterpret_cast<float*>(arena + a.heap_off + ((size_t)a.beam_capacity + 2) * 8);
+    w.hg = reinterpret_cast<uint4*>(arena + a.heap_off);
     w.bitmap = a.bitmaps + (size_t)slot * a.bitmap_words;
     if (k <= kNNSmem) {
         w.nn_d = reinterpret_cast<float*>(sm);
@@ -289,7 +343,10 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
     }
     const Calib& cal = ix.calib;
     Stats st{};
-    const uint32_t block_lines = (ix.aux_off + 644 + 127) >> 7;
+    if (lane == 0) mbar_init(mbar, 1);
+    __syncwarp();
+    uint32_t phase = 0;
+    const uint8_t* aux = stage + aux_off;   // staged block: codes at 0, aux fields at aux_off
 
     for (;;) {
         uint32_t wi = 0;
@@ -325,6 +382,8 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
         bool overflow = false;
         uint32_t max_beam = 0;
         uint32_t dirty = 0;   // this lane's share of the 32 bitmap chunks it has set bits in
+        float lk = 0.0f;      // the frontier's last entry (what the next pop re-inserts), kept in registers
+        uint2 lp = make_uint2(0, 0);
 
         {
             const float d0 = exact_group(ix, w, ep, true, qn);
@@ -336,6 +395,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                 dirty |= 1u << (ep >> a.chunk_shift);
             }
             heap_n = 1;
+            lk = d0; lp = make_uint2(__float_as_uint(0.0f), ep);
             __syncwarp();
         }
 
@@ -345,27 +405,29 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             const uint2 top = w.ps[0];
             const float cur_lower = __uint_as_float(top.x);
             const uint32_t cur = top.y;
-            const uint8_t* blk = ix.blocks + (size_t)cur * ix.block_stride;
             const bool full0 = nn_m >= k;
             float worst = full0 ? w.nn_d[k - 1] : FLT_MAX;
             const bool terminate = full0 && cur_est >= __fmul_rn(gamma_q, worst);   // :120
             const bool lbskip = full0 && cur_lower > worst;                          // :122
-            if (!terminate && !lbskip) {
-                // start the HBM reads of this expansion before the heap work: block lines and raw vector
-                if (lane < block_lines) prefetch_l2(blk + (size_t)lane * 128);
-                else if (lane - block_lines < (D * 4 + 127) / 128) prefetch_l2(ix.rawT + (size_t)cur * D + (size_t)(lane - block_lines) * 32);
+            const bool expand = !terminate && !lbskip;
+            // start the HBM reads of this expansion before the heap work: neighbour block and raw vector
+            if (expand && lane == 0) {
+                mbar_expect_tx(mbar, blk_bytes + D * 4);
+                bulk_g2s(stage, ix.blocks + (size_t)cur * block_stride, blk_bytes, mbar);
+                bulk_g2s(stage + raw_off, ix.rawT + (size_t)cur * D, D * 4, mbar);
             }
-            __syncwarp();
-            heap_pop(w, heap_n);
+            heap_pop(w, heap_n, lk, lp);
             --heap_n;
+            if (heap_n > 0) eget(w, heap_n - 1, lk, lp);   // in flight until the next pop (or replaced by a push)
             if (STATS) ++st.pops;
             if (terminate) { if (STATS) ++st.gamma_terms; break; }
             if (lbskip) { if (STATS) ++st.lb_skips; continue; }
+            mbar_wait(mbar, phase);
+            phase ^= 1u;
 
             // neighbour ids first: their "estimated" probes travel while the distances are computed
-            const uint8_t* aux = blk + ix.aux_off;
-            const uint32_t count = __ldg(reinterpret_cast<const uint32_t*>(aux + 640));
-            const uint32_t nid = __ldg(reinterpret_cast<const uint32_t*>(aux) + lane);
+            const uint32_t count = *reinterpret_cast<const uint32_t*>(aux + 640);
+            const uint32_t nid = reinterpret_cast<const uint32_t*>(aux)[lane];
             const bool valid = lane < count;
             // ---- check_and_mark_estimated for all slots at once (:227); slots are distinct ids unless
             //      the index says otherwise, then only the first of equal ids may be new
@@ -377,7 +439,12 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             uint32_t old = 0xFFFFFFFFu;
             if (leader) old = atomicOr(&w.bitmap[nid >> 5], 1u << (nid & 31));
 
-            const float exact_dist = exact_group(ix, w, cur, true, qn);   // :130-133
+            float exact_dist;   // :130-133, from the staged vector
+            {
+                const float dot = group_chain<false, true>(reinterpret_cast<const float*>(stage + raw_off) + (size_t)(lane & 7u) * T,
+                                                           w.qrow, T, true);
+                exact_dist = exact_from_dot(qn, __ldg(ix.norm_sq + cur), dot);
+            }
             nn_push(w, nn_m, k, cur, exact_dist);
             if (STATS) { ++st.exact_calls; ++st.nn_pushes; ++st.expansions; }
             // (count == 0 -> `continue` in the reference: no lane is valid, nothing below acts)
@@ -391,12 +458,12 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             // ---- FastScan over the 32-code block + epilogue (:150-207); lane = neighbour slot -----
             float est = FLT_MAX, lower = 0.0f;
             if (count > 0) {
-                const float nop = __ldg(reinterpret_cast<const float*>(aux + 128) + lane);
-                const float ipqo = __ldg(reinterpret_cast<const float*>(aux + 256) + lane);
-                const float ipcp = __ldg(reinterpret_cast<const float*>(aux + 384) + lane);
-                const uint32_t pops = __ldg(reinterpret_cast<const uint32_t*>(aux + 512) + lane);
+                const float nop = reinterpret_cast<const float*>(aux + 128)[lane];
+                const float ipqo = reinterpret_cast<const float*>(aux + 256)[lane];
+                const float ipcp = reinterpret_cast<const float*>(aux + 384)[lane];
+                const uint32_t pops = reinterpret_cast<const uint32_t*>(aux + 512)[lane];
                 uint32_t ps[B];
-                plane_sums<B>(reinterpret_cast<const uint4*>(blk), nch, lane, w.uq, ps);
+                plane_sums<B, true>(reinterpret_cast<const uint4*>(stage), nch, lane, w.uq, ps);
                 uint32_t nbit, msb, msb2;
                 combine_planes<B>(ps, nbit, msb, msb2);
                 const float sq = __fsqrt_rn(dqp);
@@ -436,7 +503,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                     if (STATS) ++st.nn_pushes;
                     if (ex < dabs) {
                         if (heap_n >= a.beam_capacity) { overflow = true; break; }
-                        heap_push(w, heap_n, ex, make_uint2(__float_as_uint(ex), id));
+                        heap_push(w, heap_n, ex, make_uint2(__float_as_uint(ex), id), lk, lp);
                         ++heap_n;
                         if (STATS) ++st.beam_pushes;
                     }
@@ -461,7 +528,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                         pm &= pm - 1;
                         if (heap_n >= a.beam_capacity) { overflow = true; break; }
                         heap_push(w, heap_n, __shfl_sync(kFull, est, j),
-                                  make_uint2(__float_as_uint(__shfl_sync(kFull, lower, j)), __shfl_sync(kFull, nid, j)));
+                                  make_uint2(__float_as_uint(__shfl_sync(kFull, lower, j)), __shfl_sync(kFull, nid, j)), lk, lp);
                         ++heap_n;
                         if (STATS) ++st.beam_pushes;
                     }
@@ -476,7 +543,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                         if (STATS) ++st.nn_pushes;
                         if (ex < dabs) {
                             if (heap_n >= a.beam_capacity) { overflow = true; break; }
-                            heap_push(w, heap_n, ex, make_uint2(__float_as_uint(lo), id));
+                            heap_push(w, heap_n, ex, make_uint2(__float_as_uint(lo), id), lk, lp);
                             ++heap_n;
                             if (STATS) ++st.beam_pushes;
                         }
@@ -543,18 +610,22 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
     }
 }
 
-size_t search_smem_per_warp(const DevIndex& ix, uint32_t k) { return smem_per_warp(ix.T, ix.nch, k); }
+size_t search_smem_per_warp(const DevIndex& ix, uint32_t k) { return smem_per_warp(ix.D, ix.B, k); }
 
 typedef void (*SearchKernel)(const DevIndex, const SearchArgs);
 
-static SearchKernel pick_kernel(uint32_t B, bool stats) {
-    if (stats) return B == 1 ? search_kernel<1, true> : B == 2 ? search_kernel<2, true> : search_kernel<4, true>;
-    return B == 1 ? search_kernel<1, false> : B == 2 ? search_kernel<2, false> : search_kernel<4, false>;
+template <int DT>
+static SearchKernel pick_kernel_d(uint32_t B, bool stats) {
+    if (stats) return B == 1 ? search_kernel<1, true, DT> : B == 2 ? search_kernel<2, true, DT> : search_kernel<4, true, DT>;
+    return B == 1 ? search_kernel<1, false, DT> : B == 2 ? search_kernel<2, false, DT> : search_kernel<4, false, DT>;
+}
+static SearchKernel pick_kernel(const DevIndex& ix, bool stats) {
+    return ix.D == 128 ? pick_kernel_d<128>(ix.B, stats) : pick_kernel_d<0>(ix.B, stats);
 }
 
 int search_max_ctas_per_sm(const DevIndex& ix, uint32_t k, int warps_per_cta, bool stats) {
     const size_t smem = search_smem_per_warp(ix, k) * warps_per_cta;
-    SearchKernel kern = pick_kernel(ix.B, stats);
+    SearchKernel kern = pick_kernel(ix, stats);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;
@@ -570,7 +641,7 @@ int search_max_ctas_per_sm(const DevIndex& ix, uint32_t k, int warps_per_cta, bo
 cudaError_t launch_search(const DevIndex& ix, const SearchArgs& a, int ctas, int warps_per_cta, bool stats,
                           cudaStream_t stream) {
     const size_t smem = search_smem_per_warp(ix, a.k) * warps_per_cta;
-    SearchKernel kern = pick_kernel(ix.B, stats);
+    SearchKernel kern = pick_kernel(ix, stats);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<ctas, warps_per_cta * 32, smem, stream>>>(ix, a);
