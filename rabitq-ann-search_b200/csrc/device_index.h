@@ -46,6 +46,7 @@ struct Level {
 //   aux_off + 384  ip_cp f32[32]
 //   aux_off + 512  pops  u32[32]   lo16 = popcounts (plane-0 popcount), hi16 = weighted_popcounts
 //   aux_off + 640  count u32
+//   aux_off + 644  norm_sq f32     |x|^2 of the vertex itself (one bulk copy brings all an expansion reads)
 struct DevIndex {
     uint32_t D, B, dim;
     uint32_t nch;  // 128-dim chunks per code plane = max(D,128)/128

@@ -46,7 +46,10 @@ __global__ void __launch_bounds__(128) relayout_blocks_kernel(const DevIndex ix,
         const uint32_t wpop = nbit ? reinterpret_cast<const uint16_t*>(s_wpop)[l] : 0u;
         reinterpret_cast<uint32_t*>(aux + 512)[l] = pop | (wpop << 16);
         const uint32_t cnt = reinterpret_cast<const uint32_t*>(s_ids + 128)[0];
-        if (l == 0) reinterpret_cast<uint32_t*>(aux + 640)[0] = cnt < 32 ? cnt : 32;
+        if (l == 0) {
+            reinterpret_cast<uint32_t*>(aux + 640)[0] = cnt < 32 ? cnt : 32;
+            reinterpret_cast<float*>(aux + 644)[0] = ix.norm_sq[first + v];   // the vertex's own |x|^2 rides along
+        }
         // sanity of the graph: ids in range, and whether any id repeats inside the block
         const uint32_t id = reinterpret_cast<const uint32_t*>(s_ids)[l];
         const bool valid = l < cnt;

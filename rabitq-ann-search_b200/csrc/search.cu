@@ -53,7 +53,7 @@ __host__ __device__ inline uint32_t stage_raw_off(uint32_t aux_off) { return (bl
 
 __host__ __device__ inline size_t smem_per_warp(uint32_t D, uint32_t B, uint32_t k) {
     const uint32_t T = D / 8, nch = (D > 128 ? D : 128) / 128, aux_off = B * nch * 512;
-    size_t s = (size_t)stage_raw_off(aux_off) + (size_t)D * 4 + 16;   // staged block + raw vector + mbarrier
+    size_t s = (size_t)stage_raw_off(aux_off) + (size_t)D * 4 + 16 + 64;   // staged block + raw vector + mbarrier + WarpState
     s += (size_t)8 * (T + 4) * 4 + (size_t)nch * 64 + (size_t)(kHC + 1) * 12 + (size_t)nn_smem_entries(k) * 8;
     return (s + 127) & ~(size_t)127;
 }
@@ -72,11 +72,22 @@ struct WarpCtx {
     uint32_t* nn_i;
     uint32_t lane;
     uint32_t D, T;    // padded dimension and D/8 (compile-time constants in the D = 128 instantiation)
-    // lane constants of the frontier walk: lane L < 31 owns sibling pair L of the 5-level subtree under
-    // the hole (pair L = children of subtree node L, level dlev, index jpair in its level)
-    uint32_t dlev, jpair;
-    uint32_t anc_mask, anc_need;  // pairs above pair L on the way to the subtree root / which child they must pick
+    struct WarpState* ws;
+    const uint2* walk;  // per-lane constants of the frontier walk (shared by the CTA), see init_walk_table
 };
+
+// Per-query state that is touched rarely or only by uniform reads: kept in shared memory, not in
+// registers (the kernel is register-bound at 64/thread; a spilled in-flight load costs its latency).
+struct WarpState {
+    double ratio_sum, ratio_sq_sum;   // gamma_q adaptation (search/rabitq_search.hpp:255-267)
+    float A, Bc, C, qn;               // estimator coefficients of the query, |q|^2
+    float gamma_q;
+    uint32_t ratio_count;
+    float lk;                         // the frontier's last entry, when known without reading it back
+    uint32_t lp_x, lp_y;
+    uint32_t last_valid;
+};
+static_assert(sizeof(WarpState) <= 64, "WarpState must fit its shared-memory slot");
 
 __device__ __forceinline__ float kget(const WarpCtx& w, uint32_t i) {
     return i < kHC ? w.ks[i] : *reinterpret_cast<const float*>(w.hg + i + 1);
@@ -89,10 +100,10 @@ __device__ __forceinline__ void eset(const WarpCtx& w, uint32_t i, float key, ui
     if (i < kHC) { w.ks[i] = key; w.ps[i] = pay; } else w.hg[i + 1] = make_uint4(__float_as_uint(key), pay.x, pay.y, 0u);
 }
 
-__device__ __forceinline__ void init_walk_constants(WarpCtx& w) {
-    const uint32_t L = w.lane;
-    w.dlev = 32u - __clz(L + 1);
-    w.jpair = L + 1 - (1u << (w.dlev - 1));
+// Lane L < 31 owns sibling pair L of the 5-level subtree under the hole (pair L = the children of subtree
+// node L).  walk[L] = {mask of the pairs above pair L on the way to the subtree root, which child (bit = 1:
+// right) each of them must prefer for the walk to reach pair L}.
+__device__ __forceinline__ void init_walk_table(uint2* tab, uint32_t L) {
     uint32_t m = 0, need = 0, a = L;
     while (a > 0 && L < 31) {
         const uint32_t p = (a - 1) >> 1, r = (a - 1) & 1u;   // pair a hangs under child r of pair p
@@ -100,13 +111,12 @@ __device__ __forceinline__ void init_walk_constants(WarpCtx& w) {
         need |= r << p;
         a = p;
     }
-    w.anc_mask = m;
-    w.anc_need = need;
+    tab[L] = make_uint2(m, need);
 }
 
 // std::push_heap of (vk, vp) onto a heap of n entries, comp(a,b) = a.est > b.est.  Warp-cooperative.
-// (lk, lp) track the entry at the last index (what the next pop re-inserts) without reading it back.
-__device__ __forceinline__ void heap_push(const WarpCtx& w, uint32_t n, float vk, uint2 vp, float& lk, uint2& lp) {
+// ws->lk/lp track the entry at the last index (what the next pop re-inserts) without reading it back.
+__device__ __forceinline__ void heap_push(const WarpCtx& w, uint32_t n, float vk, uint2 vp) {
     const uint32_t m = n + 1;                      // 1-based index of the new leaf
     const uint32_t depth = 31u - __clz(m);         // number of ancestors
     const uint32_t l = w.lane;
@@ -116,17 +126,14 @@ __device__ __forceinline__ void heap_push(const WarpCtx& w, uint32_t n, float vk
     const unsigned up = __ballot_sync(kFull, l < depth && ka > vk);
     const uint32_t cnt = __ffs(~up) - 1;           // the new entry passes ancestors 0 .. cnt-1
     if (cnt == 0) {                                 // the common case: it stays a leaf
-        if (l == 0) eset(w, n, vk, vp);
-        lk = vk; lp = vp;
+        if (l == 0) { eset(w, n, vk, vp); w.ws->lk = vk; w.ws->lp_x = vp.x; w.ws->lp_y = vp.y; w.ws->last_valid = 1u; }
     } else {
         uint2 pa = make_uint2(0, 0);
         if (l < cnt) { float t; eget(w, anc, t, pa); }
         __syncwarp();
         if (l < cnt) eset(w, (m >> l) - 1, ka, pa);    // ancestor l moves to where ancestor l-1 (or the leaf) was
         if (l == cnt) eset(w, (m >> cnt) - 1, vk, vp);
-        lk = __shfl_sync(kFull, ka, 0);                 // the parent now sits in the leaf
-        lp.x = __shfl_sync(kFull, pa.x, 0);
-        lp.y = __shfl_sync(kFull, pa.y, 0);
+        if (l == 0) { w.ws->lk = ka; w.ws->lp_x = pa.x; w.ws->lp_y = pa.y; w.ws->last_valid = 1u; }   // the parent now sits in the leaf
     }
     __syncwarp();
 }
@@ -137,7 +144,9 @@ __device__ __forceinline__ void heap_push(const WarpCtx& w, uint32_t n, float vk
 template <bool SMEM>
 __device__ __forceinline__ uint32_t pop_step(const WarpCtx& w, uint32_t& hole, uint32_t len, float vk) {
     const uint32_t L = w.lane;
-    const uint32_t p = SMEM ? L : ((hole + 1) << (w.dlev - 1)) - 1 + w.jpair;
+    const uint32_t dlev = 32u - __clz(L + 1);      // pair L sits dlev levels below the hole, jpair-th in its level
+    const uint32_t jpair = L + 1 - (1u << (dlev - 1));
+    const uint32_t p = SMEM ? L : ((hole + 1) << (dlev - 1)) - 1 + jpair;
     const uint32_t left = 2 * p + 1;
     const bool hl = L < 31 && left < len, hr = L < 31 && left + 1 < len;
     float kl = 0.0f, kr = 0.0f;
@@ -151,7 +160,8 @@ __device__ __forceinline__ uint32_t pop_step(const WarpCtx& w, uint32_t& hole, u
     const bool ok = hl && (right ? kr : kl) <= vk;  // the preferred child still moves up
     const unsigned rmask = __ballot_sync(kFull, right);
     const unsigned omask = __ballot_sync(kFull, ok);
-    const bool mv = ok && (omask & w.anc_mask) == w.anc_mask && (rmask & w.anc_mask) == w.anc_need;
+    const uint2 wk = w.walk[L];
+    const bool mv = ok && (omask & wk.x) == wk.x && (rmask & wk.x) == wk.y;
     const unsigned M = __ballot_sync(kFull, mv);   // the pairs on the walk: one per level, top down
     const uint32_t src = left + (right ? 1u : 0u);
     float mk = 0.0f;
@@ -166,10 +176,16 @@ __device__ __forceinline__ uint32_t pop_step(const WarpCtx& w, uint32_t& hole, u
     return __popc(M);
 }
 
-// std::pop_heap + pop_back on a heap of n >= 1 entries whose last entry is (vk, vp).  Warp-cooperative.
-__device__ __forceinline__ void heap_pop(const WarpCtx& w, uint32_t n, float vk, uint2 vp) {
-    if (n <= 1) return;
+// std::pop_heap + pop_back on a heap of n >= 1 entries.  Warp-cooperative.
+__device__ __forceinline__ void heap_pop(const WarpCtx& w, uint32_t n) {
+    if (n <= 1) { w.ws->last_valid = 0u; return; }
     const uint32_t len = n - 1;                    // entries 0 .. len-1 remain, the hole starts at the root
+    float vk;
+    uint2 vp;
+    if (w.ws->last_valid) { vk = w.ws->lk; vp = make_uint2(w.ws->lp_x, w.ws->lp_y); }   // known from the last push
+    else eget(w, len, vk, vp);
+    __syncwarp();
+    w.ws->last_valid = 0u;
     uint32_t hole = 0;
     uint32_t moved = pop_step<true>(w, hole, len, vk);
     while (moved == 5) {
@@ -320,10 +336,15 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
     WarpCtx w;
     w.lane = lane;
     w.D = D; w.T = T;
-    init_walk_constants(w);
+    __shared__ uint2 walk_tab[32];
+    if (warp == 0) init_walk_table(walk_tab, lane);
+    w.walk = walk_tab;
+    __syncthreads();
     const uint32_t blk_bytes = block_copy_bytes(aux_off), raw_off = stage_raw_off(aux_off);
     uint8_t* stage = sm;                                          sm += (size_t)raw_off + (size_t)D * 4;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sm);             sm += 16;
+    WarpState* ws = reinterpret_cast<WarpState*>(sm);             sm += 64;
+    w.ws = ws;
     float* qs = reinterpret_cast<float*>(sm);                     sm += (size_t)8 * Tp * 4;
     uint4* uqs = reinterpret_cast<uint4*>(sm);                    sm += (size_t)nch * 64;
     w.ps = reinterpret_cast<uint2*>(sm);                          sm += (size_t)(kHC + 1) * 8;
@@ -363,27 +384,25 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             const uint4* us = reinterpret_cast<const uint4*>(a.uplanes + (size_t)q * 16 * nch);
             for (uint32_t i = lane; i < 4 * nch; i += 32) uqs[i] = us[i];
         }
-        const float* cf = a.coeffs + (size_t)q * kCoeffStride;
-        QParams qp;
-        qp.A = cf[0]; qp.Bc = cf[1]; qp.C = cf[2];
-        qp.a = cal.affine_a; qp.b = cal.affine_b; qp.floor_ = cal.ip_qo_floor; qp.slack = cal.slack[0];
-        const float qn = cf[3];
+        if (lane == 0) {
+            const float* cf = a.coeffs + (size_t)q * kCoeffStride;
+            ws->A = cf[0]; ws->Bc = cf[1]; ws->C = cf[2]; ws->qn = cf[3];
+            ws->gamma_q = cal.gamma;
+            ws->ratio_sum = 0.0; ws->ratio_sq_sum = 0.0; ws->ratio_count = 0u;
+            ws->last_valid = 0u;
+        }
         __syncwarp();
+        const float qn = ws->qn;
 
         const uint32_t ep = greedy_descent<STATS>(ix, w, st.descent_dists);
         if (a.entry_out) { if (lane == 0) a.entry_out[q] = ep; continue; }
 
         // ---- layer-0 search state (search/rabitq_search.hpp:77-97) ----------------------------
         uint32_t heap_n = 0, nn_m = 0;
-        float gamma_q = cal.gamma;
-        double ratio_sum = 0.0, ratio_sq_sum = 0.0;
-        uint32_t ratio_count = 0;
         int slack_batch_count = 0;
         bool overflow = false;
         uint32_t max_beam = 0;
         uint32_t dirty = 0;   // this lane's share of the 32 bitmap chunks it has set bits in
-        float lk = 0.0f;      // the frontier's last entry (what the next pop re-inserts), kept in registers
-        uint2 lp = make_uint2(0, 0);
 
         {
             const float d0 = exact_group(ix, w, ep, true, qn);
@@ -395,7 +414,6 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                 dirty |= 1u << (ep >> a.chunk_shift);
             }
             heap_n = 1;
-            lk = d0; lp = make_uint2(__float_as_uint(0.0f), ep);
             __syncwarp();
         }
 
@@ -407,7 +425,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             const uint32_t cur = top.y;
             const bool full0 = nn_m >= k;
             float worst = full0 ? w.nn_d[k - 1] : FLT_MAX;
-            const bool terminate = full0 && cur_est >= __fmul_rn(gamma_q, worst);   // :120
+            const bool terminate = full0 && cur_est >= __fmul_rn(ws->gamma_q, worst);   // :120
             const bool lbskip = full0 && cur_lower > worst;                          // :122
             const bool expand = !terminate && !lbskip;
             // start the HBM reads of this expansion before the heap work: neighbour block and raw vector
@@ -416,9 +434,8 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                 bulk_g2s(stage, ix.blocks + (size_t)cur * block_stride, blk_bytes, mbar);
                 bulk_g2s(stage + raw_off, ix.rawT + (size_t)cur * D, D * 4, mbar);
             }
-            heap_pop(w, heap_n, lk, lp);
+            heap_pop(w, heap_n);
             --heap_n;
-            if (heap_n > 0) eget(w, heap_n - 1, lk, lp);   // in flight until the next pop (or replaced by a push)
             if (STATS) ++st.pops;
             if (terminate) { if (STATS) ++st.gamma_terms; break; }
             if (lbskip) { if (STATS) ++st.lb_skips; continue; }
@@ -443,16 +460,20 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             {
                 const float dot = group_chain<false, true>(reinterpret_cast<const float*>(stage + raw_off) + (size_t)(lane & 7u) * T,
                                                            w.qrow, T, true);
-                exact_dist = exact_from_dot(qn, __ldg(ix.norm_sq + cur), dot);
+                exact_dist = exact_from_dot(ws->qn, *reinterpret_cast<const float*>(aux + 644), dot);   // norm_sq rides in the block
             }
             nn_push(w, nn_m, k, cur, exact_dist);
             if (STATS) { ++st.exact_calls; ++st.nn_pushes; ++st.expansions; }
             // (count == 0 -> `continue` in the reference: no lane is valid, nothing below acts)
             const float dqp = exact_dist;
-            if (cal.num_slack > 0 && count > 0) {   // :141-145
-                const int li = slack_batch_count < cal.num_slack - 1 ? slack_batch_count : cal.num_slack - 1;
-                qp.slack = cal.slack[li];
-                ++slack_batch_count;
+            QParams qp;
+            qp.A = ws->A; qp.Bc = ws->Bc; qp.C = ws->C;
+            qp.a = cal.affine_a; qp.b = cal.affine_b; qp.floor_ = cal.ip_qo_floor;
+            {   // :141-145: the slack level of this expansion (level 0 applies until the first non-empty block)
+                int li = slack_batch_count - (count > 0 ? 0 : 1);
+                li = li < 0 ? 0 : (li < cal.num_slack - 1 ? li : cal.num_slack - 1);
+                qp.slack = cal.num_slack > 0 ? cal.slack[li] : cal.slack[0];
+                if (cal.num_slack > 0 && count > 0) ++slack_batch_count;
             }
 
             // ---- FastScan over the 32-code block + epilogue (:150-207); lane = neighbour slot -----
@@ -498,12 +519,12 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                     rem &= rem - 1;
                     const float ex = __shfl_sync(kFull, myex, j);
                     const uint32_t id = __shfl_sync(kFull, nid, j);
-                    const float dabs = nn_m >= k ? __fmul_rn(gamma_q, w.nn_d[k - 1]) : FLT_MAX;   // :230-232
+                    const float dabs = nn_m >= k ? __fmul_rn(ws->gamma_q, w.nn_d[k - 1]) : FLT_MAX;   // :230-232
                     nn_push(w, nn_m, k, id, ex);
                     if (STATS) ++st.nn_pushes;
                     if (ex < dabs) {
                         if (heap_n >= a.beam_capacity) { overflow = true; break; }
-                        heap_push(w, heap_n, ex, make_uint2(__float_as_uint(ex), id), lk, lp);
+                        heap_push(w, heap_n, ex, make_uint2(__float_as_uint(ex), id));
                         ++heap_n;
                         if (STATS) ++st.beam_pushes;
                     }
@@ -521,14 +542,14 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                     const unsigned exm = __ballot_sync(kFull, pex) & rem;
                     const int first = exm ? __ffs(exm) - 1 : 32;
                     const unsigned batch = first < 32 ? (rem & ((1u << first) - 1u)) : rem;
-                    const float dabs = __fmul_rn(gamma_q, worst);
+                    const float dabs = __fmul_rn(ws->gamma_q, worst);
                     unsigned pm = __ballot_sync(kFull, !skip && !pex && est < dabs) & batch;   // :269-271
                     while (pm) {
                         const int j = __ffs(pm) - 1;
                         pm &= pm - 1;
                         if (heap_n >= a.beam_capacity) { overflow = true; break; }
                         heap_push(w, heap_n, __shfl_sync(kFull, est, j),
-                                  make_uint2(__float_as_uint(__shfl_sync(kFull, lower, j)), __shfl_sync(kFull, nid, j)), lk, lp);
+                                  make_uint2(__float_as_uint(__shfl_sync(kFull, lower, j)), __shfl_sync(kFull, nid, j)));
                         ++heap_n;
                         if (STATS) ++st.beam_pushes;
                     }
@@ -543,23 +564,26 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                         if (STATS) ++st.nn_pushes;
                         if (ex < dabs) {
                             if (heap_n >= a.beam_capacity) { overflow = true; break; }
-                            heap_push(w, heap_n, ex, make_uint2(__float_as_uint(lo), id), lk, lp);
+                            heap_push(w, heap_n, ex, make_uint2(__float_as_uint(lo), id));
                             ++heap_n;
                             if (STATS) ++st.beam_pushes;
                         }
                         if (ex > 1e-12f) {   // gamma_q adaptation (:255-267)
                             const double r = (double)__fdiv_rn(ed, ex);
-                            ratio_sum = __dadd_rn(ratio_sum, r);
-                            ratio_sq_sum = __fma_rn(r, r, ratio_sq_sum);
-                            ++ratio_count;
-                            if ((unsigned long long)ratio_count >= cal.gamma_warmup) {
-                                const double cnt = (double)ratio_count;
-                                const double r_mean = __ddiv_rn(ratio_sum, cnt);
-                                const double r_var = __fma_rn(-r_mean, r_mean, __ddiv_rn(ratio_sq_sum, cnt));
+                            const double rs = __dadd_rn(ws->ratio_sum, r), rq = __fma_rn(r, r, ws->ratio_sq_sum);
+                            const uint32_t rc = ws->ratio_count + 1;
+                            float gq = ws->gamma_q;
+                            if ((unsigned long long)rc >= cal.gamma_warmup) {
+                                const double cnt = (double)rc;
+                                const double r_mean = __ddiv_rn(rs, cnt);
+                                const double r_var = __fma_rn(-r_mean, r_mean, __ddiv_rn(rq, cnt));
                                 const double r_std = __dsqrt_rn(r_var > 0.0 ? r_var : 0.0);
-                                const float gq = __fmul_rn(cal.gamma, (float)__fma_rn((double)cal.gamma_beta, r_std, 1.0));
-                                gamma_q = gq < cal.gamma ? cal.gamma : (cal.gamma_max < gq ? cal.gamma_max : gq);
+                                const float g = __fmul_rn(cal.gamma, (float)__fma_rn((double)cal.gamma_beta, r_std, 1.0));
+                                gq = g < cal.gamma ? cal.gamma : (cal.gamma_max < g ? cal.gamma_max : g);
                             }
+                            __syncwarp();
+                            if (lane == 0) { ws->ratio_sum = rs; ws->ratio_sq_sum = rq; ws->ratio_count = rc; ws->gamma_q = gq; }
+                            __syncwarp();
                         }
                         worst = w.nn_d[k - 1];
                     }
