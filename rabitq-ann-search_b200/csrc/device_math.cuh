@@ -54,6 +54,19 @@ __device__ __forceinline__ void plane_sums(const uint4* __restrict__ planes, uin
     }
 }
 
+// One plane only (the N-bit path of the search kernel evaluates planes lazily).
+template <bool SMEM>
+__device__ __forceinline__ uint32_t plane_sum_one(const uint4* __restrict__ planes, uint32_t b, uint32_t nch, uint32_t lane,
+                                                  const uint4* __restrict__ uq) {
+    uint32_t s = 0;
+    for (uint32_t c = 0; c < nch; ++c) {
+        const uint4* wp = planes + ((size_t)b * nch + c) * 32 + lane;
+        const uint4 w = SMEM ? *wp : __ldg(wp);
+        s += weighted_popc(w, uq[0 * nch + c], uq[1 * nch + c], uq[2 * nch + c], uq[3 * nch + c]);
+    }
+    return s;
+}
+
 // compute_nbit_inner_products (:197-217): nbit = sum_b 2^(B-1-b) plane_b, msb = plane_0;
 // compute_msb_only_inner_products (:349-368): msb2 = 2 plane_0 + plane_1.
 template <int B>
@@ -188,6 +201,51 @@ __device__ __forceinline__ void convert_nbit(const QParams& p, uint32_t nbit, ui
     else
         lane_scalar(A_n, B_n, (float)nbit, (float)wpop, p.A, p.Bc, (float)msb, (float)pop, false, p, sq, dqp, nop,
                     ipqo, ipcp, est, lower);
+}
+
+// The two halves of convert_nbit_to_distances_with_bounds, separately callable (bit-identical to
+// convert_nbit): the lower bound needs only plane 0 (`msb`), the estimate all planes (`nbit`).
+template <int B>
+__device__ __forceinline__ float nbit_lower(const QParams& p, uint32_t msb, float nop, float ipqo, float ipcp,
+                                            uint32_t pop, uint32_t lane, uint32_t count, float dqp, float sq) {
+    if (dqp < 1e-12f) return 0.0f;
+    if (lane < (count & ~7u)) {   // AVX2 lanes (:277-321)
+        const float q = max_ps(ipqo, p.floor_);
+        if (!(q > 1e-10f)) return 0.0f;
+        const float ip_msb = __fmaf_rn(p.A, (float)msb, __fmaf_rn(p.Bc, (float)pop, p.C));
+        float el = __fdiv_rn(__fsub_rn(ip_msb, ipcp), q);
+        el = __fmaf_rn(p.a, el, p.b);
+        float cu = __fdiv_rn(__fadd_rn(el, p.slack), max_ps(sq, 1e-10f));
+        cu = min_ps(max_ps(cu, -1.0f), 1.0f);
+        const float lo = __fmaf_rn(-__fmul_rn(__fmul_rn(2.0f, nop), sq), cu, __fmaf_rn(nop, nop, dqp));
+        return max_ps(lo, 0.0f);
+    }
+    const float q = ipqo > p.floor_ ? ipqo : p.floor_;   // scalar tail (:324-345)
+    if (!(q > 1e-10f)) return 0.0f;
+    const float el = scalar_ip_est_msbtail(p.A, p.Bc, p.C, (float)msb, (float)pop, ipcp, q, p.a, p.b);
+    return scalar_lower(el, p.slack, sq, nop, dqp);
+}
+
+template <int B>
+__device__ __forceinline__ float nbit_est(const QParams& p, uint32_t nbit, float nop, float ipqo, float ipcp,
+                                          uint32_t wpop, uint32_t lane, uint32_t count, float dqp) {
+    if (dqp < 1e-12f) return __fmaf_rn(nop, nop, dqp);
+    constexpr float inv_K = 1.0f / (float)((1u << B) - 1u);
+    const float A_n = __fmul_rn(p.A, inv_K), B_n = __fmul_rn(p.Bc, inv_K);
+    if (lane < (count & ~7u)) {
+        const float ip_approx = __fmaf_rn(A_n, (float)nbit, __fmaf_rn(B_n, (float)wpop, p.C));
+        const float q = max_ps(ipqo, p.floor_);
+        float e = q > 1e-10f ? __fdiv_rn(__fsub_rn(ip_approx, ipcp), q) : 0.0f;
+        e = __fmaf_rn(p.a, e, p.b);
+        const float d = __fmaf_rn(-__fmul_rn(2.0f, nop), e, __fmaf_rn(nop, nop, dqp));
+        return max_ps(d, 0.0f);
+    }
+    const float q = ipqo > p.floor_ ? ipqo : p.floor_;
+    float e;
+    if (q > 1e-10f) e = scalar_ip_est(A_n, B_n, p.C, (float)nbit, (float)wpop, ipcp, q, p.a, p.b);
+    else e = __fmaf_rn(0.0f, p.a, p.b);
+    const float d = __fmaf_rn(-__fadd_rn(nop, nop), e, __fmaf_rn(nop, nop, dqp));
+    return d < 0.0f ? 0.0f : d;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -477,31 +477,22 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             }
 
             // ---- FastScan over the 32-code block + epilogue (:150-207); lane = neighbour slot -----
+            // est / lower are only ever read for NEW slots of a non-warm-up expansion, and a slot whose lower
+            // bound is not under the k-th distance is dropped before its estimate is looked at (:246).  The
+            // N-bit lower bound needs plane 0 only, so: plane 0 and the bound now, the other planes (MSB-only
+            // pre-filter :170-187, full estimate :189-200) only if some new slot survives the bound.
+            const bool warmup = nn_m < k;   // :210, fixed for the whole neighbour loop
             float est = FLT_MAX, lower = 0.0f;
-            if (count > 0) {
+            uint32_t ps0 = 0;
+            const float sq = __fsqrt_rn(dqp);
+            if (count > 0 && (!warmup || STATS)) {
                 const float nop = reinterpret_cast<const float*>(aux + 128)[lane];
                 const float ipqo = reinterpret_cast<const float*>(aux + 256)[lane];
                 const float ipcp = reinterpret_cast<const float*>(aux + 384)[lane];
                 const uint32_t pops = reinterpret_cast<const uint32_t*>(aux + 512)[lane];
-                uint32_t ps[B];
-                plane_sums<B, true>(reinterpret_cast<const uint4*>(stage), nch, lane, w.uq, ps);
-                uint32_t nbit, msb, msb2;
-                combine_planes<B>(ps, nbit, msb, msb2);
-                const float sq = __fsqrt_rn(dqp);
-                if (B == 1) {
-                    convert_1bit(qp, nbit, nop, ipqo, ipcp, pops & 0xFFFFu, lane, count, dqp, sq, est, lower);
-                } else {
-                    lower = convert_msb<B>(qp, msb2, nop, ipqo, ipcp, pops & 0xFFFFu, dqp, sq);
-                    const float threshold = w.nn_d[nn_m - 1];   // nn.worst_distance(); nn is not empty here
-                    const bool any = nn_m < k || __any_sync(kFull, valid && lower < threshold);
-                    if (any) {
-                        convert_nbit<B>(qp, nbit, msb, nop, ipqo, ipcp, pops & 0xFFFFu, pops >> 16, lane, count, dqp,
-                                        sq, est, lower);
-                    } else {
-                        if (STATS) ++st.msb_skipped;
-                        est = FLT_MAX;
-                    }
-                }
+                ps0 = plane_sum_one<true>(reinterpret_cast<const uint4*>(stage), 0, nch, lane, w.uq);
+                if (B == 1) convert_1bit(qp, ps0, nop, ipqo, ipcp, pops & 0xFFFFu, lane, count, dqp, sq, est, lower);
+                else lower = nbit_lower<B>(qp, ps0, nop, ipqo, ipcp, pops & 0xFFFFu, lane, count, dqp, sq);
             }
 
             const bool isnew = leader && !(old & (1u << (nid & 31)));
@@ -509,8 +500,33 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             unsigned rem = __ballot_sync(kFull, isnew);
             if (STATS) st.estimated += __popc(rem);
 
+            if (B > 1 && count > 0 && (STATS || (!warmup && rem))) {
+                const float w0 = w.nn_d[nn_m - 1];   // nn.worst_distance() (:179), the k-th distance when nn is full
+                const unsigned cand = __ballot_sync(kFull, isnew && !(lower >= w0));
+                if (STATS || cand) {
+                    const float nop = reinterpret_cast<const float*>(aux + 128)[lane];
+                    const float ipqo = reinterpret_cast<const float*>(aux + 256)[lane];
+                    const float ipcp = reinterpret_cast<const float*>(aux + 384)[lane];
+                    const uint32_t pops = reinterpret_cast<const uint32_t*>(aux + 512)[lane];
+                    const uint32_t ps1 = plane_sum_one<true>(reinterpret_cast<const uint4*>(stage), 1, nch, lane, w.uq);
+                    const float msb_lower = convert_msb<B>(qp, 2u * ps0 + ps1, nop, ipqo, ipcp, pops & 0xFFFFu, dqp, sq);
+                    const bool any = nn_m < k || __any_sync(kFull, valid && msb_lower < w0);   // :178-187
+                    if (any) {
+                        uint32_t nbit = (ps0 << (B - 1)) + (ps1 << (B - 2));
+#pragma unroll
+                        for (int b = 2; b < B; ++b)
+                            nbit += plane_sum_one<true>(reinterpret_cast<const uint4*>(stage), b, nch, lane, w.uq) << (B - 1 - b);
+                        est = nbit_est<B>(qp, nbit, nop, ipqo, ipcp, pops >> 16, lane, count, dqp);
+                    } else {
+                        if (STATS) ++st.msb_skipped;
+                        est = FLT_MAX;
+                        lower = msb_lower;
+                    }
+                }
+                if (!warmup && !cand) rem = 0;   // no new slot passes :246 -- nothing in the neighbour loop can act
+            }
+
             // ---- the sequential neighbour loop (:218-273), batched between state changes -----------
-            const bool warmup = nn_m < k;   // :210, fixed for the whole loop
             if (warmup) {
                 const float myex = exact_for_lanes(ix, w, rem, nid, qn);
                 if (STATS) st.exact_calls += __popc(rem);
