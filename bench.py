@@ -241,6 +241,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-recall", action="store_true")
+    ap.add_argument("--no-stream", action="store_true", help="skip the K2 FastScan streaming micro-benchmark")
     ap.add_argument("--opt", action="append", default=[], help="library tuning option name=value (does not change results)")
     args = ap.parse_args()
 
@@ -403,6 +404,32 @@ def main():
             "gpu_launches": (2 + (1 if retries else 0)) * args.steps, "roofline": roofline, "clocks": clocks.summary(),
             "step_ms": [round(x, 3) for x in step_ms], "kernel_ms_per_step": [round(x, 3) for x in kernel_ms],
             "search_stats_per_query": {k: v / args.nq for k, v in st.items() if k not in ("max_beam", "overflow_retries")} | {"max_beam": st["max_beam"]}}
+
+    # -- K2 alone: the FastScan estimator streaming every neighbour block of the index once (one query) ---
+    if rank == 0 and not args.no_stream:
+        from cphnsw_b200 import hooks
+
+        prep = hooks.prepare_queries(ix, q_dev[:1])
+        nblk = info["n"]
+        dqp = torch.full((nblk,), 200.0, dtype=torch.float32, device="cuda")
+        outs = None
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        times = []
+        for it in range(args.warmup + args.steps):
+            ev[0].record()
+            outs = hooks.fastscan_blocks(ix, prep["uplanes"], prep["coeffs"], dqp, first_vertex=0, nblocks=nblk, want=("est", "lower"))
+            ev[1].record()
+            torch.cuda.synchronize()
+            if it >= args.warmup:
+                times.append(ev[0].elapsed_time(ev[1]))
+        del outs
+        fs_bytes = 4 * D * B + 384 + 64 * (2 if B > 1 else 1)            # per 32-code block, ids excluded
+        log(f"[bench] K2 stream times (ms): {[round(t, 3) for t in times]}")
+        fs_ms = float(np.mean(times))
+        fs_gbs = nblk * fs_bytes / (fs_ms / 1e3) / 1e9
+        line["fastscan_stream"] = {"kernel": f"fastscan_blocks_kernel<{B}> (K2, TMA-pipelined stream of all {nblk} blocks, one query, est+lower written)",
+                                   "achieved": fs_gbs, "unit": "GB/s", "peak": peak, "frac": fs_gbs / peak, "ms": fs_ms,
+                                   "algorithmic_bytes_per_block": fs_bytes, "blocks_per_s": nblk / (fs_ms / 1e3), "codes_per_s": 32 * nblk / (fs_ms / 1e3)}
 
     if rank == 0:
         ids_np = ids_dev.cpu().numpy()

@@ -7,8 +7,12 @@
 // the estimator the search kernel runs per expansion: the parity hook for integer sums and float
 // estimates, and the kernel behind the "FastScan HBM GB/s" figure (a pure stream of blocks).
 //
-// One warp per block, lane = neighbour slot; persistent grid-stride over blocks; the query's
-// bit-planes sit in shared memory per warp and are re-staged only when the block's query changes.
+// One warp per block, lane = neighbour slot.  Each warp owns a ring of NS shared-memory stages; lane 0
+// keeps NS bulk asynchronous copies (cp.async.bulk, the TMA engine) in flight, one block per stage,
+// each completing on the stage's own mbarrier, while the warp runs the popcount / epilogue work of
+// the oldest stage out of shared memory.  Persistent grid (SMs x resident CTAs), blocks strided over
+// all warps.  The query's bit-planes sit in shared memory per warp and are re-staged only when the
+// block's query changes.
 #include <float.h>
 
 #include "device_math.cuh"
@@ -16,47 +20,97 @@
 
 namespace cpb {
 
-constexpr int kFsWarps = 8;
+constexpr int kFsMaxWarps = 8;
+
+__device__ __forceinline__ uint32_t fs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fs_mbar_init(uint64_t* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fs_smem_u32(bar)));
+}
+__device__ __forceinline__ void fs_issue(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fs_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(fs_smem_u32(dst)), "l"(src), "r"(bytes), "r"(fs_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fs_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(fs_smem_u32(bar)), "r"(phase) : "memory");
+    } while (!done);
+}
 
 template <int B>
-__global__ void __launch_bounds__(kFsWarps * 32) fastscan_blocks_kernel(const DevIndex ix, const FastScanArgs a) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(kFsMaxWarps * 32) fastscan_blocks_kernel(const DevIndex ix, const FastScanArgs a,
+                                                                            uint32_t ns, uint32_t stage_bytes) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const uint32_t nch = ix.nch;
-    uint4* uqs = reinterpret_cast<uint4*>(smem_raw) + (size_t)warp * 4 * nch;
+    const size_t per_warp = (size_t)ns * stage_bytes + 64 + (size_t)nch * 64;
+    uint8_t* sm = smem_raw + (size_t)warp * ((per_warp + 127) & ~(size_t)127);
+    uint8_t* stages = sm;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sm + (size_t)ns * stage_bytes);   // ns <= 8 barriers
+    uint4* uqs = reinterpret_cast<uint4*>(sm + (size_t)ns * stage_bytes + 64);
+    const uint32_t copy_bytes = (ix.aux_off + 644u + 15u) & ~15u;
+
     const Calib& cal = ix.calib;
     uint32_t staged_q = kInvalid;
     QParams qp;
     qp.a = cal.affine_a; qp.b = cal.affine_b; qp.floor_ = cal.ip_qo_floor;
     qp.A = qp.Bc = qp.C = 0.0f; qp.slack = 0.0f;
 
-    const uint64_t stride = (uint64_t)gridDim.x * kFsWarps;
-    for (uint64_t i = (uint64_t)blockIdx.x * kFsWarps + warp; i < a.nblocks; i += stride) {
+    if (lane == 0) {
+        for (uint32_t s = 0; s < ns; ++s) fs_mbar_init(mbar + s);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+
+    const uint64_t stride = (uint64_t)gridDim.x * nwarps;
+    const uint64_t first = (uint64_t)blockIdx.x * nwarps + warp;
+    auto block_ptr = [&](uint64_t i) -> const uint8_t* {
+        const uint64_t v = a.vertex_ids ? (uint64_t)__ldg(a.vertex_ids + i) : a.first_vertex + i;
+        return ix.blocks + v * ix.block_stride;
+    };
+    // prologue: fill the ring
+    if (lane == 0)
+        for (uint32_t s = 0; s < ns; ++s) {
+            const uint64_t i = first + (uint64_t)s * stride;
+            if (i < a.nblocks) fs_issue(stages + (size_t)s * stage_bytes, block_ptr(i), copy_bytes, mbar + s);
+        }
+
+    uint32_t j = 0;
+    for (uint64_t i = first; i < a.nblocks; i += stride, ++j) {
+        const uint32_t s = j % ns, phase = (j / ns) & 1u;
         const uint32_t q = a.query_of_block ? __ldg(a.query_of_block + i) : 0u;
         if (q != staged_q) {
             __syncwarp();
             const uint4* us = reinterpret_cast<const uint4*>(a.uplanes + (size_t)q * 16 * nch);
-            for (uint32_t j = lane; j < 4 * nch; j += 32) uqs[j] = us[j];
+            for (uint32_t t = lane; t < 4 * nch; t += 32) uqs[t] = us[t];
             const float* cf = a.coeffs + (size_t)q * kCoeffStride;
             qp.A = cf[0]; qp.Bc = cf[1]; qp.C = cf[2];
             staged_q = q;
             __syncwarp();
         }
-        const uint64_t v = a.vertex_ids ? (uint64_t)__ldg(a.vertex_ids + i) : a.first_vertex + i;
-        const uint8_t* blk = ix.blocks + v * ix.block_stride;
-        const uint8_t* aux = blk + ix.aux_off;
-        const uint32_t count = __ldg(reinterpret_cast<const uint32_t*>(aux + 640));
-        const float nop = __ldg(reinterpret_cast<const float*>(aux + 128) + lane);
-        const float ipqo = __ldg(reinterpret_cast<const float*>(aux + 256) + lane);
-        const float ipcp = __ldg(reinterpret_cast<const float*>(aux + 384) + lane);
-        const uint32_t pops = __ldg(reinterpret_cast<const uint32_t*>(aux + 512) + lane);
         const float dqp = __ldg(a.dqp + i);
         int li = a.slack_level ? __ldg(a.slack_level + i) : 0;
         if (cal.num_slack > 0) { li = li < cal.num_slack - 1 ? li : cal.num_slack - 1; qp.slack = cal.slack[li < 0 ? 0 : li]; }
         else qp.slack = 0.0f;
 
+        fs_wait(mbar + s, phase);
+        const uint8_t* blk = stages + (size_t)s * stage_bytes;
+        const uint8_t* aux = blk + ix.aux_off;
+        const uint32_t count = *reinterpret_cast<const uint32_t*>(aux + 640);
+        const float nop = reinterpret_cast<const float*>(aux + 128)[lane];
+        const float ipqo = reinterpret_cast<const float*>(aux + 256)[lane];
+        const float ipcp = reinterpret_cast<const float*>(aux + 384)[lane];
+        const uint32_t pops = reinterpret_cast<const uint32_t*>(aux + 512)[lane];
         uint32_t ps[B];
-        plane_sums<B>(reinterpret_cast<const uint4*>(blk), nch, lane, uqs, ps);
+        plane_sums<B, true>(reinterpret_cast<const uint4*>(blk), nch, lane, uqs, ps);
+        __syncwarp();   // every lane is done reading this stage: refill it
+        if (lane == 0) {
+            const uint64_t nxt = i + (uint64_t)ns * stride;
+            if (nxt < a.nblocks) fs_issue(stages + (size_t)s * stage_bytes, block_ptr(nxt), copy_bytes, mbar + s);
+        }
         uint32_t nbit, msb, msb2;
         combine_planes<B>(ps, nbit, msb, msb2);
         float est, lower, msb_lower;
@@ -81,13 +135,25 @@ __global__ void __launch_bounds__(kFsWarps * 32) fastscan_blocks_kernel(const De
 
 cudaError_t launch_fastscan_blocks(const DevIndex& ix, const FastScanArgs& a, int num_sms, cudaStream_t stream) {
     if (a.nblocks == 0) return cudaSuccess;
-    const size_t smem = (size_t)kFsWarps * 64 * ix.nch;
-    uint64_t want = (a.nblocks + kFsWarps - 1) / kFsWarps;
-    const uint64_t cap = (uint64_t)num_sms * 8;
+    const uint32_t copy_bytes = (ix.aux_off + 644u + 15u) & ~15u;
+    const uint32_t stage_bytes = (copy_bytes + 127u) & ~127u;
+    // double buffering per warp and as many warps as fit: the kernel is bound by the popcount (XU) pipe,
+    // which wants many warps to stay busy, not by bytes in flight (32 warps x 2 stages per SM is ample)
+    uint32_t ns = 2;
+    const size_t per_warp = (((size_t)ns * stage_bytes + 64 + (size_t)ix.nch * 64) + 127) & ~(size_t)127;
+    int warps = (int)((200u * 1024u) / per_warp);
+    warps = warps < 1 ? 1 : (warps > kFsMaxWarps ? kFsMaxWarps : warps);
+    int ctas_per_sm = (int)((220u * 1024u) / (per_warp * warps));
+    ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 8 ? 8 : ctas_per_sm);
+    const size_t smem = per_warp * warps;
+    void (*kern)(const DevIndex, const FastScanArgs, uint32_t, uint32_t) =
+        ix.B == 1 ? fastscan_blocks_kernel<1> : ix.B == 2 ? fastscan_blocks_kernel<2> : fastscan_blocks_kernel<4>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const uint64_t want = (a.nblocks + warps - 1) / warps;
+    const uint64_t cap = (uint64_t)num_sms * ctas_per_sm;
     const int grid = (int)(want < cap ? want : cap);
-    if (ix.B == 1) fastscan_blocks_kernel<1><<<grid, kFsWarps * 32, smem, stream>>>(ix, a);
-    else if (ix.B == 2) fastscan_blocks_kernel<2><<<grid, kFsWarps * 32, smem, stream>>>(ix, a);
-    else fastscan_blocks_kernel<4><<<grid, kFsWarps * 32, smem, stream>>>(ix, a);
+    kern<<<grid, warps * 32, smem, stream>>>(ix, a, ns, stage_bytes);
     return cudaGetLastError();
 }
 
