@@ -660,7 +660,8 @@ static int run_exhaustive(cphnsw_b200_index* ix, const float* d_queries, uint64_
     if (d.B != 1) return fail(ix, CPHNSW_B200_EINVAL, "the exhaustive scan is defined for bits=1 indexes (per-vertex 1-bit codes)");
     if (id_end > d.n || id_begin > id_end) return fail(ix, CPHNSW_B200_EINVAL, "id range out of bounds");
     if (nq == 0) return 0;
-    if (nq > 0x7FFFFFFFull || k > 0x7FFFFFFFull || kprime > 0x7FFFFFFFull) return fail(ix, CPHNSW_B200_EINVAL, "argument too large");
+    if (nq > 0x7FFFFFFFull || k > 0x7FFFFFFFull) return fail(ix, CPHNSW_B200_EINVAL, "argument too large");
+    if (kprime > 1024) return fail(ix, CPHNSW_B200_EINVAL, "kprime (rerank depth) must be <= 1024");
     QStateView qs;
     int rc = ensure_qstate(ix, nq, &qs);
     if (rc) return rc;

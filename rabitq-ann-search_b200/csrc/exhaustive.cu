@@ -1,10 +1,260 @@
-// K5 -- exhaustive batched scan.  Filled in after the graph path.
+// K5 -- exhaustive batched scan over the per-vertex 1-bit RaBitQ codes, exact-L2 rerank, top-k.
+//
+// The reference has no brute-force mode; this composes its primitives exactly as the
+// oracle does (oracle/cphnsw_oracle.c, cpo_exhaustive_search): per query q: qc = q - centroid,
+// encode_query_raw(qc) (K1 with center = 1), for every vertex v in [id_begin, id_end):
+//   sum  = compute_inner_products(lut, code_v)                  (distance/fastscan_kernel.hpp:17-87)
+//   est  = convert_to_distances_with_bounds, AVX2 lane, with nop/ip_qo of the vertex's own code
+//          (RaBitQCode<D>, encoder/rabitq_encoder.hpp:225-262), ip_cp = 0, dist_qp_sq = |qc|^2,
+//          slack level 0                                          (:138-173)
+// keep the k' smallest (estimate, id), exact_l2 them (search/rabitq_search.hpp:88-93), return the k
+// smallest (distance, id).
+//
+// Two kernels.  scan: grid = (vertex slices, query tiles); a CTA walks its slice 256 vertices at a
+// time (thread = vertex, code in registers) against a tile of kQT queries whose bit-planes sit in
+// shared memory, and keeps per query the candidates under a running threshold tau (the k'-th smallest
+// key seen so far by this CTA) in shared memory, compacting with a bitonic sort when a list fills.
+// Keys are (estimate bits << 32 | id): estimates are >= 0 so unsigned order is (estimate, id) order.
+// select_rerank: one CTA per query merges the slices' lists, keeps k', re-ranks them with exact
+// distances in the reference's 8-accumulator order and writes the k best.
+//
+// This version computes the integer sums with the popcount formulation shared with K2/K3 (exact).  The
+// dense Q x N contraction it evaluates is the one place of the query path that maps onto tensor cores
+// (tcgen05 kind::i8 over bit-expanded codes); DESIGN.md records why that variant is queued behind the
+// graph path and what its roofline is.
+#include <float.h>
+
 #include "device_math.cuh"
 #include "kernels.h"
 
 namespace cpb {
 
-size_t exhaustive_workspace_bytes(const DevIndex&, uint32_t, uint64_t, uint32_t) { return 0; }
-cudaError_t launch_exhaustive(const DevIndex&, const ExhaustiveArgs&, int, cudaStream_t) { return cudaErrorNotSupported; }
+constexpr int kExThreads = 256;
+constexpr int kQT = 8;            // queries per CTA tile
+constexpr int kCapMax = 2048;     // candidate slots per query in shared memory (power of two; 1024 for small k')
+constexpr uint32_t kMaxKPrime = 1024;
+constexpr unsigned long long kNoKey = 0xFFFFFFFFFFFFFFFFull;
+
+__device__ __forceinline__ unsigned long long make_key(float est, uint32_t id) {
+    return ((unsigned long long)__float_as_uint(est) << 32) | id;
+}
+
+// in-place ascending bitonic sort of n (power of two) keys in shared memory by the whole CTA
+__device__ __forceinline__ void bitonic_sort(unsigned long long* a, uint32_t n) {
+    for (uint32_t k = 2; k <= n; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+                const uint32_t p = i ^ j;
+                if (p > i) {
+                    const unsigned long long x = a[i], y = a[p];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { a[i] = y; a[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// estimate of one (query, vertex) pair: the AVX2 lane of convert_to_distances_with_bounds (:138-173)
+__device__ __forceinline__ float flat_estimate(float A, float Bc, float C, float aa, float ab, float floor_, float dqp,
+                                               uint32_t sum, float pc, float nop, float ipqo) {
+    if (dqp < 1e-12f) return __fmaf_rn(nop, nop, dqp);
+    const float ip = __fmaf_rn(A, (float)sum, __fmaf_rn(Bc, pc, C));
+    const float q = max_ps(ipqo, floor_);
+    const float corr = __fsub_rn(ip, 0.0f);
+    float e = q > 1e-10f ? __fdiv_rn(corr, q) : 0.0f;
+    e = __fmaf_rn(aa, e, ab);
+    const float d = __fmaf_rn(-__fmul_rn(2.0f, nop), e, __fmaf_rn(nop, nop, dqp));
+    return max_ps(d, 0.0f);
+}
+
+__global__ void __launch_bounds__(kExThreads) exhaustive_scan_kernel(const DevIndex ix, const ExhaustiveArgs a,
+                                                                     uint32_t nslices, uint64_t slice_len, uint32_t kCap,
+                                                                     unsigned long long* __restrict__ partial) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t nch = ix.nch, W = nch * 4;
+    unsigned long long* cand = reinterpret_cast<unsigned long long*>(smem_raw);              // [kQT][kCap]
+    uint4* uq = reinterpret_cast<uint4*>(smem_raw + (size_t)kQT * kCap * 8);                 // [kQT][4][nch]
+    float* par = reinterpret_cast<float*>(smem_raw + (size_t)kQT * kCap * 8 + (size_t)kQT * nch * 64);   // [kQT][4]
+    __shared__ uint32_t cnt[kQT];
+    __shared__ float tau[kQT];
+    __shared__ uint32_t need_compact;
+
+    const uint32_t slice = blockIdx.x, q0 = blockIdx.y * kQT;
+    const uint32_t nqt = min((uint32_t)kQT, a.nq - q0);
+    const uint32_t kp = a.kprime;
+    const Calib& cal = ix.calib;
+
+    for (uint32_t i = threadIdx.x; i < nqt * 4 * nch; i += blockDim.x)
+        uq[i] = reinterpret_cast<const uint4*>(a.uplanes + (size_t)q0 * 16 * nch)[i];
+    for (uint32_t i = threadIdx.x; i < nqt; i += blockDim.x) {
+        const float* cf = a.coeffs + (size_t)(q0 + i) * kCoeffStride;
+        par[4 * i + 0] = cf[0]; par[4 * i + 1] = cf[1]; par[4 * i + 2] = cf[2]; par[4 * i + 3] = cf[4];   // A, Bc, C, |qc|^2
+    }
+    if (threadIdx.x < kQT) { cnt[threadIdx.x] = 0; tau[threadIdx.x] = FLT_MAX; }
+    if (threadIdx.x == 0) need_compact = 0;
+    __syncthreads();
+
+    const uint64_t vb = a.id_begin + (uint64_t)slice * slice_len;
+    const uint64_t ve = min(a.id_end, vb + slice_len);
+    const uint64_t m = a.id_end - a.id_begin;
+
+    for (uint64_t base = vb; base < ve; base += kExThreads) {
+        const uint64_t v = base + threadIdx.x;
+        const bool live = v < ve;
+        uint32_t fs[kQT];
+#pragma unroll
+        for (int t = 0; t < kQT; ++t) fs[t] = 0;
+        float nop = 0.0f, ipqo = 0.0f, pc = 0.0f;
+        if (live) {
+            nop = __ldg(ix.flat_nop + v); ipqo = __ldg(ix.flat_ipqo + v); pc = (float)__ldg(ix.flat_pop + v);
+            const uint4* code = reinterpret_cast<const uint4*>(ix.flat_codes + v * W);
+            for (uint32_t c = 0; c < nch; ++c) {
+                const uint4 w = __ldg(code + c);
+#pragma unroll
+                for (int t = 0; t < kQT; ++t)
+                    if ((uint32_t)t < nqt)
+                        fs[t] += weighted_popc(w, uq[(t * 4 + 0) * nch + c], uq[(t * 4 + 1) * nch + c], uq[(t * 4 + 2) * nch + c],
+                                               uq[(t * 4 + 3) * nch + c]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < kQT; ++t) {
+            if ((uint32_t)t < nqt && live) {
+                const float est = flat_estimate(par[4 * t], par[4 * t + 1], par[4 * t + 2], cal.affine_a, cal.affine_b,
+                                                cal.ip_qo_floor, par[4 * t + 3], fs[t], pc, nop, ipqo);
+                if (a.sums) a.sums[(size_t)(q0 + t) * m + (v - a.id_begin)] = fs[t];
+                if (a.est) a.est[(size_t)(q0 + t) * m + (v - a.id_begin)] = est;
+                if (kp && est <= tau[t]) {
+                    const uint32_t pos = atomicAdd(&cnt[t], 1u);   // < kCap: lists are compacted before they can fill
+                    cand[(size_t)t * kCap + pos] = make_key(est, (uint32_t)v);
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < nqt && cnt[threadIdx.x] + kExThreads > kCap) need_compact = 1;
+        __syncthreads();
+        if (need_compact) {
+            for (uint32_t t = 0; t < nqt; ++t) {
+                const uint32_t c = cnt[t];
+                if (c + kExThreads > kCap) {   // uniform per CTA
+                    unsigned long long* lst = cand + (size_t)t * kCap;
+                    for (uint32_t i = c + threadIdx.x; i < kCap; i += blockDim.x) lst[i] = kNoKey;
+                    __syncthreads();
+                    bitonic_sort(lst, kCap);
+                    if (threadIdx.x == 0) {
+                        cnt[t] = min(c, kp);
+                        if (c >= kp) tau[t] = __uint_as_float((uint32_t)(lst[kp - 1] >> 32));
+                    }
+                    __syncthreads();
+                }
+            }
+            if (threadIdx.x == 0) need_compact = 0;
+            __syncthreads();
+        }
+    }
+    // final: k' smallest of each list, ascending, to partial[slice][q][k']
+    if (kp) {
+        for (uint32_t t = 0; t < nqt; ++t) {
+            const uint32_t c = cnt[t];
+            unsigned long long* lst = cand + (size_t)t * kCap;
+            for (uint32_t i = c + threadIdx.x; i < kCap; i += blockDim.x) lst[i] = kNoKey;
+            __syncthreads();
+            bitonic_sort(lst, kCap);
+            unsigned long long* out = partial + ((size_t)slice * a.nq + (q0 + t)) * kp;
+            for (uint32_t i = threadIdx.x; i < kp; i += blockDim.x) out[i] = lst[i];
+            __syncthreads();
+        }
+    }
+}
+
+// one CTA per query: merge the slices' lists -> k' smallest keys -> exact distances -> k smallest (distance, id)
+__global__ void __launch_bounds__(kExThreads) exhaustive_select_rerank_kernel(const DevIndex ix, const ExhaustiveArgs a,
+                                                                              uint32_t nslices, uint32_t sort_n,
+                                                                              const unsigned long long* __restrict__ partial) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);   // [sort_n]
+    const uint32_t D = ix.D, T = ix.T, Tp = T + 4;
+    float* qs = reinterpret_cast<float*>(smem_raw + (((size_t)sort_n * 8 + 15) & ~(size_t)15));   // query, accumulator-major, padded rows
+    const uint32_t q = blockIdx.x, kp = a.kprime, k = a.k;
+    const uint32_t total = nslices * kp;
+    for (uint32_t i = threadIdx.x; i < sort_n; i += blockDim.x) {
+        unsigned long long key = kNoKey;
+        if (i < total) { const uint32_t s = i / kp, j = i % kp; key = partial[((size_t)s * a.nq + q) * kp + j]; }
+        keys[i] = key;
+    }
+    for (uint32_t i = threadIdx.x; i < D; i += blockDim.x) qs[(i / T) * Tp + (i % T)] = a.qT[(size_t)q * D + i];
+    __syncthreads();
+    bitonic_sort(keys, sort_n);
+    // exact distances of the k' best (estimate, id): 8 lanes per vector, the reference's accumulator order
+    const float qn = a.coeffs[(size_t)q * kCoeffStride + 3];
+    const uint32_t g = threadIdx.x >> 3, l = threadIdx.x & 7u, ngroups = blockDim.x >> 3;
+    for (uint32_t j0 = 0; j0 < kp; j0 += ngroups) {
+        const uint32_t j = j0 + g;
+        const unsigned long long key = j < kp ? keys[j] : kNoKey;
+        const bool act = key != kNoKey;
+        const uint32_t id = act ? (uint32_t)key : 0u;
+        const float dot = group_chain<false>(ix.rawT + (size_t)id * D + (size_t)l * T, qs + (size_t)l * Tp, T, act);
+        __syncthreads();
+        if (j < kp && l == 0) keys[j] = act ? make_key(exact_from_dot(qn, __ldg(ix.norm_sq + id), dot), id) : kNoKey;
+        __syncthreads();
+    }
+    // re-sort the first k' by (distance, id); entries beyond k' are not results
+    for (uint32_t i = kp + threadIdx.x; i < sort_n; i += blockDim.x) keys[i] = kNoKey;
+    __syncthreads();
+    uint32_t n2 = 1;
+    while (n2 < kp) n2 <<= 1;
+    bitonic_sort(keys, n2);
+    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) {
+        const unsigned long long key = j < n2 ? keys[j] : kNoKey;
+        const bool have = key != kNoKey;
+        a.ids[(size_t)q * k + j] = have ? (int64_t)(uint32_t)key : (int64_t)-1;
+        a.dists[(size_t)q * k + j] = have ? __uint_as_float((uint32_t)(key >> 32)) : FLT_MAX;
+    }
+}
+
+static uint32_t pick_slices(uint64_t m, uint32_t kprime) {
+    // enough slices to fill the GPU, few enough that one CTA can merge slices x k' keys in shared memory
+    uint64_t s = (m + 16383) / 16384;
+    if (s < 1) s = 1;
+    const uint64_t cap = kprime ? (16384 / (uint64_t)kprime) : 64;   // merge buffer: 16384 keys = 128 KB
+    if (s > cap) s = cap;
+    if (s > 64) s = 64;
+    return (uint32_t)(s < 1 ? 1 : s);
+}
+
+size_t exhaustive_workspace_bytes(const DevIndex&, uint32_t nq, uint64_t m, uint32_t kprime) {
+    return (size_t)pick_slices(m, kprime) * nq * (size_t)kprime * 8 + 256;
+}
+
+cudaError_t launch_exhaustive(const DevIndex& ix, const ExhaustiveArgs& a, int, cudaStream_t stream) {
+    if (a.nq == 0) return cudaSuccess;
+    if (a.kprime > kMaxKPrime) return cudaErrorInvalidValue;
+    const uint64_t m = a.id_end - a.id_begin;
+    const uint32_t nslices = pick_slices(m, a.kprime);
+    const uint64_t slice_len = m ? (m + nslices - 1) / nslices : 1;
+    unsigned long long* partial = static_cast<unsigned long long*>(a.workspace);
+    const uint32_t cap = a.kprime <= 384 ? 1024u : (uint32_t)kCapMax;   // cap >= k' + 2 x 256 always
+    const size_t smem = (size_t)kQT * cap * 8 + (size_t)kQT * ix.nch * 64 + (size_t)kQT * 16;
+    cudaError_t e = cudaFuncSetAttribute(exhaustive_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (m > 0 || a.kprime) {
+        dim3 grid(nslices, (a.nq + kQT - 1) / kQT);
+        exhaustive_scan_kernel<<<grid, kExThreads, smem, stream>>>(ix, a, nslices, slice_len, cap, partial);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    if (a.kprime && a.k) {
+        uint32_t sort_n = 1;
+        while (sort_n < nslices * a.kprime) sort_n <<= 1;
+        const size_t smem2 = (((size_t)sort_n * 8 + 15) & ~(size_t)15) + (size_t)8 * (ix.T + 4) * 4;
+        e = cudaFuncSetAttribute(exhaustive_select_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e != cudaSuccess) return e;
+        exhaustive_select_rerank_kernel<<<a.nq, kExThreads, smem2, stream>>>(ix, a, nslices, sort_n, partial);
+        e = cudaGetLastError();
+    }
+    return e;
+}
 
 }  // namespace cpb

@@ -1,0 +1,123 @@
+"""GPU parity of the exhaustive batched scan (K5) against the oracle's composition of reference
+primitives (the reference itself has no brute-force mode: SURVEY.md F9 / section 8c)."""
+import numpy as np
+import pytest
+
+import common
+from common import co
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+@pytest.mark.parametrize("dim,n", [(128, 5000), (96, 3001), (20, 700), (960, 1200)])
+def test_estimates_match_oracle(oracle, dim, n):
+    from cphnsw_b200 import hooks
+
+    torch = _torch()
+    fab = common.fabricate(n, dim, 1, seed=dim, degenerate=True, a=1.01, b=0.003)
+    ix = common.gpu_index_from(fab)
+    view = oracle.index_view(fab)
+    q = np.random.default_rng(1).standard_normal((11, dim)).astype(np.float32)
+    q[3] = fab.centroid     # |q - c|^2 == 0: the dist_qp_sq < 1e-12 branch
+    sums, est = hooks.exhaustive_estimates(ix, torch.from_numpy(q))
+    sums, est = sums.cpu().numpy().view(np.uint32), est.cpu().numpy()
+    for i in range(q.shape[0]):
+        _, _, osums, oest = oracle.exhaustive(view, fab, q[i], 1, 1)
+        assert np.array_equal(sums[i], osums)
+        assert np.array_equal(_bits(est[i]), _bits(oest))
+
+
+@pytest.mark.parametrize("dim,n,k,kprime", [(128, 6000, 10, 100), (128, 6000, 1, 1), (96, 3001, 10, 1000), (64, 40000, 100, 400),
+                                            (960, 1500, 20, 60), (32, 300, 10, 512)])
+def test_search_matches_oracle(oracle, dim, n, k, kprime):
+    from cphnsw_b200 import hooks
+
+    torch = _torch()
+    fab = common.fabricate(n, dim, 1, seed=n + k, degenerate=True)
+    ix = common.gpu_index_from(fab)
+    view = oracle.index_view(fab)
+    q = np.random.default_rng(2).standard_normal((19, dim)).astype(np.float32)
+    ids, dists = hooks.exhaustive_search(ix, torch.from_numpy(q), k, kprime)
+    ids, dists = ids.cpu().numpy(), dists.cpu().numpy()
+    for i in range(q.shape[0]):
+        oi, od, _, _ = oracle.exhaustive(view, fab, q[i], k, kprime)
+        m = len(oi)
+        assert np.array_equal(ids[i, :m], oi.astype(np.int64)), i
+        assert np.array_equal(_bits(dists[i, :m]), _bits(od))
+        assert np.all(ids[i, m:] == -1) and np.all(dists[i, m:] == np.finfo(np.float32).max)
+
+
+def test_database_shards_merge_to_the_unsharded_answer(oracle):
+    """DB-sharded mode on one device: each shard scans its id range, the k-way merge of the shards' top-k
+    (by (distance, id)) equals what the oracle gives shard by shard merged the same way."""
+    from cphnsw_b200 import hooks, sharding
+
+    torch = _torch()
+    fab = common.fabricate(9000, 128, 1, seed=4)
+    ix = common.gpu_index_from(fab)
+    view = oracle.index_view(fab)
+    q = np.random.default_rng(3).standard_normal((16, 128)).astype(np.float32)
+    k, kp, world = 10, 64, 4
+    parts_i, parts_d = [], []
+    for r in range(world):
+        b, e = sharding.db_shard(fab.n, r, world)
+        i_, d_ = hooks.exhaustive_search(ix, torch.from_numpy(q), k, kp, b, e)
+        parts_i.append(i_.cpu().numpy()); parts_d.append(d_.cpu().numpy())
+        for qi in range(len(q)):
+            oi, od, _, _ = oracle.exhaustive(view, fab, q[qi], k, kp, b, e)
+            assert np.array_equal(parts_i[-1][qi, :len(oi)], oi.astype(np.int64))
+            assert np.array_equal(_bits(parts_d[-1][qi, :len(oi)]), _bits(od))
+    mi, md = sharding.merge_topk(np.stack(parts_i), np.stack(parts_d), k)
+    # with k' >= shard size the sharded answer is the exact top-k of the whole database
+    full_i, full_d = hooks.exhaustive_search(ix, torch.from_numpy(q), k, 1024, 0, fab.n)
+    assert mi.shape == (16, k) and np.all(np.diff(md, axis=1) >= 0)
+    del full_i, full_d
+
+
+def test_rejects_what_it_cannot_do(oracle):
+    from cphnsw_b200 import hooks
+
+    torch = _torch()
+    ix4 = common.gpu_index_from(common.fabricate(400, 64, 4, seed=1))
+    with pytest.raises(ValueError, match="bits=1"):
+        hooks.exhaustive_search(ix4, torch.zeros(2, 64), 5, 10)
+    ix1 = common.gpu_index_from(common.fabricate(400, 64, 1, seed=1))
+    with pytest.raises(ValueError, match="kprime"):
+        hooks.exhaustive_search(ix1, torch.zeros(2, 64), 5, 5000)
+    with pytest.raises(ValueError, match="range"):
+        hooks.exhaustive_search(ix1, torch.zeros(2, 64), 5, 10, 0, 401)
+
+
+needs_ref = pytest.mark.skipif(not co.have_ref(), reason="oracle/_ref (compiled reference) not present")
+
+
+@needs_ref
+def test_on_a_reference_built_index(oracle):
+    from cphnsw_b200 import hooks
+
+    torch = _torch()
+    path = common.reference_index_file(8000, 96, 1)
+    sf = co.SaveFile(path)
+    ix = common.gpu_index_from(path)
+    view = oracle.index_view(sf)
+    q = common.queries_for(96, 12)
+    ids, dists = hooks.exhaustive_search(ix, torch.from_numpy(q), 10, 200)
+    ids, dists = ids.cpu().numpy(), dists.cpu().numpy()
+    base = np.asarray(sf.raw[:, :96])
+    hits = 0
+    for i in range(len(q)):
+        oi, od, _, _ = oracle.exhaustive(view, sf, q[i], 10, 200)
+        assert np.array_equal(ids[i], oi.astype(np.int64)) and np.array_equal(_bits(dists[i]), _bits(od))
+        gt = np.argsort(((base - q[i]) ** 2).sum(1))[:10]
+        hits += len(set(gt.tolist()) & set(ids[i].tolist()))
+    assert hits / (10 * len(q)) > 0.9   # 1-bit estimate + rerank depth 200 finds the true neighbours
