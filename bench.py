@@ -75,7 +75,8 @@ def obtain_index(args, rank, world):
         synthetic(args.n, args.dim, args.seed, args.clusters).tofile(vec)
         t = time.time()
         tmp = str(path) + ".part"
-        subprocess.run([str(refbuild), str(args.dim), str(args.bits), str(args.n), str(vec), tmp], check=True, stdout=sys.stderr)
+        env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count()))   # torchrun pins OMP_NUM_THREADS=1 for its workers
+        subprocess.run([str(refbuild), str(args.dim), str(args.bits), str(args.n), str(vec), tmp], check=True, stdout=sys.stderr, env=env)
         os.replace(tmp, path)
         vec.unlink()
         log(f"[bench] index built in {time.time() - t:.0f} s")
@@ -186,6 +187,9 @@ class ClockSampler:
 # reference arm / CPU baseline: the unmodified reference's search_batch on the host cores
 # ---------------------------------------------------------------------------------------------------
 def reference_module():
+    # all host cores for the reference's OpenMP loop (src/bindings.cpp:196-200), also under torchrun, which
+    # exports OMP_NUM_THREADS=1 to its workers; must be set before libgomp initialises
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
     ref_dir = ROOT / "oracle" / "_ref"
     if not any((ref_dir / "cphnsw").glob("_core*.so")):
         return None
@@ -231,7 +235,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--nvec", "--n", dest="n", type=int, default=1_000_000)
     ap.add_argument("--dim", type=int, default=128)
     ap.add_argument("--bits", type=int, default=4)
     ap.add_argument("--nq", type=int, default=10_000)

@@ -2,7 +2,7 @@
 # Quick evaluation on the GPU box: parity tests, bench at N (default 250000), instruction count of the search kernel.
 N=${1:-250000}
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-CMD="python bench.py --n $N --steps 3 --warmup 1 --no-cpu-baseline --no-recall"
+CMD="python bench.py --nvec $N --steps 3 --warmup 1 --no-cpu-baseline --no-recall"
 $CMD 2>/dev/null | tee gpurun_out/quick_plain.json | python profiles/pj.py && \
 ncu --metrics smsp__inst_executed.sum,gpu__time_duration.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum \
     --clock-control none -k regex:search_kernel -s 2 -c 1 --csv --log-file gpurun_out/quick_metrics.csv $CMD > /dev/null 2>&1
