@@ -450,9 +450,19 @@ static int run_search(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq
     a.nq = (uint32_t)nq; a.query_list = nullptr; a.k = k; a.kout = (uint32_t)k_user;
     a.ids = d_ids; a.dists = d_dists; a.qT = qs.qT; a.uplanes = qs.uplanes; a.coeffs = qs.coeffs;
     a.entry_out = d_entry_out;
-    uint32_t cap = (uint32_t)std::min<uint64_t>((uint64_t)ix->beam_capacity, d.n + 1);
-    layout(cap, a);
+    // frontier arena per slot: the option if set, else as much as an 8 GiB (or an eighth of free HBM) budget
+    // gives every slot -- a frontier can hold at most n entries, and re-running an overflowed query
+    // throws its first attempt away, so be generous where memory allows (1-bit indexes reach 40k+)
     const size_t slots = (size_t)ctas * warps;
+    uint64_t cap64 = (uint64_t)ix->beam_capacity;
+    if (cap64 == 0) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const size_t budget = std::min<size_t>((size_t)8 << 30, (free_b + ix->scratch_bytes) / 8);
+        cap64 = std::max<uint64_t>(4096, budget / (slots * 16));
+    }
+    uint32_t cap = (uint32_t)std::min<uint64_t>(cap64, d.n + 1);
+    layout(cap, a);
     const size_t list_bytes = ((size_t)nq * 4 + 255) & ~(size_t)255;
     rc = ensure_buffer(ix, &ix->scratch, &ix->scratch_bytes, list_bytes + slots * a.slot_stride, false);
     if (rc) return rc;

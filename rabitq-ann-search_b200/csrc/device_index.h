@@ -99,7 +99,7 @@ struct cphnsw_b200_index {
     // options (do not change results)
     int64_t warps_per_cta = 8;
     int64_t ctas_per_sm = 4;
-    int64_t beam_capacity = 1 << 15;  // frontier entries per in-flight query (first attempt)
+    int64_t beam_capacity = 0;        // frontier entries per in-flight query (first attempt); 0 = sized from free HBM
     int64_t collect_stats = 0;        // per-batch counters (costs registers: off on the fast path)
     // scratch, grown on demand
     void* scratch = nullptr;
