@@ -106,18 +106,20 @@ int ensure_buffer(cphnsw_b200_index* ix, void** buf, size_t* have, size_t want, 
     return 0;
 }
 
-struct QStateView { float* qT; uint32_t* uplanes; float* coeffs; };
+struct QStateView { float* qT; uint32_t* uplanes; float* coeffs; uint8_t* ubytes; };
 
 int ensure_qstate(cphnsw_b200_index* ix, uint64_t nq, QStateView* v) {
     const DevIndex& d = ix->dev;
     const size_t qT = (size_t)nq * d.D * 4, up = (size_t)nq * 16 * d.nch * 4, co = (size_t)nq * kCoeffStride * 4;
-    const size_t a = (qT + 255) & ~(size_t)255, b = (up + 255) & ~(size_t)255;
-    int rc = ensure_buffer(ix, &ix->qstate, &ix->qstate_bytes, a + b + co + 256, false);
+    const size_t a = (qT + 255) & ~(size_t)255, b = (up + 255) & ~(size_t)255, c = (co + 255) & ~(size_t)255;
+    const size_t ub = (size_t)nq * d.nch * 128;
+    int rc = ensure_buffer(ix, &ix->qstate, &ix->qstate_bytes, a + b + c + ub + 256, false);
     if (rc) return rc;
     uint8_t* p = static_cast<uint8_t*>(ix->qstate);
     v->qT = reinterpret_cast<float*>(p);
     v->uplanes = reinterpret_cast<uint32_t*>(p + a);
     v->coeffs = reinterpret_cast<float*>(p + a + b);
+    v->ubytes = p + a + b + c;
     return 0;
 }
 
@@ -186,6 +188,7 @@ int cphnsw_b200_set_option(cphnsw_b200_index* ix, const char* name, int64_t valu
     if (n == "warps_per_cta") { if (value < 1 || value > 8) return fail(ix, CPHNSW_B200_EINVAL, "warps_per_cta must be 1..8"); ix->warps_per_cta = value; }
     else if (n == "ctas_per_sm") { if (value < 1 || value > 32) return fail(ix, CPHNSW_B200_EINVAL, "ctas_per_sm must be 1..32"); ix->ctas_per_sm = value; }
     else if (n == "collect_stats") ix->collect_stats = value ? 1 : 0;
+    else if (n == "exhaustive_tensor_cores") ix->exhaustive_tensor_cores = value ? 1 : 0;
     else if (n == "beam_capacity") { if (value < 64) return fail(ix, CPHNSW_B200_EINVAL, "beam_capacity must be >= 64"); ix->beam_capacity = value; }
     else return fail(ix, CPHNSW_B200_EINVAL, "unknown option " + n);
     return 0;
@@ -676,10 +679,12 @@ static int run_exhaustive(cphnsw_b200_index* ix, const float* d_queries, uint64_
     int rc = ensure_qstate(ix, nq, &qs);
     if (rc) return rc;
     PrepOut po{};
-    po.coeffs = qs.coeffs; po.uplanes = qs.uplanes; po.qT = qs.qT;
+    po.coeffs = qs.coeffs; po.uplanes = qs.uplanes; po.qT = qs.qT; po.ubytes = qs.ubytes;
+    CUDA_TRY(ix, cudaMemsetAsync(qs.ubytes, 0, (size_t)nq * d.nch * 128, st));   // padded dimensions carry 0
     CUDA_TRY(ix, launch_query_prep(d, d_queries, (uint32_t)nq, 1, po, st));
     ExhaustiveArgs a{};
-    a.uplanes = qs.uplanes; a.coeffs = qs.coeffs; a.qT = qs.qT; a.nq = (uint32_t)nq;
+    a.uplanes = qs.uplanes; a.coeffs = qs.coeffs; a.qT = qs.qT; a.ubytes = qs.ubytes; a.nq = (uint32_t)nq;
+    a.use_tensor_cores = ix->exhaustive_tensor_cores ? 1 : 0;
     a.id_begin = id_begin; a.id_end = id_end; a.k = (uint32_t)k; a.kprime = (uint32_t)kprime;
     a.sums = d_sums; a.est = d_est; a.ids = d_ids; a.dists = d_dists;
     const size_t wb = exhaustive_workspace_bytes(d, (uint32_t)nq, id_end - id_begin, (uint32_t)kprime);

@@ -101,6 +101,7 @@ struct cphnsw_b200_index {
     int64_t ctas_per_sm = 4;
     int64_t beam_capacity = 0;        // frontier entries per in-flight query (first attempt); 0 = sized from free HBM
     int64_t collect_stats = 0;        // per-batch counters (costs registers: off on the fast path)
+    int64_t exhaustive_tensor_cores = 1;  // K5 scan on tcgen05 where applicable (0: popcount form)
     // scratch, grown on demand
     void* scratch = nullptr;
     size_t scratch_bytes = 0;

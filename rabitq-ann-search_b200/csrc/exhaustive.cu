@@ -22,52 +22,9 @@
 // dense Q x N contraction it evaluates is the one place of the query path that maps onto tensor cores
 // (tcgen05 kind::i8 over bit-expanded codes); DESIGN.md records why that variant is queued behind the
 // graph path and what its roofline is.
-#include <float.h>
-
-#include "device_math.cuh"
-#include "kernels.h"
+#include "exhaustive_common.cuh"
 
 namespace cpb {
-
-constexpr int kExThreads = 256;
-constexpr int kQT = 8;            // queries per CTA tile
-constexpr int kCapMax = 2048;     // candidate slots per query in shared memory (power of two; 1024 for small k')
-constexpr uint32_t kMaxKPrime = 1024;
-constexpr unsigned long long kNoKey = 0xFFFFFFFFFFFFFFFFull;
-
-__device__ __forceinline__ unsigned long long make_key(float est, uint32_t id) {
-    return ((unsigned long long)__float_as_uint(est) << 32) | id;
-}
-
-// in-place ascending bitonic sort of n (power of two) keys in shared memory by the whole CTA
-__device__ __forceinline__ void bitonic_sort(unsigned long long* a, uint32_t n) {
-    for (uint32_t k = 2; k <= n; k <<= 1) {
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-                const uint32_t p = i ^ j;
-                if (p > i) {
-                    const unsigned long long x = a[i], y = a[p];
-                    const bool up = (i & k) == 0;
-                    if ((x > y) == up) { a[i] = y; a[p] = x; }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
-// estimate of one (query, vertex) pair: the AVX2 lane of convert_to_distances_with_bounds (:138-173)
-__device__ __forceinline__ float flat_estimate(float A, float Bc, float C, float aa, float ab, float floor_, float dqp,
-                                               uint32_t sum, float pc, float nop, float ipqo) {
-    if (dqp < 1e-12f) return __fmaf_rn(nop, nop, dqp);
-    const float ip = __fmaf_rn(A, (float)sum, __fmaf_rn(Bc, pc, C));
-    const float q = max_ps(ipqo, floor_);
-    const float corr = __fsub_rn(ip, 0.0f);
-    float e = q > 1e-10f ? __fdiv_rn(corr, q) : 0.0f;
-    e = __fmaf_rn(aa, e, ab);
-    const float d = __fmaf_rn(-__fmul_rn(2.0f, nop), e, __fmaf_rn(nop, nop, dqp));
-    return max_ps(d, 0.0f);
-}
 
 __global__ void __launch_bounds__(kExThreads) exhaustive_scan_kernel(const DevIndex ix, const ExhaustiveArgs a,
                                                                      uint32_t nslices, uint64_t slice_len, uint32_t kCap,
@@ -106,9 +63,10 @@ __global__ void __launch_bounds__(kExThreads) exhaustive_scan_kernel(const DevIn
         uint32_t fs[kQT];
 #pragma unroll
         for (int t = 0; t < kQT; ++t) fs[t] = 0;
-        float nop = 0.0f, ipqo = 0.0f, pc = 0.0f;
+        float nop = 0.0f, ipqo = 0.0f, pc = 0.0f, rq = 0.0f;
         if (live) {
             nop = __ldg(ix.flat_nop + v); ipqo = __ldg(ix.flat_ipqo + v); pc = (float)__ldg(ix.flat_pop + v);
+            { const float qq = max_ps(ipqo, cal.ip_qo_floor); rq = qq > 1e-10f ? __frcp_rn(qq) : 0.0f; }
             const uint4* code = reinterpret_cast<const uint4*>(ix.flat_codes + v * W);
             for (uint32_t c = 0; c < nch; ++c) {
                 const uint4 w = __ldg(code + c);
@@ -122,13 +80,20 @@ __global__ void __launch_bounds__(kExThreads) exhaustive_scan_kernel(const DevIn
 #pragma unroll
         for (int t = 0; t < kQT; ++t) {
             if ((uint32_t)t < nqt && live) {
-                const float est = flat_estimate(par[4 * t], par[4 * t + 1], par[4 * t + 2], cal.affine_a, cal.affine_b,
-                                                cal.ip_qo_floor, par[4 * t + 3], fs[t], pc, nop, ipqo);
-                if (a.sums) a.sums[(size_t)(q0 + t) * m + (v - a.id_begin)] = fs[t];
-                if (a.est) a.est[(size_t)(q0 + t) * m + (v - a.id_begin)] = est;
-                if (kp && est <= tau[t]) {
-                    const uint32_t pos = atomicAdd(&cnt[t], 1u);   // < kCap: lists are compacted before they can fill
-                    cand[(size_t)t * kCap + pos] = make_key(est, (uint32_t)v);
+                const bool dense = a.sums || a.est;
+                // (dist_qp_sq < 1e-12 takes another formula: no screen there; q <= 1e-10 makes the estimate
+                //  nop^2 + dqp - 2 nop b, which the screen reproduces with rq = 0)
+                if (dense || par[4 * t + 3] < 1e-12f ||
+                    (kp && flat_screen(par[4 * t], par[4 * t + 1], par[4 * t + 2], cal.affine_a, cal.affine_b, par[4 * t + 3], fs[t],
+                                       pc, nop, rq, tau[t]))) {
+                    const float est = flat_estimate(par[4 * t], par[4 * t + 1], par[4 * t + 2], cal.affine_a, cal.affine_b,
+                                                    cal.ip_qo_floor, par[4 * t + 3], fs[t], pc, nop, ipqo);
+                    if (a.sums) a.sums[(size_t)(q0 + t) * m + (v - a.id_begin)] = fs[t];
+                    if (a.est) a.est[(size_t)(q0 + t) * m + (v - a.id_begin)] = est;
+                    if (kp && est <= tau[t]) {
+                        const uint32_t pos = atomicAdd(&cnt[t], 1u);   // < capacity: lists are compacted before they can fill
+                        cand[(size_t)t * kCap + pos] = make_key(est, (uint32_t)v);
+                    }
                 }
             }
         }
@@ -214,32 +179,39 @@ __global__ void __launch_bounds__(kExThreads) exhaustive_select_rerank_kernel(co
     }
 }
 
-static uint32_t pick_slices(uint64_t m, uint32_t kprime) {
-    // enough slices to fill the GPU, few enough that one CTA can merge slices x k' keys in shared memory
-    uint64_t s = (m + 16383) / 16384;
-    if (s < 1) s = 1;
-    const uint64_t cap = kprime ? (16384 / (uint64_t)kprime) : 64;   // merge buffer: 16384 keys = 128 KB
+// Vertex slices per query tile.  Every (slice, query tile) CTA pays a fixed price in list compactions and a
+// final sort, so slices should be long (>= 64 K vertices) -- but the grid still has to fill the GPU when there
+// are few queries, and one CTA must be able to merge slices x k' keys in shared memory (16 K keys).
+static uint32_t pick_slices(uint64_t m, uint32_t kprime, uint32_t nq, int num_sms) {
+    const uint64_t qtiles = (nq + kQT - 1) / kQT;
+    uint64_t s = ((uint64_t)8 * num_sms + qtiles - 1) / qtiles;          // enough CTAs for ~8 per SM
+    const uint64_t by_len = (m + 4095) / 4096;                            // never shorter than 4 K vertices
+    if (s > by_len) s = by_len;
+    const uint64_t cap = kprime ? (16384 / (uint64_t)kprime) : 64;
     if (s > cap) s = cap;
     if (s > 64) s = 64;
     return (uint32_t)(s < 1 ? 1 : s);
 }
 
 size_t exhaustive_workspace_bytes(const DevIndex&, uint32_t nq, uint64_t m, uint32_t kprime) {
-    return (size_t)pick_slices(m, kprime) * nq * (size_t)kprime * 8 + 256;
+    return (size_t)64 * nq * (size_t)kprime * 8 + 256;   // upper bound over pick_slices()
 }
 
-cudaError_t launch_exhaustive(const DevIndex& ix, const ExhaustiveArgs& a, int, cudaStream_t stream) {
+cudaError_t launch_exhaustive(const DevIndex& ix, const ExhaustiveArgs& a, int num_sms, cudaStream_t stream) {
     if (a.nq == 0) return cudaSuccess;
     if (a.kprime > kMaxKPrime) return cudaErrorInvalidValue;
     const uint64_t m = a.id_end - a.id_begin;
-    const uint32_t nslices = pick_slices(m, a.kprime);
+    const uint32_t nslices = pick_slices(m, a.kprime, a.nq, num_sms);
     const uint64_t slice_len = m ? (m + nslices - 1) / nslices : 1;
     unsigned long long* partial = static_cast<unsigned long long*>(a.workspace);
     const uint32_t cap = a.kprime <= 384 ? 1024u : (uint32_t)kCapMax;   // cap >= k' + 2 x 256 always
     const size_t smem = (size_t)kQT * cap * 8 + (size_t)kQT * ix.nch * 64 + (size_t)kQT * 16;
     cudaError_t e = cudaFuncSetAttribute(exhaustive_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    if (m > 0 || a.kprime) {
+    if (a.use_tensor_cores && a.ubytes && exhaustive_tc_applicable(ix, a.kprime)) {
+        e = launch_exhaustive_scan_tc(ix, a, nslices, slice_len, a.ubytes, partial, stream);
+        if (e != cudaSuccess) return e;
+    } else if (m > 0 || a.kprime) {
         dim3 grid(nslices, (a.nq + kQT - 1) / kQT);
         exhaustive_scan_kernel<<<grid, kExThreads, smem, stream>>>(ix, a, nslices, slice_len, cap, partial);
         e = cudaGetLastError();

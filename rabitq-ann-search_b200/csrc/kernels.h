@@ -16,6 +16,7 @@ struct PrepOut {
     float* rotated;     // [nq][D]
     uint32_t* uplanes;  // [nq][4][nch*4]
     float* qT;          // [nq][D] accumulator-major padded raw query
+    uint8_t* ubytes;    // [nq][nch*128] the 4-bit query values, one byte per dimension (tensor-core operand of K5)
 };
 cudaError_t launch_query_prep(const DevIndex& ix, const float* d_queries, uint32_t nq, int center,
                               const PrepOut& out, cudaStream_t stream);
@@ -76,14 +77,19 @@ cudaError_t launch_relayout_raw(const DevIndex& ix, const float* d_raw, uint64_t
 
 // ---- K5 exhaustive scan (exhaustive.cu) ---------------------------------------------------------
 struct ExhaustiveArgs {
-    const uint32_t* uplanes; const float* coeffs; const float* qT;
+    const uint32_t* uplanes; const float* coeffs; const float* qT; const uint8_t* ubytes;
     uint32_t nq; uint64_t id_begin, id_end;
     uint32_t k, kprime;
     uint32_t* sums; float* est;       // optional dense outputs [nq][id_end-id_begin]
     int64_t* ids; float* dists;       // [nq][k]
     void* workspace; size_t workspace_bytes;
+    int use_tensor_cores;             // 1: tcgen05 scan where applicable, 0: popcount scan
 };
 size_t exhaustive_workspace_bytes(const DevIndex& ix, uint32_t nq, uint64_t m, uint32_t kprime);
 cudaError_t launch_exhaustive(const DevIndex& ix, const ExhaustiveArgs& a, int num_sms, cudaStream_t stream);
+// tensor-core form of the scan stage (exhaustive_tc.cu)
+bool exhaustive_tc_applicable(const DevIndex& ix, uint32_t kprime);
+cudaError_t launch_exhaustive_scan_tc(const DevIndex& ix, const ExhaustiveArgs& a, uint32_t nslices, uint64_t slice_len,
+                                      const uint8_t* ubytes, unsigned long long* partial, cudaStream_t stream);
 
 }  // namespace cpb

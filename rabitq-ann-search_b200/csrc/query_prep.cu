@@ -97,6 +97,7 @@ query_prep_kernel(DevIndex ix, const float* __restrict__ queries, uint32_t nq, i
             u8[i] = (uint8_t)u;
             usum += (uint32_t)u;
         }
+        if (out.ubytes) out.ubytes[(size_t)q * nch * 128 + i] = (uint8_t)u;
         if (out.uplanes) {   // word i0/32 of plane t = bit t of u over these 32 dims
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
