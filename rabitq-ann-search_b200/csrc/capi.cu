@@ -63,6 +63,7 @@ void release_index(cphnsw_b200_index* ix) {
     ix->device_bytes = 0;
     ix->loaded = false;
     ix->dev = DevIndex{};
+    ix->frontier_budget = 0;
     // the bitmap arena is laid out for one n
     if (ix->bitmaps) { cudaFree(ix->bitmaps); ix->bitmaps = nullptr; ix->bitmaps_bytes = 0; }
 }
@@ -459,10 +460,12 @@ static int run_search(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq
     const size_t slots = (size_t)ctas * warps;
     uint64_t cap64 = (uint64_t)ix->beam_capacity;
     if (cap64 == 0) {
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        const size_t budget = std::min<size_t>((size_t)8 << 30, (free_b + ix->scratch_bytes) / 8);
-        cap64 = std::max<uint64_t>(4096, budget / (slots * 16));
+        if (ix->frontier_budget == 0) {   // once per index: the answer must not drift from call to call
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            ix->frontier_budget = std::min<size_t>((size_t)8 << 30, (free_b + ix->scratch_bytes) / 8);
+        }
+        cap64 = std::max<uint64_t>(4096, ix->frontier_budget / (slots * 16));
     }
     uint32_t cap = (uint32_t)std::min<uint64_t>(cap64, d.n + 1);
     layout(cap, a);

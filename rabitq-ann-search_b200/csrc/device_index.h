@@ -105,6 +105,7 @@ struct cphnsw_b200_index {
     // scratch, grown on demand
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    size_t frontier_budget = 0;  // bytes of HBM the frontier arenas may take (fixed when first needed)
     void* bitmaps = nullptr;   // zero between searches; slot i at i * bitmap_words
     size_t bitmaps_bytes = 0;
     void* qstate = nullptr;

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kFsMaxWarps * 32) fastscan_blocks_kernel(const
             convert_1bit(qp, nbit, nop, ipqo, ipcp, pops & 0xFFFFu, lane, count, dqp, sq, est, lower);
             msb_lower = lower;
         } else {
-            msb_lower = convert_msb<B>(qp, msb2, nop, ipqo, ipcp, pops & 0xFFFFu, dqp, sq);
+            msb_lower = a.msb_lower ? convert_msb<B>(qp, msb2, nop, ipqo, ipcp, pops & 0xFFFFu, dqp, sq) : 0.0f;   // only when asked for
             convert_nbit<B>(qp, nbit, msb, nop, ipqo, ipcp, pops & 0xFFFFu, pops >> 16, lane, count, dqp, sq, est, lower);
         }
         if (lane >= count) { est = FLT_MAX; lower = FLT_MAX; msb_lower = FLT_MAX; }

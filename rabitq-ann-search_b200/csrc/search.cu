@@ -456,6 +456,10 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             uint32_t old = 0xFFFFFFFFu;
             if (leader) old = atomicOr(&w.bitmap[nid >> 5], 1u << (nid & 31));
 
+            // plane-0 popcounts are independent of the distance chain below: issued together, the 16-step FMA
+            // chain of the exact distance hides under them (a warp's expansion is one long dependent chain)
+            uint32_t ps0 = 0;
+            if (count > 0) ps0 = plane_sum_one<true>(reinterpret_cast<const uint4*>(stage), 0, nch, lane, w.uq);
             float exact_dist;   // :130-133, from the staged vector
             {
                 const float dot = group_chain<false, true>(reinterpret_cast<const float*>(stage + raw_off) + (size_t)(lane & 7u) * T,
@@ -483,14 +487,12 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             // pre-filter :170-187, full estimate :189-200) only if some new slot survives the bound.
             const bool warmup = nn_m < k;   // :210, fixed for the whole neighbour loop
             float est = FLT_MAX, lower = 0.0f;
-            uint32_t ps0 = 0;
             const float sq = __fsqrt_rn(dqp);
             if (count > 0 && (!warmup || STATS)) {
                 const float nop = reinterpret_cast<const float*>(aux + 128)[lane];
                 const float ipqo = reinterpret_cast<const float*>(aux + 256)[lane];
                 const float ipcp = reinterpret_cast<const float*>(aux + 384)[lane];
                 const uint32_t pops = reinterpret_cast<const uint32_t*>(aux + 512)[lane];
-                ps0 = plane_sum_one<true>(reinterpret_cast<const uint4*>(stage), 0, nch, lane, w.uq);
                 if (B == 1) convert_1bit(qp, ps0, nop, ipqo, ipcp, pops & 0xFFFFu, lane, count, dqp, sq, est, lower);
                 else lower = nbit_lower<B>(qp, ps0, nop, ipqo, ipcp, pops & 0xFFFFu, lane, count, dqp, sq);
             }

@@ -332,3 +332,64 @@ def test_drop_in_build_finalize_search(oracle, tmp_path):
     i0, d0 = mine.search(q[0], 10)
     r0, rd0 = ref.search(q[0], 10)
     assert sorted(i0.tolist()) == sorted(r0.tolist())
+
+
+# ---------------------------------------------------------------------------------------------------
+# committed golden fixtures (written by the unmodified reference, tests/golden/make_golden.py): the CUDA path
+# through the C ABI's save-file loader against the reference's own search_batch results -- needs neither the
+# oracle nor oracle/_ref at run time
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bits", [1, 2, 4])
+@pytest.mark.parametrize("k", [1, 10, 50])
+def test_golden_index_files(bits, k):
+    import cphnsw_b200
+
+    g = np.load(common.GOLDEN / "e2e_golden.npz")
+    ix = cphnsw_b200.CPIndex(24, bits)
+    ix.load(str(common.GOLDEN / f"ref_n300_d24_b{bits}.bin"))
+    assert ix.size == 300 and ix.is_finalized
+    ids, dists = ix.search_batch(g["queries"], k)
+    gi, gd = common.sorted_rows(ids, dists)
+    wi, wd = common.sorted_rows(g[f"ids_b{bits}_k{k}"], g[f"dists_b{bits}_k{k}"])
+    assert np.array_equal(gi, wi) and np.array_equal(_bits(gd), _bits(wd))
+
+
+def test_golden_kernel_vectors():
+    """K1 / K2 / K4 against the committed reference outputs (k1_golden, k2_golden, l2_golden)."""
+    from cphnsw_b200 import hooks
+
+    torch = _torch()
+    g1 = np.load(common.GOLDEN / "k1_golden.npz")
+    for dim in (16, 20, 96, 128, 960):
+        fab = common.fabricate(40, dim, 1, seed=1)
+        ix = common.gpu_index_from(fab)
+        out = hooks.prepare_queries(ix, torch.from_numpy(g1[f"q_{dim}"]).cuda())
+        assert np.array_equal(out["lut"].cpu().numpy(), g1[f"lut_{dim}"])
+        assert np.array_equal(_bits(out["coeffs"].cpu().numpy()), _bits(g1[f"coeffs_{dim}"]))
+        assert np.array_equal(_bits(out["rotated"].cpu().numpy()), _bits(g1[f"rot_{dim}"]))
+    g2 = np.load(common.GOLDEN / "k2_golden.npz")
+    for tag in ("128_1", "128_2", "128_4", "960_2", "16_4"):
+        dim, bits = map(int, tag.split("_"))
+        fab = common.fabricate(10, dim, bits, seed=dim + bits, counts=(32, 31, 24, 9, 8, 1), degenerate=True, a=1.02, b=0.01)
+        assert np.array_equal(fab.search_data[:, fab.nb_off:], g2[f"blocks_{tag}"]), "fixture generator drifted"
+        ix = common.gpu_index_from(fab)
+        # the golden LUTs came from these queries' encodings; recover the bit-planes from the LUT bytes
+        lut, coeffs = g2[f"lut_{tag}"], g2[f"coeffs_{tag}"]
+        u = np.stack([lut[:, :, 1 << b] for b in range(4)], axis=2).reshape(2, fab.D)
+        W = max(fab.D, 128) // 32
+        up = np.zeros((2, 4, W), np.uint32)
+        for t in range(4):
+            pad = np.zeros((2, W * 32), np.uint8); pad[:, :fab.D] = (u >> t) & 1
+            up[:, t, :] = np.packbits(pad.reshape(2, W, 32), axis=2, bitorder="little").view(np.uint32)[:, :, 0]
+        n = fab.n
+        qi = g2[f"qi_{tag}"].astype(np.int32)
+        out = hooks.fastscan_blocks(ix, torch.from_numpy(up.view(np.int32)).cuda(), torch.from_numpy(coeffs).cuda(),
+                                    torch.from_numpy(g2[f"dqp_{tag}"].astype(np.float32)), vertex_ids=torch.arange(n, dtype=torch.int32),
+                                    query_of_block=torch.from_numpy(qi), slack_level=torch.from_numpy((np.arange(n) % 3).astype(np.int32)))
+        out = {k_: v.cpu().numpy() for k_, v in out.items()}
+        for v in range(n):
+            c = int(g2[f"count_{tag}"][v])
+            for name in ("nbit", "msb", "msb2"):
+                assert np.array_equal(out[name][v].view(np.uint32), g2[f"{name}_{tag}"][v]), (tag, name, v)
+            for name in ("est", "lower", "msb_lower"):
+                assert np.array_equal(_bits(out[name][v][:c]), _bits(g2[f"{name}_{tag}"][v][:c])), (tag, name, v)
