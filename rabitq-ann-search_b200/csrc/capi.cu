@@ -690,7 +690,7 @@ static int run_exhaustive(cphnsw_b200_index* ix, const float* d_queries, uint64_
     a.use_tensor_cores = ix->exhaustive_tensor_cores ? 1 : 0;
     a.id_begin = id_begin; a.id_end = id_end; a.k = (uint32_t)k; a.kprime = (uint32_t)kprime;
     a.sums = d_sums; a.est = d_est; a.ids = d_ids; a.dists = d_dists;
-    const size_t wb = exhaustive_workspace_bytes(d, (uint32_t)nq, id_end - id_begin, (uint32_t)kprime);
+    const size_t wb = exhaustive_workspace_bytes(d, (uint32_t)nq, id_end - id_begin, (uint32_t)kprime, ix->num_sms);
     rc = ensure_buffer(ix, &ix->scratch, &ix->scratch_bytes, wb + 256, false);
     if (rc) return rc;
     a.workspace = ix->scratch; a.workspace_bytes = wb;

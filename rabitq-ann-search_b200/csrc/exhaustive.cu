@@ -193,23 +193,25 @@ static uint32_t pick_slices(uint64_t m, uint32_t kprime, uint32_t nq, int num_sm
     return (uint32_t)(s < 1 ? 1 : s);
 }
 
-size_t exhaustive_workspace_bytes(const DevIndex&, uint32_t nq, uint64_t m, uint32_t kprime) {
-    return (size_t)64 * nq * (size_t)kprime * 8 + 256;   // upper bound over pick_slices()
+size_t exhaustive_workspace_bytes(const DevIndex&, uint32_t nq, uint64_t m, uint32_t kprime, int num_sms) {
+    // upper bound over pick_slices(), plus the tensor-core scan's candidate lists and shared thresholds
+    return exhaustive_tc_workspace_bytes(nq, kprime, num_sms) + 256;
 }
 
 cudaError_t launch_exhaustive(const DevIndex& ix, const ExhaustiveArgs& a, int num_sms, cudaStream_t stream) {
     if (a.nq == 0) return cudaSuccess;
     if (a.kprime > kMaxKPrime) return cudaErrorInvalidValue;
     const uint64_t m = a.id_end - a.id_begin;
-    const uint32_t nslices = pick_slices(m, a.kprime, a.nq, num_sms);
+    const bool tc = a.use_tensor_cores && a.ubytes && exhaustive_tc_applicable(ix, a.kprime);
+    uint32_t nslices = tc ? 1u : pick_slices(m, a.kprime, a.nq, num_sms);   // (tensor-core form: decided by its launcher)
     const uint64_t slice_len = m ? (m + nslices - 1) / nslices : 1;
     unsigned long long* partial = static_cast<unsigned long long*>(a.workspace);
     const uint32_t cap = a.kprime <= 384 ? 1024u : (uint32_t)kCapMax;   // cap >= k' + 2 x 256 always
     const size_t smem = (size_t)kQT * cap * 8 + (size_t)kQT * ix.nch * 64 + (size_t)kQT * 16;
     cudaError_t e = cudaFuncSetAttribute(exhaustive_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    if (a.use_tensor_cores && a.ubytes && exhaustive_tc_applicable(ix, a.kprime)) {
-        e = launch_exhaustive_scan_tc(ix, a, nslices, slice_len, a.ubytes, partial, stream);
+    if (tc) {
+        e = launch_exhaustive_scan_tc(ix, a, num_sms, partial, &nslices, stream);
         if (e != cudaSuccess) return e;
     } else if (m > 0 || a.kprime) {
         dim3 grid(nslices, (a.nq + kQT - 1) / kQT);

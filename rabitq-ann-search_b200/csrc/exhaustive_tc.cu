@@ -1,24 +1,46 @@
 // K5, tensor-core form -- the exhaustive scan's integer contraction on the 5th-generation tensor cores.
 //
-// sums[v][q] = sum_i bit_i(v) * u_i(q)  (compute_inner_products, distance/fastscan_kernel.hpp:17-87) over
-// a tile of 128 vertices x 16 queries is a 128 x 16 x D u8 GEMM: A = the vertices' code bits expanded to
+// sums[v][q] = sum_i bit_i(v) * u_i(q)  (compute_inner_products, distance/fastscan_kernel.hpp:17-87) over a
+// tile of 128 vertices x 256 queries is a 128 x 256 x D u8 GEMM: A = the vertices' code bits expanded to
 // bytes 0/1, B = the queries' 4-bit values as bytes, D = s32 accumulators in tensor memory.  Exact
-// (products <= 15, sums <= 15 D).  Per 128-dim chunk: every thread expands its vertex's 128 code bits into
-// the K-major, un-swizzled canonical shared-memory layout (8-row x 16-byte core matrices; LBO = 128 B
-// between core matrices along K, SBO = 1 KB between 8-row groups), one thread issues four
-// tcgen05.mma.cta_group::1.kind::i8 (M = 128, N = 16, K = 32) per tile and a tcgen05.commit onto an
-// mbarrier, and the epilogue reads each vertex's 16 sums back with tcgen05.ld.32x32b.x16.  A CTA is 512
-// threads = 4 such tiles in flight (64 TMEM columns), thread = vertex; estimates, the running threshold and
-// the per-query candidate lists are exactly those of the popcount kernel (exhaustive.cu), which remains the
-// path for the shapes this one does not take (k' > 512).
+// (products <= 15, sums <= 15 D).
+//
+// One persistent CTA per SM, 21 warps in three roles connected by mbarriers:
+//   expanders (4 warps, thread = vertex row)  code bits -> bytes in the K-major, un-swizzled canonical layout
+//       (8-row x 16-byte core matrices; LBO = 128 B along K, SBO = 1 KB between 8-row groups), a ring of 4
+//       16 KB stages;
+//   issuer (1 thread)  four tcgen05.mma.cta_group::1.kind::i8 (M = 128, N = 256, K = 32) per 128-dim chunk,
+//       tcgen05.commit releases the stage and, after the last chunk, publishes the accumulator; two
+//       accumulators (2 x 256 TMEM columns) so the next tile's MMAs run under this tile's epilogue;
+//   epilogue (16 warps: 4 lane quarters x 4 column groups, thread = vertex, 64 queries each)
+//       tcgen05.ld.32x32b.x32, then per (vertex, query) pair a division-free candidate screen.
+// The screen: est <= tau is, in exact arithmetic, fs >= thr(v,q) with
+//       thr = [ s_v (w_v + dqp_q - tau_q) - pc_v Bc_q - C_q ] / A_q,   s_v = q_v / (2 nop_v a),  w_v = nop_v (nop_v - 2 b)
+// a bilinear form of three per-vertex and four per-query numbers: three FMAs and a compare per pair, with
+// the float error of both sides (bounded by 2^-19 of the sum of the magnitudes of all terms, see
+// tc_query_params) and the rounding of the compare itself folded into the per-query constant.  Pairs that
+// pass (a few per thousand) get the exact estimate -- the op-for-op AVX2 lane of
+// convert_to_distances_with_bounds (:138-173), flat_estimate -- and, if est <= tau, join the query's
+// candidate list.  Lists live in HBM/L2 per (CTA, query); when one is within a tile of full its owner warp
+// selects the k' smallest keys in registers (bitwise search for the k'-th key) and lowers tau.  tau is only
+// ever an upper bound of the final k'-th smallest estimate, so it is shared between CTAs through a global
+// array (atomicMin): what ends in the lists differs from run to run, the k' smallest keys never do.
+// A work item is (group of 256 queries, slice of vertices); each item leaves its <= k' best keys in
+// partial[slice][query][k'], merged and re-ranked by exhaustive_select_rerank_kernel (exhaustive.cu).
 #include "exhaustive_common.cuh"
 
 namespace cpb {
 
-constexpr int kTcThreads = 512;   // 4 vertex tiles of 128
-constexpr int kTcNQ = 16;         // queries per CTA tile = MMA N
-constexpr int kTcCap = 1024;      // candidate slots per query (>= k' + kTcThreads)
-constexpr uint32_t kTcCols = 64;  // TMEM columns: 4 tiles x 16
+constexpr int kTcNQ = 256;           // queries per work item = MMA N
+constexpr int kTcM = 128;            // vertices per tile = MMA M
+constexpr int kTcStages = 4;         // A-operand ring
+constexpr int kTcCap = 512;          // candidate slots per (CTA, query)
+constexpr uint32_t kTcMaxKPrime = 256;   // k' + one tile of appends must fit the list
+constexpr int kTcExpWarps = 4, kTcEpiWarps = 16;
+constexpr int kTcThreads = (kTcExpWarps + kTcEpiWarps + 1) * 32;   // + the issuer warp
+constexpr uint32_t kTcCols = 512;    // TMEM columns: 2 accumulators x 256
+constexpr float kTcBig = 3.0e38f;
+constexpr float kTcTauInf = 1.0e37f;   // tau at or above this = no threshold yet
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -36,6 +58,12 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint6
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
 
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t phase) {
     uint32_t done;
     do {
@@ -43,6 +71,17 @@ __device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t phase) {
                      : "=r"(done) : "r"(tc_smem_u32(bar)), "r"(phase) : "memory");
     } while (!done);
 }
+// for the roles that run ahead and then wait long (expanders, issuer): do not spin in the epilogue's issue slots
+__device__ __forceinline__ void tc_wait_relaxed(uint64_t* bar, uint32_t phase) {
+    uint32_t done;
+    for (;;) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(tc_smem_u32(bar)), "r"(phase) : "memory");
+        if (done) break;
+        __nanosleep(128);
+    }
+}
+__device__ __forceinline__ void tc_group_sync(uint32_t id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 // 16 code bits -> 16 bytes (0/1), little-endian bit order
 __device__ __forceinline__ uint4 expand16(uint32_t bits) {
@@ -54,180 +93,470 @@ __device__ __forceinline__ uint4 expand16(uint32_t bits) {
     return r;
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc_kernel(const DevIndex ix, const ExhaustiveArgs a,
-                                                                           uint32_t nslices, uint64_t slice_len,
-                                                                           const uint8_t* __restrict__ ubytes,
+// ---- the screen's per-vertex and per-query numbers ----------------------------------------------------
+struct TcLimits { float slim, alim; };   // vertices with s_v or |alpha_v| above these skip the screen
+
+// s_v, alpha_v = s_v w_v; `force` = the screen does not apply to this vertex (every pair gets the exact estimate)
+__device__ __forceinline__ void tc_vertex_params(const Calib& cal, float nop, float ipqo, const TcLimits& lim, float& sv, float& av,
+                                                 bool& force) {
+    const float qv = max_ps(ipqo, cal.ip_qo_floor);
+    const float den = __fmul_rn(__fmul_rn(2.0f, nop), cal.affine_a);
+    sv = __fdiv_rn(qv, den);
+    av = __fmul_rn(sv, __fmul_rn(nop, __fsub_rn(nop, __fmul_rn(2.0f, cal.affine_b))));
+    force = !(qv > 1e-10f) || !(den > 0.0f) || !(sv <= lim.slim) || !(fabsf(av) <= lim.alim);
+    if (force) { sv = 0.0f; av = 0.0f; }
+}
+
+// {1/A, (dqp - tau)/A, -Bc/A, cut}: pair (v, q) passes the screen iff
+//     (2^23 + fs) - alpha_v x - s_v y - pc_v z  >=  cut            (three FMAs at magnitude 2^23: <= 1.5 of rounding)
+// cut = 2^23 + floor(-C/A - margin) - 2, margin = 2^-19 (sum of the magnitudes of every term of thr and of the
+// estimate's own chain, in units of fs): the exact float estimate differs from the real-number one by at most
+// 8 ulp of its largest intermediate, thr's own evaluation by as much again; 2^-19 = 32 ulp covers both.
+// Queries the screen cannot serve (dqp < 1e-12 takes another formula; A = 0; no tau yet; magnitudes too large
+// for the margin to stay under half a unit) get cut = -big: every pair passes.  Absent queries never pass.
+__device__ __forceinline__ float4 tc_query_params(bool valid, float A, float Bc, float C, float dqp, float tau, const TcLimits& lim,
+                                                  float dmax) {
+    if (!valid) return make_float4(0.0f, 0.0f, 0.0f, kTcBig);
+    const float4 all = make_float4(0.0f, 0.0f, 0.0f, -kTcBig);
+    if (!(dqp >= 1e-12f) || !(A > 0.0f) || !(tau < kTcTauInf)) return all;
+    const float ia = __fdiv_rn(1.0f, A);
+    const float y = __fmul_rn(__fsub_rn(dqp, tau), ia), z = -__fmul_rn(Bc, ia), c0 = -__fmul_rn(C, ia);
+    const float sabs = lim.alim * ia + lim.slim * (fabsf(dqp) + fabsf(tau)) * ia + dmax * fabsf(z) + fabsf(c0) + 15.0f * dmax;
+    if (!(sabs < 262144.0f)) return all;
+    const float cut = floorf(c0 - sabs * 1.9073486328125e-6f) - 2.0f + 8388608.0f;
+    return make_float4(ia, y, z, cut);
+}
+
+// mean of s_v and |alpha_v| over the scanned range -> limits (16 x mean); also resets the shared thresholds
+__global__ void exhaustive_tc_prepare_kernel(const DevIndex ix, uint64_t id_begin, uint64_t id_end, uint32_t nq, float* __restrict__ acc,
+                                             uint32_t* __restrict__ taug) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = gid; i < nq; i += stride) taug[i] = __float_as_uint(FLT_MAX);
+    const Calib& cal = ix.calib;
+    float s = 0.0f, a = 0.0f, c = 0.0f;
+    TcLimits none{FLT_MAX, FLT_MAX};
+    for (uint64_t v = id_begin + gid; v < id_end; v += stride) {
+        float sv, av; bool force;
+        tc_vertex_params(cal, __ldg(ix.flat_nop + v), __ldg(ix.flat_ipqo + v), none, sv, av, force);
+        if (!force && sv < 1e30f && fabsf(av) < 1e30f) { s += sv; a += fabsf(av); c += 1.0f; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(kFull, s, o); a += __shfl_xor_sync(kFull, a, o); c += __shfl_xor_sync(kFull, c, o);
+    }
+    if ((threadIdx.x & 31) == 0 && c > 0.0f) { atomicAdd(acc + 0, s); atomicAdd(acc + 1, a); atomicAdd(acc + 2, c); }
+}
+
+// k' smallest of the c <= kTcCap keys of one list, in place, by one warp; returns the new count and the k'-th
+// key's estimate bits.  Keys are distinct (ids are), empty slots compare as kNoKey.
+__device__ __forceinline__ uint32_t tc_select(unsigned long long* __restrict__ lst, uint32_t c, uint32_t kp, uint32_t lane, uint32_t& tau_bits) {
+    constexpr int KPL = kTcCap / 32;
+    uint32_t hi[KPL], lo[KPL];
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+        const uint32_t idx = (uint32_t)i * 32 + lane;
+        const unsigned long long key = idx < c ? lst[idx] : kNoKey;
+        hi[i] = (uint32_t)(key >> 32); lo[i] = (uint32_t)key;
+    }
+    uint32_t cur = 0;
+    for (int bit = 30; bit >= 0; --bit) {   // estimates are non-negative floats: bit 31 is clear
+        const uint32_t t = cur | (1u << bit);
+        uint32_t nl = 0;
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) nl += hi[i] < t ? 1u : 0u;
+        nl = __reduce_add_sync(kFull, nl);
+        if (nl < kp) cur = t;
+    }
+    uint32_t nlt = 0, neq = 0;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) { nlt += hi[i] < cur ? 1u : 0u; neq += hi[i] == cur ? 1u : 0u; }
+    nlt = __reduce_add_sync(kFull, nlt); neq = __reduce_add_sync(kFull, neq);
+    const uint32_t r = kp - nlt;   // 1 <= r <= neq of the keys with this estimate stay
+    uint32_t cutlo = 0xFFFFFFFFu;
+    if (neq != r) {
+        uint32_t cl = 0;
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t t = cl | (1u << bit);
+            uint32_t nl = 0;
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) nl += (hi[i] == cur && lo[i] < t) ? 1u : 0u;
+            nl = __reduce_add_sync(kFull, nl);
+            if (nl < r) cl = t;
+        }
+        cutlo = cl;
+    }
+    uint32_t mine = 0;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) mine += (hi[i] < cur || (hi[i] == cur && lo[i] <= cutlo)) ? 1u : 0u;
+    uint32_t pos = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(kFull, pos, o); if (lane >= (uint32_t)o) pos += t; }
+    pos -= mine;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < KPL; ++i)
+        if (hi[i] < cur || (hi[i] == cur && lo[i] <= cutlo)) lst[pos++] = ((unsigned long long)hi[i] << 32) | lo[i];
+    __syncwarp();
+    tau_bits = cur;
+    return kp;
+}
+
+struct TcShared {
+    float4 qpar[kTcNQ];    // screen constants
+    float4 par[kTcNQ];     // A, Bc, C, |q-c|^2
+    float tau[kTcNQ];
+    uint32_t cnt[kTcNQ];
+    uint64_t a_full[kTcStages], a_empty[kTcStages], acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+};
+
+// a pair that passed the screen: the exact estimate, dense outputs (parity hooks), the candidate list
+struct TcExact { float aa, ab, floor_; uint32_t kp; uint32_t* sums; float* est; };
+
+template <bool DENSE>
+__device__ __forceinline__ void tc_candidate(const TcExact x, TcShared& sh, unsigned long long* __restrict__ mylists, uint32_t col,
+                                          size_t dense_off, uint32_t id, uint32_t fs, float pc, float nop, float ipqo) {
+    const float4 P = sh.par[col];
+    const float est = flat_estimate(P.x, P.y, P.z, x.aa, x.ab, x.floor_, P.w, fs, pc, nop, ipqo);
+    if (DENSE) {
+        if (x.sums) x.sums[dense_off] = fs;
+        if (x.est) x.est[dense_off] = est;
+    }
+    if (x.kp && est <= sh.tau[col]) {
+        const uint32_t pos = atomicAdd(&sh.cnt[col], 1u);   // < capacity: lists are trimmed a tile ahead
+        mylists[(size_t)col * kTcCap + pos] = make_key(est, id);
+    }
+}
+
+template <bool DENSE>
+__global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc_kernel(const DevIndex ix, const ExhaustiveArgs a, uint32_t tiles_per_group,
+                                                                           uint64_t units_per_cta, uint32_t ngroups,
+                                                                           const float* __restrict__ vstat, uint32_t* __restrict__ taug,
+                                                                           unsigned long long* __restrict__ lists,
                                                                            unsigned long long* __restrict__ partial) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t nch = ix.nch, W = nch * 4;
-    uint8_t* As = smem_raw;                                                    // 4 tiles x 16 KB
-    uint8_t* Bs = smem_raw + 65536;                                            // nch x 2 KB
-    unsigned long long* cand = reinterpret_cast<unsigned long long*>(smem_raw + 65536 + (size_t)nch * 2048);   // [16][1024]
-    float* par = reinterpret_cast<float*>(smem_raw + 65536 + (size_t)nch * 2048 + (size_t)kTcNQ * kTcCap * 8);  // [16][4]
-    __shared__ __align__(8) uint64_t mbar;
-    __shared__ uint32_t tmem_base_s;
-    __shared__ uint32_t cnt[kTcNQ];
-    __shared__ float tau[kTcNQ];
-    __shared__ uint32_t need_compact;
+    uint8_t* As = smem_raw;                                           // kTcStages x 16 KB
+    uint8_t* Bs = smem_raw + (size_t)kTcStages * 16384;               // nch x 32 KB
+    TcShared& sh = *reinterpret_cast<TcShared*>(smem_raw + (size_t)kTcStages * 16384 + (size_t)nch * 32768);
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t slice = blockIdx.x, q0 = blockIdx.y * kTcNQ;
-    const uint32_t nqt = min((uint32_t)kTcNQ, a.nq - q0);
     const uint32_t kp = a.kprime;
     const Calib& cal = ix.calib;
+    const uint64_t m = a.id_end - a.id_begin;
+    const float dmax = (float)(nch * 128u);
+    unsigned long long* mylists = lists + (size_t)blockIdx.x * kTcNQ * kTcCap;
+    const uint32_t G = kp ? (kTcCap - kp) / kTcM : 1u;   // 2 or 3: tiles between list checks
+    const TcExact ex{cal.affine_a, cal.affine_b, cal.ip_qo_floor, kp, a.sums, a.est};
 
-    // ---- one-time setup: TMEM, mbarrier, the query operand B, per-query constants ------------------------
+    TcLimits lim;
+    {
+        const float c = vstat[2];
+        lim.slim = c > 0.0f ? 16.0f * vstat[0] / c : 0.0f;
+        lim.alim = c > 0.0f ? 16.0f * vstat[1] / c : 0.0f;
+    }
+
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_s)), "r"(kTcCols) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&sh.tmem_base)), "r"(kTcCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&mbar)));
+        for (int s = 0; s < kTcStages; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(&sh.a_full[s])), "r"(kTcExpWarps));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&sh.a_empty[s])));
+        }
+        for (int b = 0; b < 2; ++b) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&sh.acc_full[b])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(&sh.acc_empty[b])), "r"(kTcEpiWarps));
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        need_compact = 0;
     }
-    // B[c][n][k]: core matrices of 8 queries x 16 bytes; absent queries are zero rows
-    for (uint32_t i = tid; i < (uint32_t)kTcNQ * nch * 8; i += blockDim.x) {
-        const uint32_t kc = i & 7u, n = (i >> 3) % kTcNQ, c = i / (8u * kTcNQ);
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (n < nqt) v = *reinterpret_cast<const uint4*>(ubytes + ((size_t)(q0 + n) * nch + c) * 128 + kc * 16);
-        *reinterpret_cast<uint4*>(Bs + (size_t)c * 2048 + (n >> 3) * 1024 + kc * 128 + (n & 7u) * 16) = v;
-    }
-    for (uint32_t i = tid; i < nqt; i += blockDim.x) {
-        const float* cf = a.coeffs + (size_t)(q0 + i) * kCoeffStride;
-        par[4 * i + 0] = cf[0]; par[4 * i + 1] = cf[1]; par[4 * i + 2] = cf[2]; par[4 * i + 3] = cf[4];
-    }
-    if (tid < kTcNQ) { cnt[tid] = 0; tau[tid] = FLT_MAX; }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = tmem_base_s;
-    // instruction descriptor: D = s32, A = B = unsigned 8-bit, both K-major, N = 16, M = 128
-    const uint32_t idesc = (2u << 4) | ((uint32_t)(kTcNQ >> 3) << 17) | ((128u >> 4) << 24);
-    uint32_t phase = 0;
+    const uint32_t tmem_base = sh.tmem_base;
+    // instruction descriptor: D = s32, A = B = unsigned 8-bit, both K-major, N = 256, M = 128
+    const uint32_t idesc = (2u << 4) | ((uint32_t)(kTcNQ >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
 
-    const uint64_t vb = a.id_begin + (uint64_t)slice * slice_len;
-    const uint64_t ve = min(a.id_end, vb + slice_len);
-    const uint64_t m = a.id_end - a.id_begin;
-    const uint32_t tile = tid >> 7, row = tid & 127u;
-    uint8_t* arow = As + (size_t)tile * 16384 + (row >> 3) * 1024 + (row & 7u) * 16;
+    uint32_t step = 0, tcount = 0;   // running counters of this thread's role (ring stage / accumulator phases)
+    // Work = (query group, tile) pairs, group-major; this CTA owns the contiguous range [u0, u1) of them, i.e. at
+    // most one run of tiles ("segment") per group: its candidate lists and thresholds live for the whole run.
+    const uint64_t nunits = (uint64_t)ngroups * tiles_per_group;
+    const uint64_t u0 = (uint64_t)blockIdx.x * units_per_cta;
+    const uint64_t u1 = min(nunits, u0 + units_per_cta);
 
-    for (uint64_t base = vb; base < ve; base += kTcThreads) {
-        const uint64_t v = base + tid;
-        const bool live = v < ve;
-        float nop = 0.0f, ipqo = 0.0f, pc = 0.0f, rq = 0.0f;
-        if (live) {
-            nop = __ldg(ix.flat_nop + v); ipqo = __ldg(ix.flat_ipqo + v); pc = (float)__ldg(ix.flat_pop + v);
-            const float qq = max_ps(ipqo, cal.ip_qo_floor);
-            rq = qq > 1e-10f ? __frcp_rn(qq) : 0.0f;
+    for (uint64_t u = u0; u < u1;) {
+        const uint32_t grp = (uint32_t)(u / tiles_per_group), tile0 = (uint32_t)(u % tiles_per_group);
+        const uint32_t ntiles = (uint32_t)min((uint64_t)(tiles_per_group - tile0), u1 - u);
+        u += ntiles;
+        // ordinal of this segment among the segments of its group (CTAs cover the group in order)
+        const uint32_t slice = blockIdx.x - (uint32_t)(((uint64_t)grp * tiles_per_group) / units_per_cta);
+        const uint32_t q0 = grp * kTcNQ;
+        const uint32_t nqt = min((uint32_t)kTcNQ, a.nq - q0);
+        const uint64_t vb = a.id_begin + (uint64_t)tile0 * kTcM;
+        const uint64_t ve = min(a.id_end, vb + (uint64_t)ntiles * kTcM);
+
+        // ---- item prologue: the query operand B, per-query constants, empty lists -------------------------
+        // B[c][n][k]: core matrices of 8 queries x 16 bytes; absent queries are zero rows
+        for (uint32_t i = tid; i < (uint32_t)kTcNQ * nch * 8; i += blockDim.x) {
+            const uint32_t kc = i & 7u, n = (i >> 3) % kTcNQ, c = i / (8u * kTcNQ);
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (n < nqt) v = *reinterpret_cast<const uint4*>(a.ubytes + ((size_t)(q0 + n) * nch + c) * 128 + kc * 16);
+            *reinterpret_cast<uint4*>(Bs + (size_t)c * 32768 + (n >> 3) * 1024 + kc * 128 + (n & 7u) * 16) = v;
         }
-        for (uint32_t c = 0; c < nch; ++c) {
-            uint4 w = make_uint4(0, 0, 0, 0);
-            if (live) w = __ldg(reinterpret_cast<const uint4*>(ix.flat_codes + v * W) + c);
-            // this vertex's row of A: 8 pieces of 16 bytes, 128 B apart (one per core matrix along K)
-            *reinterpret_cast<uint4*>(arow + 0 * 128) = expand16(w.x);
-            *reinterpret_cast<uint4*>(arow + 1 * 128) = expand16(w.x >> 16);
-            *reinterpret_cast<uint4*>(arow + 2 * 128) = expand16(w.y);
-            *reinterpret_cast<uint4*>(arow + 3 * 128) = expand16(w.y >> 16);
-            *reinterpret_cast<uint4*>(arow + 4 * 128) = expand16(w.z);
-            *reinterpret_cast<uint4*>(arow + 5 * 128) = expand16(w.z >> 16);
-            *reinterpret_cast<uint4*>(arow + 6 * 128) = expand16(w.w);
-            *reinterpret_cast<uint4*>(arow + 7 * 128) = expand16(w.w >> 16);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
-            __syncthreads();
-            if (tid == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                for (uint32_t j = 0; j < 4; ++j)
-#pragma unroll
-                    for (uint32_t ks = 0; ks < 4; ++ks)
-                        tc_mma_i8(tmem_base + j * kTcNQ, tc_desc(tc_smem_u32(As) + j * 16384 + ks * 256),
-                                  tc_desc(tc_smem_u32(Bs) + c * 2048 + ks * 256), idesc, (c > 0 || ks > 0) ? 1u : 0u);
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(&mbar)) : "memory");
+        for (uint32_t i = tid; i < (uint32_t)kTcNQ; i += blockDim.x) {
+            float4 p = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            float tau = FLT_MAX;
+            if (i < nqt) {
+                const float* cf = a.coeffs + (size_t)(q0 + i) * kCoeffStride;
+                p = make_float4(cf[0], cf[1], cf[2], cf[4]);
+                if (kp) tau = __uint_as_float(taug[q0 + i]);
             }
-            tc_wait(&mbar, phase);   // MMAs done: A may be overwritten, accumulators are readable
-            phase ^= 1u;
+            sh.par[i] = p; sh.tau[i] = tau; sh.cnt[i] = 0;
+            sh.qpar[i] = DENSE ? make_float4(0.0f, 0.0f, 0.0f, i < nqt ? -kTcBig : kTcBig)
+                               : tc_query_params(i < nqt, p.x, p.y, p.z, p.w, tau, lim, dmax);
         }
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t fs[kTcNQ];
-        {
-            const uint32_t taddr = tmem_base + (((warp & 3u) * 32u) << 16) + tile * kTcNQ;
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                         : "=r"(fs[0]), "=r"(fs[1]), "=r"(fs[2]), "=r"(fs[3]), "=r"(fs[4]), "=r"(fs[5]), "=r"(fs[6]), "=r"(fs[7]),
-                           "=r"(fs[8]), "=r"(fs[9]), "=r"(fs[10]), "=r"(fs[11]), "=r"(fs[12]), "=r"(fs[13]), "=r"(fs[14]), "=r"(fs[15])
-                         : "r"(taddr) : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+
+        if (warp < (uint32_t)kTcExpWarps) {
+            // ================= expanders: thread = vertex row ==============================================
+            const uint32_t row = tid;
+            uint8_t* rowoff = As + (row >> 3) * 1024 + (row & 7u) * 16;
+            const uint32_t nsteps = ntiles * nch;
+            uint4 nxt = make_uint4(0, 0, 0, 0);
+            if (nsteps && vb + row < ve) nxt = __ldg(reinterpret_cast<const uint4*>(ix.flat_codes + (vb + row) * W));
+            for (uint32_t i = 0; i < nsteps; ++i, ++step) {
+                const uint4 w = nxt;
+                if (i + 1 < nsteps) {
+                    const uint32_t t1 = (i + 1) / nch, c1 = (i + 1) % nch;
+                    const uint64_t v1 = vb + (uint64_t)t1 * kTcM + row;
+                    nxt = v1 < ve ? __ldg(reinterpret_cast<const uint4*>(ix.flat_codes + v1 * W) + c1) : make_uint4(0, 0, 0, 0);
+                }
+                const uint32_t s = step % kTcStages;
+                tc_wait_relaxed(&sh.a_empty[s], ((step / kTcStages) & 1u) ^ 1u);
+                uint8_t* arow = rowoff + (size_t)s * 16384;
+                // this vertex's row of A: 8 pieces of 16 bytes, 128 B apart (one per core matrix along K)
+                *reinterpret_cast<uint4*>(arow + 0 * 128) = expand16(w.x);
+                *reinterpret_cast<uint4*>(arow + 1 * 128) = expand16(w.x >> 16);
+                *reinterpret_cast<uint4*>(arow + 2 * 128) = expand16(w.y);
+                *reinterpret_cast<uint4*>(arow + 3 * 128) = expand16(w.y >> 16);
+                *reinterpret_cast<uint4*>(arow + 4 * 128) = expand16(w.z);
+                *reinterpret_cast<uint4*>(arow + 5 * 128) = expand16(w.z >> 16);
+                *reinterpret_cast<uint4*>(arow + 6 * 128) = expand16(w.w);
+                *reinterpret_cast<uint4*>(arow + 7 * 128) = expand16(w.w >> 16);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
+                __syncwarp();
+                if (lane == 0) tc_arrive(&sh.a_full[s]);
+            }
+        } else if (warp == (uint32_t)(kTcExpWarps + kTcEpiWarps)) {
+            // ================= issuer: one thread ==========================================================
+            if (lane == 0) {
+                for (uint32_t t = 0; t < ntiles; ++t, ++tcount) {
+                    const uint32_t buf = tcount & 1u;
+                    tc_wait_relaxed(&sh.acc_empty[buf], ((tcount >> 1) & 1u) ^ 1u);
+                    for (uint32_t c = 0; c < nch; ++c, ++step) {
+                        const uint32_t s = step % kTcStages;
+                        tc_wait_relaxed(&sh.a_full[s], (step / kTcStages) & 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-        for (int t = 0; t < kTcNQ; ++t) {
-            if ((uint32_t)t < nqt && live) {
-                const bool dense = a.sums || a.est;
-                // (dist_qp_sq < 1e-12 takes another formula: no screen there; q <= 1e-10 makes the estimate
-                //  nop^2 + dqp - 2 nop b, which the screen reproduces with rq = 0)
-                if (dense || par[4 * t + 3] < 1e-12f ||
-                    (kp && flat_screen(par[4 * t], par[4 * t + 1], par[4 * t + 2], cal.affine_a, cal.affine_b, par[4 * t + 3], fs[t],
-                                       pc, nop, rq, tau[t]))) {
-                    const float est = flat_estimate(par[4 * t], par[4 * t + 1], par[4 * t + 2], cal.affine_a, cal.affine_b,
-                                                    cal.ip_qo_floor, par[4 * t + 3], fs[t], pc, nop, ipqo);
-                    if (a.sums) a.sums[(size_t)(q0 + t) * m + (v - a.id_begin)] = fs[t];
-                    if (a.est) a.est[(size_t)(q0 + t) * m + (v - a.id_begin)] = est;
-                    if (kp && est <= tau[t]) {
-                        const uint32_t pos = atomicAdd(&cnt[t], 1u);   // < capacity: lists are compacted before they can fill
-                        cand[(size_t)t * kTcCap + pos] = make_key(est, (uint32_t)v);
+                        for (uint32_t ks = 0; ks < 4; ++ks)
+                            tc_mma_i8(tmem_base + buf * kTcNQ, tc_desc(tc_smem_u32(As) + s * 16384 + ks * 256),
+                                      tc_desc(tc_smem_u32(Bs) + c * 32768 + ks * 256), idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                        tc_commit(&sh.a_empty[s]);       // the stage may be overwritten once these MMAs have read it
                     }
+                    tc_commit(&sh.acc_full[buf]);        // accumulator complete
+                }
+            }
+        } else {
+            // ================= epilogue: thread = vertex, 64 queries per warp ================================
+            const uint32_t e = warp - kTcExpWarps, quarter = warp & 3u, cg = e >> 2;
+            const uint32_t row = quarter * 32 + lane;
+            const uint32_t colbase = cg * 64;
+            const uint32_t own0 = colbase + quarter * 16;     // the 16 lists this warp maintains between tiles
+            float nop_n = 0.0f, ipqo_n = 0.0f;
+            uint32_t pop_n = 0;
+            if (ntiles && vb + row < ve) {
+                nop_n = __ldg(ix.flat_nop + vb + row); ipqo_n = __ldg(ix.flat_ipqo + vb + row); pop_n = __ldg(ix.flat_pop + vb + row);
+            }
+            for (uint32_t t = 0; t < ntiles; ++t, ++tcount) {
+                const uint64_t v = vb + (uint64_t)t * kTcM + row;
+                const bool live = v < ve;
+                const float nop = nop_n, ipqo = ipqo_n, pc = (float)pop_n;
+                {
+                    const uint64_t v1 = v + kTcM;
+                    if (t + 1 < ntiles && v1 < ve) {
+                        nop_n = __ldg(ix.flat_nop + v1); ipqo_n = __ldg(ix.flat_ipqo + v1); pop_n = __ldg(ix.flat_pop + v1);
+                    }
+                }
+                float sv, av;
+                bool force;
+                tc_vertex_params(cal, nop, ipqo, lim, sv, av, force);
+                const float nsv = -sv, nav = -av, npc = force ? 0.0f : -pc;
+                // rows the screen does not apply to: 2^126 (1 + fs 2^-23) instead of 2^23 + fs clears every cut of a
+                // present query (and the three FMAs, whose vertex factors are zero, leave it alone)
+                const uint32_t orv = (force || DENSE) ? 0x7E800000u : 0x4B000000u;
+
+                const uint32_t buf = tcount & 1u;
+                tc_wait(&sh.acc_full[buf], (tcount >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                for (uint32_t half = 0; half < 2; ++half) {
+                    const uint32_t col0 = colbase + half * 32;
+                    const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * kTcNQ + col0;
+                    uint32_t r[32];
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                        : "r"(taddr) : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    // the screen, 6 instructions per pair (LDS.128, LOP3, 3 FFMA, FSETP.OR): one flag per 8 columns
+                    bool h[4] = {false, false, false, false};
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float4 Q = sh.qpar[col0 + j];
+                        float x = __uint_as_float(r[j] | orv);   // 2^23 + fs, exact
+                        x = __fmaf_rn(nsv, Q.y, x);
+                        x = __fmaf_rn(npc, Q.z, x);
+                        x = __fmaf_rn(nav, Q.x, x);
+                        h[j >> 3] = h[j >> 3] || (x >= Q.w);
+                    }
+                    uint32_t hits = live ? ((h[0] ? 1u : 0u) | (h[1] ? 2u : 0u) | (h[2] ? 4u : 0u) | (h[3] ? 8u : 0u)) : 0u;
+                    uint32_t any = __reduce_or_sync(kFull, hits);
+                    while (any) {   // some lane passed somewhere in this group of 8 columns: exact estimates for the passers
+                        const uint32_t g8 = __ffs(any) - 1;
+                        any &= any - 1;
+                        uint32_t f8[8];
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                     : "=r"(f8[0]), "=r"(f8[1]), "=r"(f8[2]), "=r"(f8[3]), "=r"(f8[4]), "=r"(f8[5]), "=r"(f8[6]), "=r"(f8[7])
+                                     : "r"(taddr + g8 * 8) : "memory");
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (live && ((hits >> g8) & 1u)) {
+#pragma unroll
+                            for (uint32_t jj = 0; jj < 8; ++jj) {
+                                const uint32_t col = col0 + g8 * 8 + jj, fs = f8[jj];
+                                const float4 Q = sh.qpar[col];
+                                float x = __uint_as_float(fs | orv);
+                                x = __fmaf_rn(nsv, Q.y, x);
+                                x = __fmaf_rn(npc, Q.z, x);
+                                x = __fmaf_rn(nav, Q.x, x);
+                                if (x >= Q.w) tc_candidate<DENSE>(ex, sh, mylists, col, (size_t)(q0 + col) * m + (v - a.id_begin), (uint32_t)v, fs, pc, nop, ipqo);
+                            }
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) tc_arrive(&sh.acc_empty[buf]);
+
+                // ---- every G tiles: trim the lists that could overflow before the next check, refresh tau ---------
+                // (a tile appends at most 128 keys to a list; G = the tiles a just-trimmed list of k' keys can take)
+                if (kp && (t % G == G - 1 || t + 1 == ntiles)) {
+                    tc_group_sync(1 + cg);   // the four warps appending to these 64 lists are done with this tile
+                    const uint32_t mycol = own0 + (lane & 15u);
+                    const uint32_t need = __ballot_sync(kFull, lane < 16 && sh.cnt[mycol] + G * kTcM > (uint32_t)kTcCap);
+                    uint32_t todo = need;
+                    while (todo) {
+                        const uint32_t jl = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const uint32_t col = own0 + jl;
+                        uint32_t tb;
+                        const uint32_t nc = tc_select(mylists + (size_t)col * kTcCap, sh.cnt[col], kp, lane, tb);
+                        if (lane == 0) {
+                            const uint32_t old = atomicMin(taug + q0 + col, tb);
+                            sh.cnt[col] = nc;
+                            sh.tau[col] = __uint_as_float(min(old, tb));
+                        }
+                    }
+                    __syncwarp();
+                    const bool refresh = (t / G) % 3u == 2u;
+                    if (lane < 16 && mycol < nqt && (refresh || ((need >> lane) & 1u))) {
+                        float tau = sh.tau[mycol];
+                        if (refresh) { const float tg = __uint_as_float(taug[q0 + mycol]); if (tg < tau) tau = tg; }
+                        const float4 P = sh.par[mycol];
+                        sh.tau[mycol] = tau;
+                        sh.qpar[mycol] = tc_query_params(true, P.x, P.y, P.z, P.w, tau, lim, dmax);
+                    }
+                    tc_group_sync(1 + cg);
                 }
             }
         }
+
+        // ---- item epilogue: every list down to its k' best, out to partial[slice][q][k'] ----------------------
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (tid < nqt && cnt[tid] + kTcThreads > kTcCap) need_compact = 1;
-        __syncthreads();
-        if (need_compact) {
-            for (uint32_t t = 0; t < nqt; ++t) {
-                const uint32_t c = cnt[t];
-                if (c + kTcThreads > kTcCap) {
-                    unsigned long long* lst = cand + (size_t)t * kTcCap;
-                    for (uint32_t i = c + tid; i < kTcCap; i += blockDim.x) lst[i] = kNoKey;
-                    __syncthreads();
-                    bitonic_sort(lst, kTcCap);
-                    if (tid == 0) {
-                        cnt[t] = min(c, kp);
-                        if (c >= kp) tau[t] = __uint_as_float((uint32_t)(lst[kp - 1] >> 32));
-                    }
-                    __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (kp) {
+            for (uint32_t col = warp; col < nqt; col += blockDim.x >> 5) {
+                unsigned long long* lst = mylists + (size_t)col * kTcCap;
+                uint32_t c = sh.cnt[col];
+                if (c > kp) {
+                    uint32_t tb;
+                    c = tc_select(lst, c, kp, lane, tb);
+                    if (lane == 0) atomicMin(taug + q0 + col, tb);
                 }
+                unsigned long long* out = partial + ((size_t)slice * a.nq + (q0 + col)) * kp;
+                for (uint32_t i = lane; i < kp; i += 32) out[i] = i < c ? lst[i] : kNoKey;
             }
-            if (tid == 0) need_compact = 0;
-            __syncthreads();
         }
+        __syncthreads();
     }
-    if (kp) {
-        for (uint32_t t = 0; t < nqt; ++t) {
-            const uint32_t c = cnt[t];
-            unsigned long long* lst = cand + (size_t)t * kTcCap;
-            for (uint32_t i = c + tid; i < kTcCap; i += blockDim.x) lst[i] = kNoKey;
-            __syncthreads();
-            bitonic_sort(lst, kTcCap);
-            unsigned long long* out = partial + ((size_t)slice * a.nq + (q0 + t)) * kp;
-            for (uint32_t i = tid; i < kp; i += blockDim.x) out[i] = lst[i];
-            __syncthreads();
-        }
-    }
-    __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTcCols) : "memory");
 }
 
 bool exhaustive_tc_applicable(const DevIndex& ix, uint32_t kprime) {
-    return kprime + kTcThreads <= (uint32_t)kTcCap && ix.nch <= 8;
+    return kprime <= kTcMaxKPrime && ix.nch <= 2 && ix.calib.affine_a > 0.0f;
 }
 
-cudaError_t launch_exhaustive_scan_tc(const DevIndex& ix, const ExhaustiveArgs& a, uint32_t nslices, uint64_t slice_len,
-                                      const uint8_t* ubytes, unsigned long long* partial, cudaStream_t stream) {
-    const size_t smem = 65536 + (size_t)ix.nch * 2048 + (size_t)kTcNQ * kTcCap * 8 + (size_t)kTcNQ * 16;
-    cudaError_t e = cudaFuncSetAttribute(exhaustive_scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+size_t exhaustive_tc_workspace_bytes(uint32_t nq, uint32_t kprime, int num_sms) {
+    return (size_t)64 * nq * (size_t)kprime * 8 + (size_t)num_sms * kTcNQ * kTcCap * 8 + (size_t)nq * 4 + 1024;
+}
+
+// Returns through *nseg the number of per-group segments (the "slices" exhaustive_select_rerank_kernel merges).
+cudaError_t launch_exhaustive_scan_tc(const DevIndex& ix, const ExhaustiveArgs& a, int num_sms, unsigned long long* partial,
+                                      uint32_t* nseg, cudaStream_t stream) {
+    // workspace: partial | lists | taug | vstat
+    uint8_t* ws = reinterpret_cast<uint8_t*>(partial) + (size_t)64 * a.nq * (size_t)a.kprime * 8;
+    unsigned long long* lists = reinterpret_cast<unsigned long long*>(ws);
+    ws += (size_t)num_sms * kTcNQ * kTcCap * 8;
+    uint32_t* taug = reinterpret_cast<uint32_t*>(ws);
+    ws += (((size_t)a.nq * 4 + 15) & ~(size_t)15);
+    float* vstat = reinterpret_cast<float*>(ws);
+    cudaError_t e = cudaMemsetAsync(vstat, 0, 16, stream);
     if (e != cudaSuccess) return e;
-    dim3 grid(nslices, (a.nq + kTcNQ - 1) / kTcNQ);
-    exhaustive_scan_tc_kernel<<<grid, kTcThreads, smem, stream>>>(ix, a, nslices, slice_len, ubytes, partial);
+    exhaustive_tc_prepare_kernel<<<num_sms * 2, 256, 0, stream>>>(ix, a.id_begin, a.id_end, a.nq, vstat, taug);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // work split: (group, tile) units, group-major, an equal contiguous share per CTA; a group may not be cut into
+    // more segments than one CTA can merge (slices x k' keys sorted in shared memory by the second kernel)
+    const uint64_t m = a.id_end - a.id_begin;
+    const uint32_t ngroups = (a.nq + kTcNQ - 1) / kTcNQ;
+    const uint32_t tiles = (uint32_t)((m + kTcM - 1) / kTcM);
+    const uint64_t units = (uint64_t)ngroups * tiles;
+    uint64_t maxseg = a.kprime ? 16384 / (uint64_t)a.kprime : 64;
+    if (maxseg > 64) maxseg = 64;
+    uint64_t W = (units + num_sms - 1) / num_sms;
+    if (maxseg > 1) { const uint64_t wmin = (tiles + maxseg - 2) / (maxseg - 1); if (W < wmin) W = wmin; }
+    else W = tiles;
+    if (W < 1) W = 1;
+    const uint32_t grid = units ? (uint32_t)((units + W - 1) / W) : 1u;
+    *nseg = tiles ? (uint32_t)((tiles + W - 1) / W) + 1u : 1u;
+    if (a.kprime) {   // (segment, query) slots nobody writes must read as empty
+        e = cudaMemsetAsync(partial, 0xFF, (size_t)*nseg * a.nq * (size_t)a.kprime * 8, stream);
+        if (e != cudaSuccess) return e;
+    }
+    const size_t smem = (size_t)kTcStages * 16384 + (size_t)ix.nch * 32768 + sizeof(TcShared) + 1024;
+    const bool dense = a.sums || a.est;
+    auto kern = dense ? exhaustive_scan_tc_kernel<true> : exhaustive_scan_tc_kernel<false>;
+    // more than half an SM's shared memory: exactly one CTA (and its 512 TMEM columns) per SM
+    const size_t smem_req = smem < (size_t)120 * 1024 ? (size_t)120 * 1024 : smem;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kTcThreads, smem_req, stream>>>(ix, a, tiles, W, ngroups, vstat, taug, lists, partial);
     return cudaGetLastError();
 }
 

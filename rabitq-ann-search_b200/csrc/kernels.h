@@ -85,11 +85,12 @@ struct ExhaustiveArgs {
     void* workspace; size_t workspace_bytes;
     int use_tensor_cores;             // 1: tcgen05 scan where applicable, 0: popcount scan
 };
-size_t exhaustive_workspace_bytes(const DevIndex& ix, uint32_t nq, uint64_t m, uint32_t kprime);
+size_t exhaustive_workspace_bytes(const DevIndex& ix, uint32_t nq, uint64_t m, uint32_t kprime, int num_sms);
 cudaError_t launch_exhaustive(const DevIndex& ix, const ExhaustiveArgs& a, int num_sms, cudaStream_t stream);
 // tensor-core form of the scan stage (exhaustive_tc.cu)
 bool exhaustive_tc_applicable(const DevIndex& ix, uint32_t kprime);
-cudaError_t launch_exhaustive_scan_tc(const DevIndex& ix, const ExhaustiveArgs& a, uint32_t nslices, uint64_t slice_len,
-                                      const uint8_t* ubytes, unsigned long long* partial, cudaStream_t stream);
+size_t exhaustive_tc_workspace_bytes(uint32_t nq, uint32_t kprime, int num_sms);
+cudaError_t launch_exhaustive_scan_tc(const DevIndex& ix, const ExhaustiveArgs& a, int num_sms, unsigned long long* partial,
+                                      uint32_t* nseg, cudaStream_t stream);
 
 }  // namespace cpb

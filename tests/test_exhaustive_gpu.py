@@ -19,13 +19,15 @@ def _torch():
     return torch
 
 
-@pytest.mark.parametrize("dim,n", [(128, 5000), (96, 3001), (20, 700), (960, 1200)])
-def test_estimates_match_oracle(oracle, dim, n):
+@pytest.mark.parametrize("tc", [1, 0])
+@pytest.mark.parametrize("dim,n", [(128, 5000), (96, 3001), (20, 700), (960, 1200), (256, 900)])
+def test_estimates_match_oracle(oracle, dim, n, tc):
     from cphnsw_b200 import hooks
 
     torch = _torch()
     fab = common.fabricate(n, dim, 1, seed=dim, degenerate=True, a=1.01, b=0.003)
     ix = common.gpu_index_from(fab)
+    ix.set_option("exhaustive_tensor_cores", tc)   # 1: tcgen05 scan where it applies (D <= 256), 0: popcount scan
     view = oracle.index_view(fab)
     q = np.random.default_rng(1).standard_normal((11, dim)).astype(np.float32)
     q[3] = fab.centroid     # |q - c|^2 == 0: the dist_qp_sq < 1e-12 branch
@@ -37,14 +39,16 @@ def test_estimates_match_oracle(oracle, dim, n):
         assert np.array_equal(_bits(est[i]), _bits(oest))
 
 
+@pytest.mark.parametrize("tc", [1, 0])
 @pytest.mark.parametrize("dim,n,k,kprime", [(128, 6000, 10, 100), (128, 6000, 1, 1), (96, 3001, 10, 1000), (64, 40000, 100, 400),
-                                            (960, 1500, 20, 60), (32, 300, 10, 512)])
-def test_search_matches_oracle(oracle, dim, n, k, kprime):
+                                            (960, 1500, 20, 60), (32, 300, 10, 512), (64, 40000, 100, 256), (256, 9000, 10, 30)])
+def test_search_matches_oracle(oracle, dim, n, k, kprime, tc):
     from cphnsw_b200 import hooks
 
     torch = _torch()
     fab = common.fabricate(n, dim, 1, seed=n + k, degenerate=True)
     ix = common.gpu_index_from(fab)
+    ix.set_option("exhaustive_tensor_cores", tc)
     view = oracle.index_view(fab)
     q = np.random.default_rng(2).standard_normal((19, dim)).astype(np.float32)
     ids, dists = hooks.exhaustive_search(ix, torch.from_numpy(q), k, kprime)
@@ -55,6 +59,30 @@ def test_search_matches_oracle(oracle, dim, n, k, kprime):
         assert np.array_equal(ids[i, :m], oi.astype(np.int64)), i
         assert np.array_equal(_bits(dists[i, :m]), _bits(od))
         assert np.all(ids[i, m:] == -1) and np.all(dists[i, m:] == np.finfo(np.float32).max)
+
+
+def test_tensor_core_scan_equals_popcount_scan_on_a_larger_batch(oracle):
+    """Several query groups (one of them partial), several vertex slices, thresholds shared between CTAs: the
+    tcgen05 scan and the popcount scan must return the same ids and the same distance bits; a sample of the
+    queries is checked against the oracle as well."""
+    from cphnsw_b200 import hooks
+
+    torch = _torch()
+    fab = common.fabricate(150_000, 128, 1, seed=77)
+    ix = common.gpu_index_from(fab)
+    view = oracle.index_view(fab)
+    q = np.random.default_rng(5).standard_normal((700, 128)).astype(np.float32)
+    q[5] = fab.centroid
+    out = {}
+    for tc in (1, 0):
+        ix.set_option("exhaustive_tensor_cores", tc)
+        ids, dists = hooks.exhaustive_search(ix, torch.from_numpy(q), 10, 100)
+        out[tc] = (ids.cpu().numpy(), dists.cpu().numpy())
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(_bits(out[0][1]), _bits(out[1][1]))
+    for i in (0, 5, 255, 256, 511, 699):
+        oi, od, _, _ = oracle.exhaustive(view, fab, q[i], 10, 100)
+        assert np.array_equal(out[1][0][i, :len(oi)], oi.astype(np.int64)), i
+        assert np.array_equal(_bits(out[1][1][i, :len(oi)]), _bits(od))
 
 
 def test_database_shards_merge_to_the_unsharded_answer(oracle):
