@@ -7,8 +7,8 @@
 //
 // One persistent CTA per SM, 21 warps in three roles connected by mbarriers:
 //   expanders (4 warps, thread = vertex row)  code bits -> bytes in the K-major, un-swizzled canonical layout
-//       (8-row x 16-byte core matrices; LBO = 128 B along K, SBO = 1 KB between 8-row groups), a ring of 4
-//       16 KB stages;
+//       (8-row x 16-byte core matrices; LBO = 128 B along K, SBO = 1 KB between 8-row groups), a ring of 3
+//       16 KB stages; they also leave each vertex's three screen numbers in shared memory for the epilogue;
 //   issuer (1 thread)  four tcgen05.mma.cta_group::1.kind::i8 (M = 128, N = 256, K = 32) per 128-dim chunk,
 //       tcgen05.commit releases the stage and, after the last chunk, publishes the accumulator; two
 //       accumulators (2 x 256 TMEM columns) so the next tile's MMAs run under this tile's epilogue;
@@ -33,11 +33,13 @@ namespace cpb {
 
 constexpr int kTcNQ = 256;           // queries per work item = MMA N
 constexpr int kTcM = 128;            // vertices per tile = MMA M
-constexpr int kTcStages = 4;         // A-operand ring
+constexpr int kTcStages = 3;         // A-operand ring
+constexpr int kTcVRing = 8;          // per-tile vertex screen parameters: ring deeper than expander lead + accumulators in flight
 constexpr int kTcCap = 512;          // candidate slots per (CTA, query)
 constexpr uint32_t kTcMaxKPrime = 256;   // k' + one tile of appends must fit the list
 constexpr int kTcExpWarps = 4, kTcEpiWarps = 16;
 constexpr int kTcThreads = (kTcExpWarps + kTcEpiWarps + 1) * 32;   // + the issuer warp
+constexpr int kTcQueue = 1280;        // passer queue entries (4 B) per epilogue warp: 32 columns x 32 lanes + a quarter
 constexpr uint32_t kTcCols = 512;    // TMEM columns: 2 accumulators x 256
 constexpr float kTcBig = 3.0e38f;
 constexpr float kTcTauInf = 1.0e37f;   // tau at or above this = no threshold yet
@@ -72,13 +74,13 @@ __device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t phase) {
     } while (!done);
 }
 // for the roles that run ahead and then wait long (expanders, issuer): do not spin in the epilogue's issue slots
+template <int NS>
 __device__ __forceinline__ void tc_wait_relaxed(uint64_t* bar, uint32_t phase) {
     uint32_t done;
     for (;;) {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(tc_smem_u32(bar)), "r"(phase) : "memory");
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(tc_smem_u32(bar)), "r"(phase), "r"((uint32_t)NS) : "memory");   // suspend-time hint, ns
         if (done) break;
-        __nanosleep(128);
     }
 }
 __device__ __forceinline__ void tc_group_sync(uint32_t id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
@@ -207,25 +209,57 @@ struct TcShared {
     float tau[kTcNQ];
     uint32_t cnt[kTcNQ];
     uint64_t a_full[kTcStages], a_empty[kTcStages], acc_full[2], acc_empty[2];
+    uint32_t qn[kTcEpiWarps];   // passer queue fill, per epilogue warp
     uint32_t tmem_base;
 };
 
-// a pair that passed the screen: the exact estimate, dense outputs (parity hooks), the candidate list
-struct TcExact { float aa, ab, floor_; uint32_t kp; uint32_t* sums; float* est; };
+// Pairs that pass the screen are rare and scattered over lanes, so the lane that finds one only queues a 4-byte
+// record {fs : 12 | column : 8 | row : 7 | tile within the checkpoint window : 2} in its warp's shared-memory queue
+// (a handful of divergent instructions); the queue is drained by the whole warp, one pair per lane: the exact
+// estimate (flat_estimate, the op-for-op AVX2 lane), the dense parity outputs, the append to the candidate list.
+struct TcDrain {
+    const float* nop; const float* ipqo; const uint16_t* pop;
+    float aa, ab, floor_;
+    uint32_t kp, q0;
+    uint64_t id_begin, m;
+    uint32_t* sums; float* est;
+    unsigned long long* lists;
+};
 
+__device__ __forceinline__ uint32_t tc_lds(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tc_enqueue(uint32_t qn_saddr, uint32_t q_saddr, uint32_t rec) {
+    uint32_t pos;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(qn_saddr) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(q_saddr + pos * 4u), "r"(rec) : "memory");
+}
+
+// `wbase` = id of row 0 of the first tile of the current checkpoint window
 template <bool DENSE>
-__device__ __forceinline__ void tc_candidate(const TcExact x, TcShared& sh, unsigned long long* __restrict__ mylists, uint32_t col,
-                                          size_t dense_off, uint32_t id, uint32_t fs, float pc, float nop, float ipqo) {
-    const float4 P = sh.par[col];
-    const float est = flat_estimate(P.x, P.y, P.z, x.aa, x.ab, x.floor_, P.w, fs, pc, nop, ipqo);
-    if (DENSE) {
-        if (x.sums) x.sums[dense_off] = fs;
-        if (x.est) x.est[dense_off] = est;
+__device__ __noinline__ void tc_drain(const TcDrain d, TcShared& sh, const uint32_t* __restrict__ wq, uint32_t* qn, uint32_t lane, uint32_t wbase) {
+    __syncwarp();
+    const uint32_t n = *qn;
+    for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t e = wq[i];
+        const uint32_t fs = e & 0xFFFu, col = (e >> 12) & 0xFFu, id = wbase + (e >> 20);   // (row | tile << 7) = offset in the window
+        const float4 P = sh.par[col];
+        const float est = flat_estimate(P.x, P.y, P.z, d.aa, d.ab, d.floor_, P.w, fs, (float)__ldg(d.pop + id), __ldg(d.nop + id), __ldg(d.ipqo + id));
+        if (DENSE) {
+            const size_t o = (size_t)(d.q0 + col) * d.m + (id - d.id_begin);
+            if (d.sums) d.sums[o] = fs;
+            if (d.est) d.est[o] = est;
+        }
+        if (d.kp && est <= sh.tau[col]) {
+            const uint32_t pos = atomicAdd(&sh.cnt[col], 1u);   // < capacity: lists are trimmed G tiles ahead
+            d.lists[(size_t)col * kTcCap + pos] = make_key(est, id);
+        }
     }
-    if (x.kp && est <= sh.tau[col]) {
-        const uint32_t pos = atomicAdd(&sh.cnt[col], 1u);   // < capacity: lists are trimmed a tile ahead
-        mylists[(size_t)col * kTcCap + pos] = make_key(est, id);
-    }
+    __syncwarp();
+    if (lane == 0) *qn = 0;
+    __syncwarp();
 }
 
 template <bool DENSE>
@@ -239,6 +273,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc_kernel(const
     uint8_t* As = smem_raw;                                           // kTcStages x 16 KB
     uint8_t* Bs = smem_raw + (size_t)kTcStages * 16384;               // nch x 32 KB
     TcShared& sh = *reinterpret_cast<TcShared*>(smem_raw + (size_t)kTcStages * 16384 + (size_t)nch * 32768);
+    uint32_t* queues = reinterpret_cast<uint32_t*>(smem_raw + (size_t)kTcStages * 16384 + (size_t)nch * 32768 + ((sizeof(TcShared) + 15) & ~(size_t)15));   // [kTcEpiWarps][kTcQueue]
+    float4* vring = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(queues) + (size_t)kTcEpiWarps * kTcQueue * 4);   // [kTcVRing][kTcM]
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t kp = a.kprime;
@@ -246,8 +282,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc_kernel(const
     const uint64_t m = a.id_end - a.id_begin;
     const float dmax = (float)(nch * 128u);
     unsigned long long* mylists = lists + (size_t)blockIdx.x * kTcNQ * kTcCap;
-    const uint32_t G = kp ? (kTcCap - kp) / kTcM : 1u;   // 2 or 3: tiles between list checks
-    const TcExact ex{cal.affine_a, cal.affine_b, cal.ip_qo_floor, kp, a.sums, a.est};
+    // tiles between list checks: a list is trimmed when it could overflow before the next check, i.e. at
+    // cnt > cap - 128 G; G = 2 leaves room for ~150 new candidates between two trims of a k' = 100 list
+    const uint32_t G = kp ? min(2u, (kTcCap - kp) / kTcM) : 1u;
 
     TcLimits lim;
     {
@@ -260,6 +297,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc_kernel(const
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&sh.tmem_base)), "r"(kTcCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (tid < (uint32_t)kTcEpiWarps) sh.qn[tid] = 0;
     if (tid == 0) {
         for (int s = 0; s < kTcStages; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(&sh.a_full[s])), "r"(kTcExpWarps));
@@ -325,16 +363,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc_kernel(const
             uint8_t* rowoff = As + (row >> 3) * 1024 + (row & 7u) * 16;
             const uint32_t nsteps = ntiles * nch;
             uint4 nxt = make_uint4(0, 0, 0, 0);
-            if (nsteps && vb + row < ve) nxt = __ldg(reinterpret_cast<const uint4*>(ix.flat_codes + (vb + row) * W));
+            float nop_n = 0.0f, ipqo_n = 0.0f;
+            uint32_t pop_n = 0;
+            if (nsteps && vb + row < ve) {
+                nxt = __ldg(reinterpret_cast<const uint4*>(ix.flat_codes + (vb + row) * W));
+                nop_n = __ldg(ix.flat_nop + vb + row); ipqo_n = __ldg(ix.flat_ipqo + vb + row); pop_n = __ldg(ix.flat_pop + vb + row);
+            }
             for (uint32_t i = 0; i < nsteps; ++i, ++step) {
                 const uint4 w = nxt;
+                const uint32_t c0 = i % nch;
+                if (c0 == 0) {
+                    // the screen numbers of this tile's vertices {-s_v, -alpha_v, -pc_v, what to OR onto the accumulator}:
+                    // 2^23 + fs normally; 2^126 (1 + fs 2^-23) for rows the screen does not apply to -- it clears every
+                    // cut of a present query and the three FMAs, whose vertex factors are then zero, leave it alone;
+                    // NaN, which clears nothing, for rows past the end of the range
+                    const uint64_t v0 = vb + (uint64_t)(i / nch) * kTcM + row;
+                    float sv, av;
+                    bool force;
+                    tc_vertex_params(cal, nop_n, ipqo_n, lim, sv, av, force);
+                    const uint32_t orv = !(v0 < ve) ? 0x7FC00000u : ((force || DENSE) ? 0x7E800000u : 0x4B000000u);
+                    vring[(size_t)(tcount % kTcVRing) * kTcM + row] = make_float4(-sv, -av, force ? 0.0f : -(float)pop_n, __uint_as_float(orv));
+                    ++tcount;
+                    const uint64_t v1 = v0 + kTcM;
+                    if (v1 < ve) { nop_n = __ldg(ix.flat_nop + v1); ipqo_n = __ldg(ix.flat_ipqo + v1); pop_n = __ldg(ix.flat_pop + v1); }
+                }
                 if (i + 1 < nsteps) {
                     const uint32_t t1 = (i + 1) / nch, c1 = (i + 1) % nch;
                     const uint64_t v1 = vb + (uint64_t)t1 * kTcM + row;
                     nxt = v1 < ve ? __ldg(reinterpret_cast<const uint4*>(ix.flat_codes + v1 * W) + c1) : make_uint4(0, 0, 0, 0);
                 }
                 const uint32_t s = step % kTcStages;
-                tc_wait_relaxed(&sh.a_empty[s], ((step / kTcStages) & 1u) ^ 1u);
+                tc_wait_relaxed<4000>(&sh.a_empty[s], ((step / kTcStages) & 1u) ^ 1u);
                 uint8_t* arow = rowoff + (size_t)s * 16384;
                 // this vertex's row of A: 8 pieces of 16 bytes, 128 B apart (one per core matrix along K)
                 *reinterpret_cast<uint4*>(arow + 0 * 128) = expand16(w.x);
@@ -354,10 +413,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc_kernel(const
             if (lane == 0) {
                 for (uint32_t t = 0; t < ntiles; ++t, ++tcount) {
                     const uint32_t buf = tcount & 1u;
-                    tc_wait_relaxed(&sh.acc_empty[buf], ((tcount >> 1) & 1u) ^ 1u);
+                    tc_wait_relaxed<2000>(&sh.acc_empty[buf], ((tcount >> 1) & 1u) ^ 1u);
                     for (uint32_t c = 0; c < nch; ++c, ++step) {
                         const uint32_t s = step % kTcStages;
-                        tc_wait_relaxed(&sh.a_full[s], (step / kTcStages) & 1u);
+                        tc_wait_relaxed<1000>(&sh.a_full[s], (step / kTcStages) & 1u);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                         for (uint32_t ks = 0; ks < 4; ++ks)
@@ -374,32 +433,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc_kernel(const
             const uint32_t row = quarter * 32 + lane;
             const uint32_t colbase = cg * 64;
             const uint32_t own0 = colbase + quarter * 16;     // the 16 lists this warp maintains between tiles
-            float nop_n = 0.0f, ipqo_n = 0.0f;
-            uint32_t pop_n = 0;
-            if (ntiles && vb + row < ve) {
-                nop_n = __ldg(ix.flat_nop + vb + row); ipqo_n = __ldg(ix.flat_ipqo + vb + row); pop_n = __ldg(ix.flat_pop + vb + row);
-            }
+            uint32_t* myq = queues + (size_t)e * kTcQueue;
+            uint32_t* myqn = &sh.qn[e];
+            const uint32_t myq_s = tc_smem_u32(myq), myqn_s = tc_smem_u32(myqn);
+            const TcDrain dr{ix.flat_nop, ix.flat_ipqo, ix.flat_pop, cal.affine_a, cal.affine_b, cal.ip_qo_floor, kp, q0, a.id_begin, m, a.sums, a.est, mylists};
             for (uint32_t t = 0; t < ntiles; ++t, ++tcount) {
-                const uint64_t v = vb + (uint64_t)t * kTcM + row;
-                const bool live = v < ve;
-                const float nop = nop_n, ipqo = ipqo_n, pc = (float)pop_n;
-                {
-                    const uint64_t v1 = v + kTcM;
-                    if (t + 1 < ntiles && v1 < ve) {
-                        nop_n = __ldg(ix.flat_nop + v1); ipqo_n = __ldg(ix.flat_ipqo + v1); pop_n = __ldg(ix.flat_pop + v1);
-                    }
-                }
-                float sv, av;
-                bool force;
-                tc_vertex_params(cal, nop, ipqo, lim, sv, av, force);
-                const float nsv = -sv, nav = -av, npc = force ? 0.0f : -pc;
-                // rows the screen does not apply to: 2^126 (1 + fs 2^-23) instead of 2^23 + fs clears every cut of a
-                // present query (and the three FMAs, whose vertex factors are zero, leave it alone)
-                const uint32_t orv = (force || DENSE) ? 0x7E800000u : 0x4B000000u;
+                const uint32_t rowtag = (row | ((t % G) << 7)) << 20;                           // queue record: where this vertex is
+                const uint32_t wbase = (uint32_t)(vb + (uint64_t)(t - t % G) * kTcM);           // ... relative to this id
 
                 const uint32_t buf = tcount & 1u;
-                tc_wait(&sh.acc_full[buf], (tcount >> 1) & 1u);
+                tc_wait_relaxed<1000>(&sh.acc_full[buf], (tcount >> 1) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const float4 vp = vring[(size_t)(tcount % kTcVRing) * kTcM + row];   // written by the expanders before this tile's MMAs
+                const float nsv = vp.x, nav = vp.y, npc = vp.z;
+                const uint32_t orv = __float_as_uint(vp.w);
 #pragma unroll 1
                 for (uint32_t half = 0; half < 2; ++half) {
                     const uint32_t col0 = colbase + half * 32;
@@ -414,48 +461,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc_kernel(const
                           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                         : "r"(taddr) : "memory");
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    // the screen, 6 instructions per pair (LDS.128, LOP3, 3 FFMA, FSETP.OR): one flag per 8 columns
-                    bool h[4] = {false, false, false, false};
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float4 Q = sh.qpar[col0 + j];
-                        float x = __uint_as_float(r[j] | orv);   // 2^23 + fs, exact
-                        x = __fmaf_rn(nsv, Q.y, x);
-                        x = __fmaf_rn(npc, Q.z, x);
-                        x = __fmaf_rn(nav, Q.x, x);
-                        h[j >> 3] = h[j >> 3] || (x >= Q.w);
+                    if (half == 1) {   // both halves are in registers: the accumulator may be overwritten
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) tc_arrive(&sh.acc_empty[buf]);
                     }
-                    uint32_t hits = live ? ((h[0] ? 1u : 0u) | (h[1] ? 2u : 0u) | (h[2] ? 4u : 0u) | (h[3] ? 8u : 0u)) : 0u;
-                    uint32_t any = __reduce_or_sync(kFull, hits);
-                    while (any) {   // some lane passed somewhere in this group of 8 columns: exact estimates for the passers
-                        const uint32_t g8 = __ffs(any) - 1;
-                        any &= any - 1;
-                        uint32_t f8[8];
-                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                                     : "=r"(f8[0]), "=r"(f8[1]), "=r"(f8[2]), "=r"(f8[3]), "=r"(f8[4]), "=r"(f8[5]), "=r"(f8[6]), "=r"(f8[7])
-                                     : "r"(taddr + g8 * 8) : "memory");
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        if (live && ((hits >> g8) & 1u)) {
+                    // room for every pair of this half (32 columns x 32 lanes)?
+                    if (tc_lds(myqn_s) > (uint32_t)(kTcQueue - 1024)) tc_drain<DENSE>(dr, sh, myq, myqn, lane, wbase);
+                    // the screen, 7 instructions per pair (LDS.128, LOP3, 3 FFMA, FSETP.OR), branch-free over 8 columns;
+                    // only a lane with a hit among its 8 pairs looks at them one by one and queues the passers
 #pragma unroll
-                            for (uint32_t jj = 0; jj < 8; ++jj) {
-                                const uint32_t col = col0 + g8 * 8 + jj, fs = f8[jj];
-                                const float4 Q = sh.qpar[col];
-                                float x = __uint_as_float(fs | orv);
-                                x = __fmaf_rn(nsv, Q.y, x);
-                                x = __fmaf_rn(npc, Q.z, x);
-                                x = __fmaf_rn(nav, Q.x, x);
-                                if (x >= Q.w) tc_candidate<DENSE>(ex, sh, mylists, col, (size_t)(q0 + col) * m + (v - a.id_begin), (uint32_t)v, fs, pc, nop, ipqo);
-                            }
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        float x8[8], w8[8];
+                        bool hit = false;
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            const float4 Q = sh.qpar[col0 + c8 * 8 + jj];
+                            float x = __uint_as_float(r[c8 * 8 + jj] | orv);   // 2^23 + fs, exact
+                            x = __fmaf_rn(nsv, Q.y, x);
+                            x = __fmaf_rn(npc, Q.z, x);
+                            x = __fmaf_rn(nav, Q.x, x);
+                            x8[jj] = x; w8[jj] = Q.w;
+                            hit = hit || (x >= Q.w);
+                        }
+                        if (hit) {
+#pragma unroll
+                            for (int jj = 0; jj < 8; ++jj)
+                                if (x8[jj] >= w8[jj]) tc_enqueue(myqn_s, myq_s, r[c8 * 8 + jj] | ((col0 + (uint32_t)(c8 * 8 + jj)) << 12) | rowtag);
                         }
                     }
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) tc_arrive(&sh.acc_empty[buf]);
 
-                // ---- every G tiles: trim the lists that could overflow before the next check, refresh tau ---------
-                // (a tile appends at most 128 keys to a list; G = the tiles a just-trimmed list of k' keys can take)
-                if (kp && (t % G == G - 1 || t + 1 == ntiles)) {
+                const bool checkpoint = t % G == G - 1 || t + 1 == ntiles;
+                if (checkpoint || DENSE) tc_drain<DENSE>(dr, sh, myq, myqn, lane, wbase);
+                if (kp && checkpoint) {
                     tc_group_sync(1 + cg);   // the four warps appending to these 64 lists are done with this tile
                     const uint32_t mycol = own0 + (lane & 15u);
                     const uint32_t need = __ballot_sync(kFull, lane < 16 && sh.cnt[mycol] + G * kTcM > (uint32_t)kTcCap);
@@ -549,7 +588,7 @@ cudaError_t launch_exhaustive_scan_tc(const DevIndex& ix, const ExhaustiveArgs& 
         e = cudaMemsetAsync(partial, 0xFF, (size_t)*nseg * a.nq * (size_t)a.kprime * 8, stream);
         if (e != cudaSuccess) return e;
     }
-    const size_t smem = (size_t)kTcStages * 16384 + (size_t)ix.nch * 32768 + sizeof(TcShared) + 1024;
+    const size_t smem = (size_t)kTcStages * 16384 + (size_t)ix.nch * 32768 + sizeof(TcShared) + (size_t)kTcEpiWarps * kTcQueue * 4 + (size_t)kTcVRing * kTcM * 16 + 1024;
     const bool dense = a.sums || a.est;
     auto kern = dense ? exhaustive_scan_tc_kernel<true> : exhaustive_scan_tc_kernel<false>;
     // more than half an SM's shared memory: exactly one CTA (and its 512 TMEM columns) per SM
