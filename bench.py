@@ -199,8 +199,9 @@ def reference_module():
     return cphnsw
 
 
-def time_reference(args, path, q, budget_s, steps, warmup):
+def time_reference(args, path, q, budget_s, steps, warmup, k=None):
     """QPS of the stock reference CPIndex.search_batch (all host cores) on a bounded sample of q."""
+    k = args.k if k is None else k
     cph = reference_module()
     if cph is None:
         return None
@@ -211,16 +212,16 @@ def time_reference(args, path, q, budget_s, steps, warmup):
     log(f"[bench] reference loaded the index in {time.time() - t:.1f} s")
     probe = min(len(q), 4 * cores)
     t = time.perf_counter()
-    idx.search_batch(q[:probe], args.k)
+    idx.search_batch(q[:probe], k)
     per_q = (time.perf_counter() - t) / probe
     m = int(min(len(q), max(probe, budget_s / max(per_q, 1e-9) / max(steps + warmup, 1))))
     sample = q[:m]
     for _ in range(warmup):
-        idx.search_batch(sample, args.k)
+        idx.search_batch(sample, k)
     times = []
     for _ in range(steps):
         t = time.perf_counter()
-        ids, _ = idx.search_batch(sample, args.k)
+        ids, _ = idx.search_batch(sample, k)
         times.append(time.perf_counter() - t)
     total = sum(times)
     return {"value": m * steps / total, "unit": "queries/s", "cores": cores, "kind": "reference",
@@ -246,6 +247,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-recall", action="store_true")
     ap.add_argument("--no-stream", action="store_true", help="skip the K2 FastScan streaming micro-benchmark")
+    ap.add_argument("--no-gate", action="store_true", help="skip the recall@10 >= 0.95 operating point")
+    ap.add_argument("--gate", type=float, default=0.95)
     ap.add_argument("--opt", action="append", default=[], help="library tuning option name=value (does not change results)")
     args = ap.parse_args()
 
@@ -449,6 +452,63 @@ def main():
                 line["cpu_baseline"]["ids_identical_to_gpu"] = bool(same)
                 if not args.no_recall:
                     line["cpu_baseline"]["recall_at_10"] = recall_at_k(r["ids"], gt[:r["m"]])
+        # -- the operating point the metric names: recall@10 >= 0.95.  The reference's k results hold ~5 distinct ids
+        #    (it lists a vertex once per time it was scored), which caps recall@10 at k = 10 near 0.5 for
+        #    both arms; so: search k_search > k results exactly as the reference does, de-duplicate (on the device for
+        #    this arm, in numpy for the reference), keep the k best, and find the smallest k_search that clears the
+        #    gate.  Both arms are then timed at that k_search.
+        if world == 1 and not args.no_recall and not args.no_gate:
+            gate, curve = None, []
+            for ks in (20, 40, 80, 160):
+                ui, _ = ix.search_batch_unique(q_dev, args.k, k_search=ks)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                ui, _ = ix.search_batch_unique(q_dev, args.k, k_search=ks)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                rec = recall_at_k(ui.cpu().numpy(), gt)
+                curve.append({"k_search": ks, "recall_at_10": rec, "qps": args.nq / dt})
+                log(f"[bench] k_search={ks}: de-duplicated recall@{args.k} = {rec:.4f} at {args.nq / dt:.0f} QPS")
+                if rec >= args.gate:
+                    gate = {"k_search": ks, "recall_at_10": rec}
+                    break
+            if gate is None:
+                line["recall_gate"] = {"reached": False, "gate": args.gate, "curve": curve,
+                                       "note": "the reference's own search does not reach the gate on this index at any k_search tried "
+                                               "(SURVEY H5); both arms return identical ids, so neither does this one"}
+            else:
+                ks = gate["k_search"]
+                for _ in range(2):
+                    ix.search_batch_unique(q_dev, args.k, k_search=ks)
+                ge = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                torch.cuda.synchronize()
+                ge[0].record()
+                for _ in range(args.steps):
+                    ix.search_batch_unique(q_dev, args.k, k_search=ks)
+                ge[1].record()
+                torch.cuda.synchronize()
+                gate["value"] = args.nq * args.steps / (ge[0].elapsed_time(ge[1]) / 1e3)
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    hi, _ = ix.search_batch_unique(q, args.k, k_search=ks)      # numpy in, numpy out
+                gate["e2e"] = args.nq * args.steps / (time.perf_counter() - t0)
+                gate["unit"] = "queries/s"
+                gate["how"] = (f"search_batch(k={ks}) as the reference does it, then first {args.k} distinct ids "
+                               "(cphnsw_b200_unique_topk on the device)")
+                if not args.no_cpu_baseline:
+                    r = time_reference(args, path, q, budget_s=args.cpu_budget, steps=1, warmup=0, k=ks)
+                    if r is not None:
+                        ri = np.full((r["m"], args.k), -1, np.int64)
+                        for row, src in enumerate(r["ids"]):
+                            u = list(dict.fromkeys(int(x) for x in src if x >= 0))[:args.k]
+                            ri[row, :len(u)] = u
+                        gate["cpu_baseline"] = {"value": r["value"], "unit": "queries/s", "cores": r["cores"], "kind": "reference",
+                                                "sample": r["sample"] + f" at k={ks}; de-duplication (numpy) not timed",
+                                                "recall_at_10": recall_at_k(ri, gt[:r["m"]]),
+                                                "ids_identical_to_gpu": bool(np.array_equal(np.sort(ri, 1), np.sort(hi[:r["m"]], 1)))}
+                gate["reached"] = True
+                gate["curve"] = curve
+                line["recall_gate"] = gate
         print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -153,6 +153,18 @@ int cphnsw_b200_exhaustive_estimates(cphnsw_b200_index* ix, const float* d_queri
                                      uint64_t id_begin, uint64_t id_end,
                                      uint32_t* d_sums, float* d_est, void* stream);
 
+/* ---- opt-in post-processing, outside the parity path ---------------------------------------- */
+/* The reference returns a vertex once per time it was scored (search/rabitq_search.hpp:133,236,250;
+ * BoundedMaxHeap::push does not de-duplicate, :26-35) and internal BFS-reordered ids
+ * (graph/rabitq_graph.hpp:208-278); search_batch reproduces both.  This call cleans a result up:
+ * from each ascending row of k_in pairs (the output of search_batch*, device buffers) it keeps
+ * the first occurrence of every id, writes the first k_out of them padded with -1 / FLT_MAX
+ * (src/bindings.cpp:201-210) and, when d_id_map [map_size] is not NULL, replaces every internal
+ * id by d_id_map[id] (the caller's original id).  In and out buffers must not overlap. */
+int cphnsw_b200_unique_topk(cphnsw_b200_index* ix, const int64_t* d_ids_in, const float* d_dists_in,
+                            uint64_t nq, uint64_t k_in, uint64_t k_out, const uint32_t* d_id_map,
+                            uint64_t map_size, int64_t* d_ids_out, float* d_dists_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,6 +103,7 @@ class CPIndex:
         v = np.ascontiguousarray(v, dtype=np.float32)
         self._host_index = _host().CPIndex(dim=self._dim, bits=self._bits)
         self._finalized = False
+        self._built_from = v
         self._host_index.build(v)
 
     def finalize(self) -> None:
@@ -114,6 +115,9 @@ class CPIndex:
         path = os.path.join(self._tmp.name, "index.bin")
         self._host_index.save(path)
         self._load_device(path)
+        if getattr(self, "_built_from", None) is not None:
+            self.set_original_ids(self._built_from)
+            self._built_from = None
 
     def save(self, path) -> None:
         if not self._finalized:
@@ -125,6 +129,7 @@ class CPIndex:
 
     def load(self, path) -> None:
         self._host_index = None
+        self._id_map = self._id_map_dev = None
         self._load_device(str(path))
 
     def _load_device(self, path: str) -> None:
@@ -188,6 +193,71 @@ class CPIndex:
         _capi.check(self._h, self._lib.cphnsw_b200_search_batch_device(
             self._h, q.data_ptr(), nq, k, ids.data_ptr(), dists.data_ptr(), stream))
         return ids, dists
+
+    # ---- opt-in clean-up of the reference's result conventions (outside the parity path) ---------
+    def search_batch_unique(self, queries, k: int = 10, k_search: int | None = None, original_ids: bool = False):
+        """`search_batch(queries, k_search)` -- bit-identical to the reference's -- followed on the device by
+        de-duplication (the reference lists a vertex once per time it was scored, rabitq_search.hpp:133,236,250)
+        and, with ``original_ids=True``, translation of the internal BFS-reordered ids
+        (rabitq_graph.hpp:208-278) to row numbers of the array given to `build` / `set_original_ids`.
+
+        Returns the k closest distinct neighbours found, padded with -1 / FLT_MAX.  k_search defaults to 3k
+        (the reference returns ~5.3 distinct ids out of 10 on iid data)."""
+        import torch
+
+        k = int(k)
+        ks = int(k_search) if k_search is not None else 3 * max(k, 1)
+        if ks < k:
+            raise ValueError("k_search must be at least k")
+        dev = torch.device("cuda", self._device)
+        cuda_in = _is_torch(queries) and queries.is_cuda
+        q = queries if cuda_in else torch.from_numpy(np.ascontiguousarray(np.asarray(
+            queries.detach() if _is_torch(queries) else queries), dtype=np.float32)).to(dev)
+        ids, dists = self._search_batch_cuda(q, ks)
+        out_i = torch.empty((q.shape[0], k), dtype=torch.int64, device=dev)
+        out_d = torch.empty((q.shape[0], k), dtype=torch.float32, device=dev)
+        idmap = self._device_id_map() if original_ids else None
+        _capi.check(self._h, self._lib.cphnsw_b200_unique_topk(
+            self._h, ids.data_ptr(), dists.data_ptr(), q.shape[0], ks, k,
+            idmap.data_ptr() if idmap is not None else None, idmap.numel() if idmap is not None else 0,
+            out_i.data_ptr(), out_d.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+        if cuda_in:
+            return out_i, out_d
+        return out_i.cpu().numpy(), out_d.cpu().numpy()
+
+    def set_original_ids(self, vectors) -> None:
+        """Recover the internal-id -> original-row map by matching the index's stored vectors (save-file
+        section `raw`, internal order: api/hnsw_index.hpp:217-303) against `vectors` (the array the index was
+        built from).  Rows of `vectors` that are bit-identical are indistinguishable: any of them is returned."""
+        self._require_finalized()
+        v = np.ascontiguousarray(np.asarray(vectors), dtype=np.float32)
+        if v.ndim != 2 or v.shape[1] != self._dim or v.shape[0] != self.size:
+            raise ValueError("vectors must be the (n, dim) float32 array the index was built from")
+        with open(self._source_path, "rb") as f:
+            hdr = f.read(68)
+        D = int.from_bytes(hdr[12:16], "little")
+        n = int.from_bytes(hdr[28:36], "little")
+        off = 68 + 248 + 72 + 4 * self._dim + 8 * n
+        raw = np.memmap(self._source_path, np.float32, "r", off, (n, D))[:, : self._dim]
+        key = lambda a: np.ascontiguousarray(a).view(np.dtype((np.void, 4 * self._dim))).ravel()  # noqa: E731
+        ko, kr = key(v), key(np.ascontiguousarray(raw))
+        order = np.argsort(ko, kind="stable")
+        pos = np.searchsorted(ko[order], kr)
+        pos = np.minimum(pos, n - 1)
+        m = order[pos].astype(np.uint32)
+        if not np.array_equal(ko[m], kr):
+            raise ValueError("the index does not hold these vectors")
+        self._id_map = m
+        self._id_map_dev = None
+
+    def _device_id_map(self):
+        import torch
+
+        if getattr(self, "_id_map", None) is None:
+            raise RuntimeError("original ids are unknown: call set_original_ids(vectors) first (build() does it)")
+        if getattr(self, "_id_map_dev", None) is None:
+            self._id_map_dev = torch.from_numpy(self._id_map.view(np.int32)).to(torch.device("cuda", self._device))
+        return self._id_map_dev
 
     def _require_finalized(self):
         if not self._finalized:

@@ -717,4 +717,17 @@ int cphnsw_b200_exhaustive_estimates(cphnsw_b200_index* ix, const float* d_queri
                           static_cast<cudaStream_t>(stream));
 }
 
+int cphnsw_b200_unique_topk(cphnsw_b200_index* ix, const int64_t* d_ids_in, const float* d_dists_in, uint64_t nq,
+                            uint64_t k_in, uint64_t k_out, const uint32_t* d_id_map, uint64_t map_size,
+                            int64_t* d_ids_out, float* d_dists_out, void* stream) {
+    if (!ix) return CPHNSW_B200_EINVAL;
+    if (nq == 0 || k_out == 0) return 0;
+    if (!d_ids_in || !d_dists_in || !d_ids_out || !d_dists_out) return fail(ix, CPHNSW_B200_EINVAL, "null buffer");
+    if (k_in > 0x7FFFFFFFull || k_out > 0x7FFFFFFFull) return fail(ix, CPHNSW_B200_EINVAL, "argument too large");
+    CUDA_TRY(ix, cudaSetDevice(ix->device));
+    CUDA_TRY(ix, launch_unique_topk(d_ids_in, d_dists_in, nq, (uint32_t)k_in, (uint32_t)k_out, d_id_map, map_size, d_ids_out,
+                                    d_dists_out, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
 }  // extern "C"

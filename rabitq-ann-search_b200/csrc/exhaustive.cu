@@ -1,7 +1,7 @@
 // K5 -- exhaustive batched scan over the per-vertex 1-bit RaBitQ codes, exact-L2 rerank, top-k.
 //
 // The reference has no brute-force mode; this composes its primitives exactly as the
-// oracle does (oracle/cphnsw_oracle.c, cpo_exhaustive_search): per query q: qc = q - centroid,
+// test oracle does: per query q: qc = q - centroid,
 // encode_query_raw(qc) (K1 with center = 1), for every vertex v in [id_begin, id_end):
 //   sum  = compute_inner_products(lut, code_v)                  (distance/fastscan_kernel.hpp:17-87)
 //   est  = convert_to_distances_with_bounds, AVX2 lane, with nop/ip_qo of the vertex's own code
@@ -18,10 +18,10 @@
 // select_rerank: one CTA per query merges the slices' lists, keeps k', re-ranks them with exact
 // distances in the reference's 8-accumulator order and writes the k best.
 //
-// This version computes the integer sums with the popcount formulation shared with K2/K3 (exact).  The
-// dense Q x N contraction it evaluates is the one place of the query path that maps onto tensor cores
-// (tcgen05 kind::i8 over bit-expanded codes); DESIGN.md records why that variant is queued behind the
-// graph path and what its roofline is.
+// This file computes the integer sums with the popcount formulation shared with K2/K3 (exact).  The dense
+// Q x N contraction is the one place of the query path that maps onto tensor cores: exhaustive_tc.cu is the
+// tcgen05 kind::i8 form of the scan stage (used where it applies; this one serves D > 256, k' > 256 and a
+// non-positive affine_a), both feed exhaustive_select_rerank_kernel below.
 #include "exhaustive_common.cuh"
 
 namespace cpb {

@@ -93,4 +93,8 @@ size_t exhaustive_tc_workspace_bytes(uint32_t nq, uint32_t kprime, int num_sms);
 cudaError_t launch_exhaustive_scan_tc(const DevIndex& ix, const ExhaustiveArgs& a, int num_sms, unsigned long long* partial,
                                       uint32_t* nseg, cudaStream_t stream);
 
+// ---- result post-processing, outside the parity path (postprocess.cu) -----------------------------------
+cudaError_t launch_unique_topk(const int64_t* ids_in, const float* dists_in, uint64_t nq, uint32_t kin, uint32_t kout,
+                               const uint32_t* id_map, uint64_t map_size, int64_t* ids_out, float* dists_out, cudaStream_t stream);
+
 }  // namespace cpb

@@ -393,3 +393,65 @@ def test_golden_kernel_vectors():
                 assert np.array_equal(out[name][v].view(np.uint32), g2[f"{name}_{tag}"][v]), (tag, name, v)
             for name in ("est", "lower", "msb_lower"):
                 assert np.array_equal(_bits(out[name][v][:c]), _bits(g2[f"{name}_{tag}"][v][:c])), (tag, name, v)
+
+
+# ---------------------------------------------------------------------------------------------------
+# opt-in post-processing: de-duplication and original ids, outside the parity path
+# ---------------------------------------------------------------------------------------------------
+def _numpy_unique_topk(ids, dists, k, idmap=None):
+    out_i = np.full((ids.shape[0], k), -1, np.int64)
+    out_d = np.full((ids.shape[0], k), np.finfo(np.float32).max, np.float32)
+    for r in range(ids.shape[0]):
+        seen, p = set(), 0
+        for i, d in zip(ids[r].tolist(), dists[r].tolist()):
+            if i < 0 or i in seen or p >= k:
+                continue
+            seen.add(i)
+            out_i[r, p] = i if idmap is None else int(idmap[i])
+            out_d[r, p] = d
+            p += 1
+    return out_i, out_d
+
+
+@pytest.mark.parametrize("k,ks", [(10, 30), (1, 1), (10, 10), (40, 100), (5, 300)])
+def test_unique_topk_is_the_deduplicated_prefix_of_the_parity_result(k, ks):
+    fab = common.fabricate(2000, 32, 2, seed=9, layers=1, counts=(32, 31, 7), degenerate=True)
+    ix = common.gpu_index_from(fab)
+    q = np.random.default_rng(3).standard_normal((37, 32)).astype(np.float32)
+    ids, dists = ix.search_batch(q, ks)                      # the reference's convention: duplicates, internal ids
+    assert any(len(set(r.tolist())) < len(r) for r in ids) or ks == 1
+    ui, ud = ix.search_batch_unique(q, k, k_search=ks)
+    wi, wd = _numpy_unique_topk(ids, dists, k)
+    assert np.array_equal(ui, wi) and np.array_equal(_bits(ud), _bits(wd))
+    for r in ui:
+        live = r[r >= 0]
+        assert len(set(live.tolist())) == len(live)
+
+
+@needs_ref
+def test_original_ids_and_recall_through_the_drop_in_api():
+    """build()/finalize() through the wrapper recover internal -> original ids; with them and de-duplication the
+    returned neighbours can be scored against brute force on the caller's own array."""
+    import cphnsw_b200
+
+    cphnsw_b200.set_host_module(co.ref_module())
+    base = co.synthetic(4000, 48, seed=5, clusters=16)
+    q = common.queries_for(48, 64, seed=6, clusters=16, base_seed=5)
+    ix = cphnsw_b200.CPIndex(48, bits=4)
+    ix.build(base)
+    ix.finalize()
+    ids, dists = ix.search_batch_unique(q, 10, k_search=40, original_ids=True)
+    # distances are those of the returned original rows
+    for r in range(len(q)):
+        live = ids[r] >= 0
+        ex = ((base[ids[r][live]] - q[r]) ** 2).sum(1)
+        assert np.allclose(ex, dists[r][live], rtol=1e-4, atol=1e-4)
+    gt = np.argsort(((base[None, :, :] - q[:, None, :]) ** 2).sum(2), axis=1)[:, :10]
+    recall = np.mean([len(set(a.tolist()) & set(b.tolist())) / 10 for a, b in zip(ids, gt)])
+    # (the reference's own search quality on this data; what matters here is that the ids mean something)
+    assert recall > 0.7, recall
+    # the raw parity result scored the same way is capped by its duplicates
+    pi, _ = ix.search_batch(q, 10)
+    assert np.mean([len(set(r.tolist())) for r in pi]) < 10
+    raw = np.mean([len(set(ix._id_map[a[a >= 0]].tolist()) & set(b.tolist())) / 10 for a, b in zip(pi, gt)])
+    assert recall > raw + 0.1, (recall, raw)
