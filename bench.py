@@ -230,13 +230,196 @@ def time_reference(args, path, q, budget_s, steps, warmup, k=None):
 
 
 # ---------------------------------------------------------------------------------------------------
+# workload c4 (BASELINE config 4): exhaustive batched scan over 1-bit per-vertex codes, database sharded over the ranks
+# ---------------------------------------------------------------------------------------------------
+def _c4_calibration() -> bytes:
+    """A CalibrationSnapshot (api/hnsw_index.hpp:33-58) as finalize() leaves it in practice: a = 1, b = 0."""
+    import struct
+
+    buf = bytearray(248)
+    struct.pack_into("<3f", buf, 0, 1.0, 0.0, 0.3)
+    struct.pack_into("<3f", buf, 80, 1.0e7, 1.0e7, 0.0)
+    struct.pack_into("<f", buf, 240, 1.0e7)
+    return bytes(buf)
+
+
+def _c4_upload(cph, hooks, dim, D, local, sd, raw, norm_sq, centroid):
+    ix = cph.CPIndex(dim, 1, device=local)
+    hooks.upload_arrays(ix, D=D, bits=1, dim=dim, search_data=sd, raw=raw, norm_sq=norm_sq, calibration=_c4_calibration(),
+                        centroid=centroid, max_level=0, entry_point=0, graph_entry_point=0, rotation_seed=42, layers=[])
+    return ix
+
+
+def run_c4(args, rank, world, local):
+    """n x 96 (padded to 128) synthetic vectors, 1-bit RaBitQ codes, nq queries, top-k' estimates re-ranked exactly.
+    The reference has no exhaustive mode and cannot build 10M vectors in bench time, and the scan reads only the
+    per-vertex codes, so each rank encodes its own shard exactly as RaBitQEncoder::encode_impl does
+    (encoder/rabitq_encoder.hpp:225-262; the rotation is K1's, i.e. the index's own) and leaves the neighbour
+    blocks empty.  Step = scan of the rank's shard for all queries, NCCL all-gather of the per-shard top-k,
+    device-side k-way merge.  Strong scaling: the database is fixed, shards shrink with N."""
+    import torch
+    import torch.distributed as dist
+
+    import cphnsw_b200 as cph
+    from cphnsw_b200 import hooks, sharding
+
+    dev = torch.device("cuda", local)
+    n, dim, D, k, kp, nq = args.n, 96, 128, args.k, args.kprime, args.nq
+    b, e = sharding.db_shard(n, rank, world)
+    m = e - b
+    chunk = 1 << 20
+
+    def gen_chunk(c):   # chunk c of the database, the same on every rank
+        g = torch.Generator(device=dev); g.manual_seed(args.seed + c)
+        return torch.randn((min(chunk, n - c * chunk), dim), generator=g, device=dev)
+
+    t0 = time.time()
+    base = torch.empty((m, dim), dtype=torch.float32, device=dev)
+    for c in range(b // chunk, (e + chunk - 1) // chunk):
+        x = gen_chunk(c)
+        lo, hi = max(b, c * chunk), min(e, c * chunk + x.shape[0])
+        base[lo - b:hi - b] = x[lo - c * chunk:hi - c * chunk]
+    csum = base.sum(0, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(csum)
+    centroid = (csum / n).to(torch.float32)
+    cen_np = centroid.cpu().numpy()
+    # record layout of VertexSearchData<128,32,1> (SURVEY App. B): per-vertex code at 0 (signs 16 B, nop @64, ip_qo @68),
+    # neighbour block at 128: ids @ +960 (0xFFFFFFFF = empty), count @ +1088
+    rec, nb_off = 1280, 128
+    tiny = _c4_upload(cph, hooks, dim, D, local, np.zeros((64, rec), np.uint8), np.zeros((64, D), np.float32), np.zeros(64, np.float32), cen_np)
+    sd = np.zeros((m, rec), np.uint8)
+    raw = np.zeros((m, D), np.float32)
+    norm_sq = np.empty(m, np.float32)
+    step = 1 << 18
+    shifts = torch.arange(8, device=dev, dtype=torch.uint8)
+    for s in range(0, m, step):
+        x = base[s:s + step]
+        rot = hooks.prepare_queries(tiny, x, center=True)["rotated"]
+        nop = (x - centroid).norm(dim=1)
+        packed = ((rot >= 0).to(torch.uint8).reshape(-1, D // 8, 8) << shifts).sum(2).to(torch.uint8)
+        ipqo = (rot.abs().sum(1) / (nop.clamp_min(1e-30) * (D ** 0.5))).to(torch.float32)
+        t = s + x.shape[0]
+        sd[s:t, :D // 8] = packed.cpu().numpy()
+        sd[s:t, 64:68] = nop.cpu().numpy().view(np.uint8).reshape(-1, 4)
+        sd[s:t, 68:72] = ipqo.cpu().numpy().view(np.uint8).reshape(-1, 4)
+        sd[s:t, nb_off + 960:nb_off + 1088] = 0xFF
+        raw[s:t, :dim] = x.cpu().numpy()
+        norm_sq[s:t] = (x * x).sum(1).cpu().numpy()
+    del tiny
+    ix = _c4_upload(cph, hooks, dim, D, local, sd, raw, norm_sq, cen_np)
+    del sd, raw
+    info = ix.info()
+    log(f"[bench] rank {rank}: shard [{b}, {e}) encoded and on cuda:{local} in {time.time() - t0:.1f} s, {info['device_bytes'] / 2**30:.1f} GiB")
+
+    gq = torch.Generator(device=dev); gq.manual_seed(99)
+    q_dev = torch.randn((nq, dim), generator=gq, device=dev)
+    q_pin = q_dev.cpu().pin_memory()
+    all_i = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
+    all_d = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
+
+    def step_dev(q):
+        ids, d = hooks.exhaustive_search(ix, q, k, kp)
+        ids = torch.where(ids >= 0, ids + b, ids)          # shard-local -> global ids
+        if world == 1:
+            return ids, d
+        dist.all_gather_into_tensor(all_i, ids)
+        dist.all_gather_into_tensor(all_d, d)
+        return sharding.merge_topk_device(all_i, all_d, k)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t_ = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_.item())
+
+    for _ in range(args.warmup):
+        step_dev(q_dev)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    with ClockSampler(local) as clocks:
+        time.sleep(0.2)
+        evs[0].record()
+        for i in range(args.steps):
+            out_i, out_d = step_dev(q_dev)
+            evs[i + 1].record()
+        barrier()
+    dev_ms = max_over_ranks(evs[0].elapsed_time(evs[-1]))
+    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    value = nq * args.steps / (dev_ms / 1e3)
+    # e2e: queries from pinned host memory, results back to the host, every step
+    ids_pin = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+    d_pin = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        oi, od = step_dev(q_pin.to(dev, non_blocking=True))
+        ids_pin.copy_(oi, non_blocking=True); d_pin.copy_(od, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t1)
+
+    # roofline of the scan kernel: tensor pipe, 2 D int8 operations per (vertex, query) pair of this rank's shard
+    pairs = float(m) * nq
+    scan_ms = float(np.mean(step_ms))
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except (OSError, ValueError):
+        pass
+    bf16 = float(peaks.get("bf16_tflops", peaks.get("bf16_tfs", 1650.0)))
+    achieved = pairs * 2 * D / (scan_ms / 1e3) / 1e12
+    line = {"metric": "QPS (exhaustive batched scan, queries/s over the whole database)", "value": value, "unit": "queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8 x u8 -> s32 (tcgen05 kind::i8) + f32", "data": "synthetic",
+            "config": {"workload": f"c4: {n}x{dim} synthetic iid N(0,1), 1-bit RaBitQ codes, exhaustive scan, {nq} queries, k={k}, k'={kp}",
+                       "parallelism": f"database sharded x{world}, per-shard top-k, NCCL all-gather, device merge",
+                       "l2": "the scan streams codes + 256-query operands; candidate lists live in L2 by design"},
+            "e2e": {"value": nq * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * k * 12},
+            "gpu_launches": 5 * args.steps,
+            "roofline": {"bound": "tensor", "kernel": "exhaustive_scan_tc_kernel (tcgen05.mma kind::i8, M=128 N=256 K=32)", "achieved": achieved,
+                         "peak": 2.0 * bf16, "peak_source": "2 x MEASURED_PEAKS bf16 (int8 dense rate is twice bf16)", "unit": "TOP/s",
+                         "frac": achieved / (2.0 * bf16), "traffic": None, "pairs_per_s_per_gpu": pairs / (scan_ms / 1e3),
+                         "note": "whole step timed (prep + scan + select/rerank + merge); the scan kernel is > 90% of it; it is bound by "
+                                 "the issue slots of its per-pair candidate screen, not by the tensor pipe (DESIGN.md)"},
+            "clocks": clocks.summary(), "step_ms": [round(x, 3) for x in step_ms]}
+    if rank == 0:
+        # recall@10 of the 1-bit estimate + exact rerank against brute force, on a sample of the queries (shard 0's view
+        # is the whole database only at N = 1; otherwise scored on the merged result against this rank's shard is not
+        # meaningful, so N > 1 skips it)
+        if world == 1 and not args.no_recall:
+            ns = min(nq, 500)
+            qs = q_dev[:ns]
+            bd = torch.full((ns, k), float("inf"), device=dev); bi = torch.zeros((ns, k), dtype=torch.int64, device=dev)
+            for s in range(0, m, chunk):
+                bb = base[s:s + chunk]
+                dd = (qs * qs).sum(1, keepdim=True) - 2.0 * (qs @ bb.T) + (bb * bb).sum(1)[None, :]
+                td, ti = torch.topk(dd, k, dim=1, largest=False)
+                cd, ci = torch.cat([bd, td], 1), torch.cat([bi, ti + s], 1)
+                bd, sel = torch.topk(cd, k, dim=1, largest=False)
+                bi = torch.gather(ci, 1, sel)
+            line["recall_at_10"] = recall_at_k(out_i[:ns].cpu().numpy(), bi.cpu().numpy())
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--nvec", "--n", dest="n", type=int, default=1_000_000)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
+                    help="c2: BASELINE configs[1], graph search (the default and the headline); c4: configs[3], exhaustive scan")
+    ap.add_argument("--kprime", type=int, default=100, help="c4: rerank depth")
+    ap.add_argument("--nvec", "--n", dest="n", type=int, default=None)
     ap.add_argument("--dim", type=int, default=128)
     ap.add_argument("--bits", type=int, default=4)
     ap.add_argument("--nq", type=int, default=10_000)
@@ -255,6 +438,24 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.n is None:
+        args.n = 10_000_000 if args.workload == "c4" else 1_000_000
+    if args.workload == "c4":
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the reference has no exhaustive-scan mode (SURVEY F9)"}))
+            return
+        import torch
+
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the query path has no CPU fallback")
+        torch.cuda.set_device(local)
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        run_c4(args, rank, world, local)
+        return
     workload = (f"{args.n}x{args.dim} synthetic {'clustered(%d)' % args.clusters if args.clusters else 'iid N(0,1)'}, "
                 f"{args.bits}-bit RaBitQ CP-HNSW graph search, {args.nq} queries/GPU, k={args.k}")
     metric = "QPS (search_batch queries/s; recall@10 of the reference on the same index reported beside it)"

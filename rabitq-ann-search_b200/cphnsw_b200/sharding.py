@@ -52,6 +52,27 @@ def merge_topk(ids: np.ndarray, dists: np.ndarray, k: int):
     return out_i.astype(np.int64), out_d
 
 
+def merge_topk_device(all_ids, all_dists, k: int):
+    """merge_topk on the device: torch tensors [shards, nq, k'] -> ([nq, k] int64, [nq, k] float32), the same
+    (distance, id) order.  Distances are >= 0, so their bit patterns order like the floats; ids are < 2^32."""
+    import torch
+
+    s, nq, kk = all_ids.shape
+    ii = all_ids.permute(1, 0, 2).reshape(nq, s * kk)
+    dd = all_dists.permute(1, 0, 2).reshape(nq, s * kk).contiguous()
+    key = (dd.view(torch.int32).to(torch.int64) << 32) | (ii & 0xFFFFFFFF)
+    key = torch.where(ii < 0, torch.full_like(key, torch.iinfo(torch.int64).max), key)
+    kk_out = min(k, s * kk)
+    sel = torch.topk(key, kk_out, dim=1, largest=False, sorted=True).indices
+    out_i = torch.gather(ii, 1, sel)
+    out_d = torch.gather(dd, 1, sel)
+    out_d = torch.where(out_i < 0, torch.full_like(out_d, float(_FLT_MAX)), out_d)
+    if kk_out < k:
+        out_i = torch.cat([out_i, torch.full((nq, k - kk_out), -1, dtype=out_i.dtype, device=out_i.device)], 1)
+        out_d = torch.cat([out_d, torch.full((nq, k - kk_out), float(_FLT_MAX), dtype=out_d.dtype, device=out_d.device)], 1)
+    return out_i, out_d
+
+
 def _dist():
     import torch.distributed as dist
 

@@ -57,3 +57,22 @@ def test_two_ranks_match_one(tmp_path, mode):
             a, b, _, _ = o.exhaustive(view, fab, q[i], 5, 5000)
             assert np.array_equal(got["ids"][i, :len(a)], a.astype(np.int64))
             assert np.array_equal(got["d"][i, :len(a)], b)
+
+
+def test_device_merge_equals_the_numpy_merge():
+    """merge_topk_device (torch ops; the NCCL path's merge) against merge_topk, ties and padding included."""
+    import torch
+
+    sys.path.insert(0, str(common.ROOT / "rabitq-ann-search_b200"))
+    from cphnsw_b200 import sharding
+
+    rng = np.random.default_rng(0)
+    shards, nq, kk = 4, 33, 7
+    d = np.sort(rng.integers(0, 50, (shards, nq, kk)).astype(np.float32) * 0.25, axis=2)   # many exact ties
+    i = rng.permutation(shards * nq * kk).reshape(shards, nq, kk).astype(np.int64)
+    i[1, 3, 4:] = -1; d[1, 3, 4:] = np.finfo(np.float32).max                                  # a short shard list
+    i[:, 5, :] = -1; d[:, 5, :] = np.finfo(np.float32).max                                    # a query with no result
+    for k in (1, 5, 7, 30):
+        wi, wd = sharding.merge_topk(i, d, k)
+        gi, gd = sharding.merge_topk_device(torch.from_numpy(i), torch.from_numpy(d), k)
+        assert np.array_equal(gi.numpy(), wi) and np.array_equal(gd.numpy().view(np.uint32), wd.view(np.uint32)), k
