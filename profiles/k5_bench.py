@@ -21,7 +21,7 @@ from common import co
 from cphnsw_b200 import hooks
 import cphnsw_b200
 
-args = [a for a in sys.argv[1:] if not a.startswith('--')]
+args = [a for i, a in enumerate(sys.argv[1:], 1) if not a.startswith('--') and sys.argv[i - 1] not in ('--modes', '--clusters')]
 n = int(args[0]) if len(args) > 0 else 10_000_000
 nq = int(args[1]) if len(args) > 1 else 10_000
 kp = int(args[2]) if len(args) > 2 else 100
@@ -82,6 +82,8 @@ print(f"[k5_bench] index on the device in {time.time() - t0:.1f} s, {ix.info()['
 q = gen(nq)
 res = {}
 modes = (1, 0) if '--popcount' in sys.argv else (1,)
+if '--modes' in sys.argv:
+    modes = tuple(int(x) for x in sys.argv[sys.argv.index('--modes') + 1].split(','))
 for tc in modes:
     ix.set_option("exhaustive_tensor_cores", tc)
     times = []
@@ -96,8 +98,9 @@ for tc in modes:
     pairs = n * nq / ms * 1e3
     print(f"[k5_bench] tensor_cores={tc} n={n} nq={nq} k'={kp}: {ms:.2f} ms/batch ({[round(t, 2) for t in times]}), {nq / ms * 1e3:.0f} QPS, "
           f"{pairs:.3e} pairs/s, {pairs * 2 * D / 1e12:.1f} int8 TOP/s", flush=True)
-if len(res) == 2:
-    print("[k5_bench] identical:", np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1].view(np.uint32), res[1][1].view(np.uint32)))
+if len(res) >= 2:
+    ks = list(res)
+    print("[k5_bench] identical:", all(np.array_equal(res[ks[0]][0], res[k_][0]) and np.array_equal(res[ks[0]][1].view(np.uint32), res[k_][1].view(np.uint32)) for k_ in ks[1:]))
 
 # recall@10 on a sample: exact brute force
 ns = min(nq, 500)

@@ -189,7 +189,7 @@ int cphnsw_b200_set_option(cphnsw_b200_index* ix, const char* name, int64_t valu
     if (n == "warps_per_cta") { if (value < 1 || value > 8) return fail(ix, CPHNSW_B200_EINVAL, "warps_per_cta must be 1..8"); ix->warps_per_cta = value; }
     else if (n == "ctas_per_sm") { if (value < 1 || value > 32) return fail(ix, CPHNSW_B200_EINVAL, "ctas_per_sm must be 1..32"); ix->ctas_per_sm = value; }
     else if (n == "collect_stats") ix->collect_stats = value ? 1 : 0;
-    else if (n == "exhaustive_tensor_cores") ix->exhaustive_tensor_cores = value ? 1 : 0;
+    else if (n == "exhaustive_tensor_cores") ix->exhaustive_tensor_cores = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (n == "beam_capacity") { if (value < 64) return fail(ix, CPHNSW_B200_EINVAL, "beam_capacity must be >= 64"); ix->beam_capacity = value; }
     else return fail(ix, CPHNSW_B200_EINVAL, "unknown option " + n);
     return 0;
@@ -687,7 +687,7 @@ static int run_exhaustive(cphnsw_b200_index* ix, const float* d_queries, uint64_
     CUDA_TRY(ix, launch_query_prep(d, d_queries, (uint32_t)nq, 1, po, st));
     ExhaustiveArgs a{};
     a.uplanes = qs.uplanes; a.coeffs = qs.coeffs; a.qT = qs.qT; a.ubytes = qs.ubytes; a.nq = (uint32_t)nq;
-    a.use_tensor_cores = ix->exhaustive_tensor_cores ? 1 : 0;
+    a.use_tensor_cores = (int)ix->exhaustive_tensor_cores;
     a.id_begin = id_begin; a.id_end = id_end; a.k = (uint32_t)k; a.kprime = (uint32_t)kprime;
     a.sums = d_sums; a.est = d_est; a.ids = d_ids; a.dists = d_dists;
     const size_t wb = exhaustive_workspace_bytes(d, (uint32_t)nq, id_end - id_begin, (uint32_t)kprime, ix->num_sms);

@@ -210,7 +210,10 @@ cudaError_t launch_exhaustive(const DevIndex& ix, const ExhaustiveArgs& a, int n
     const size_t smem = (size_t)kQT * cap * 8 + (size_t)kQT * ix.nch * 64 + (size_t)kQT * 16;
     cudaError_t e = cudaFuncSetAttribute(exhaustive_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    if (tc) {
+    if (tc && a.use_tensor_cores >= 2 && exhaustive_tc16_applicable(ix, a.kprime)) {
+        e = launch_exhaustive_scan_tc16(ix, a, num_sms, partial, &nslices, stream);
+        if (e != cudaSuccess) return e;
+    } else if (tc) {
         e = launch_exhaustive_scan_tc(ix, a, num_sms, partial, &nslices, stream);
         if (e != cudaSuccess) return e;
     } else if (m > 0 || a.kprime) {

@@ -27,87 +27,9 @@
 // array (atomicMin): what ends in the lists differs from run to run, the k' smallest keys never do.
 // A work item is (group of 256 queries, slice of vertices); each item leaves its <= k' best keys in
 // partial[slice][query][k'], merged and re-ranked by exhaustive_select_rerank_kernel (exhaustive.cu).
-#include "exhaustive_common.cuh"
+#include "exhaustive_tc_common.cuh"
 
 namespace cpb {
-
-constexpr int kTcNQ = 256;           // queries per work item = MMA N
-constexpr int kTcM = 128;            // vertices per tile = MMA M
-constexpr int kTcStages = 3;         // A-operand ring
-constexpr int kTcVRing = 8;          // per-tile vertex screen parameters: ring deeper than expander lead + accumulators in flight
-constexpr int kTcCap = 512;          // candidate slots per (CTA, query)
-constexpr uint32_t kTcMaxKPrime = 256;   // k' + one tile of appends must fit the list
-constexpr int kTcExpWarps = 4, kTcEpiWarps = 16;
-constexpr int kTcThreads = (kTcExpWarps + kTcEpiWarps + 1) * 32;   // + the issuer warp
-constexpr int kTcQueue = 1280;        // passer queue entries (4 B) per epilogue warp: 32 columns x 32 lanes + a quarter
-constexpr uint32_t kTcCols = 512;    // TMEM columns: 2 accumulators x 256
-constexpr float kTcBig = 3.0e38f;
-constexpr float kTcTauInf = 1.0e37f;   // tau at or above this = no threshold yet
-
-__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor layout, version 1)
-__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46);
-}
-
-__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
-}
-
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t phase) {
-    uint32_t done;
-    do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(tc_smem_u32(bar)), "r"(phase) : "memory");
-    } while (!done);
-}
-// for the roles that run ahead and then wait long (expanders, issuer): do not spin in the epilogue's issue slots
-template <int NS>
-__device__ __forceinline__ void tc_wait_relaxed(uint64_t* bar, uint32_t phase) {
-    uint32_t done;
-    for (;;) {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(tc_smem_u32(bar)), "r"(phase), "r"((uint32_t)NS) : "memory");   // suspend-time hint, ns
-        if (done) break;
-    }
-}
-__device__ __forceinline__ void tc_group_sync(uint32_t id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
-
-// 16 code bits -> 16 bytes (0/1), little-endian bit order
-__device__ __forceinline__ uint4 expand16(uint32_t bits) {
-    uint4 r;
-    r.x = ((bits & 0xFu) * 0x00204081u) & 0x01010101u;
-    r.y = (((bits >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
-    r.z = (((bits >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
-    r.w = (((bits >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
-    return r;
-}
-
-// ---- the screen's per-vertex and per-query numbers ----------------------------------------------------
-struct TcLimits { float slim, alim; };   // vertices with s_v or |alpha_v| above these skip the screen
-
-// s_v, alpha_v = s_v w_v; `force` = the screen does not apply to this vertex (every pair gets the exact estimate)
-__device__ __forceinline__ void tc_vertex_params(const Calib& cal, float nop, float ipqo, const TcLimits& lim, float& sv, float& av,
-                                                 bool& force) {
-    const float qv = max_ps(ipqo, cal.ip_qo_floor);
-    const float den = __fmul_rn(__fmul_rn(2.0f, nop), cal.affine_a);
-    sv = __fdiv_rn(qv, den);
-    av = __fmul_rn(sv, __fmul_rn(nop, __fsub_rn(nop, __fmul_rn(2.0f, cal.affine_b))));
-    force = !(qv > 1e-10f) || !(den > 0.0f) || !(sv <= lim.slim) || !(fabsf(av) <= lim.alim);
-    if (force) { sv = 0.0f; av = 0.0f; }
-}
 
 // {1/A, (dqp - tau)/A, -Bc/A, cut}: pair (v, q) passes the screen iff
 //     (2^23 + fs) - alpha_v x - s_v y - pc_v z  >=  cut            (three FMAs at magnitude 2^23: <= 1.5 of rounding)
@@ -131,9 +53,9 @@ __device__ __forceinline__ float4 tc_query_params(bool valid, float A, float Bc,
 
 // mean of s_v and |alpha_v| over the scanned range -> limits (16 x mean); also resets the shared thresholds
 __global__ void exhaustive_tc_prepare_kernel(const DevIndex ix, uint64_t id_begin, uint64_t id_end, uint32_t nq, float* __restrict__ acc,
-                                             uint32_t* __restrict__ taug) {
+                                             uint32_t* __restrict__ taug, int reset_tau) {
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = gid; i < nq; i += stride) taug[i] = __float_as_uint(FLT_MAX);
+    if (reset_tau) for (uint64_t i = gid; i < nq; i += stride) taug[i] = __float_as_uint(FLT_MAX);
     const Calib& cal = ix.calib;
     float s = 0.0f, a = 0.0f, c = 0.0f;
     TcLimits none{FLT_MAX, FLT_MAX};
@@ -147,60 +69,6 @@ __global__ void exhaustive_tc_prepare_kernel(const DevIndex ix, uint64_t id_begi
         s += __shfl_xor_sync(kFull, s, o); a += __shfl_xor_sync(kFull, a, o); c += __shfl_xor_sync(kFull, c, o);
     }
     if ((threadIdx.x & 31) == 0 && c > 0.0f) { atomicAdd(acc + 0, s); atomicAdd(acc + 1, a); atomicAdd(acc + 2, c); }
-}
-
-// k' smallest of the c <= kTcCap keys of one list, in place, by one warp; returns the new count and the k'-th
-// key's estimate bits.  Keys are distinct (ids are), empty slots compare as kNoKey.
-__device__ __forceinline__ uint32_t tc_select(unsigned long long* __restrict__ lst, uint32_t c, uint32_t kp, uint32_t lane, uint32_t& tau_bits) {
-    constexpr int KPL = kTcCap / 32;
-    uint32_t hi[KPL], lo[KPL];
-#pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-        const uint32_t idx = (uint32_t)i * 32 + lane;
-        const unsigned long long key = idx < c ? lst[idx] : kNoKey;
-        hi[i] = (uint32_t)(key >> 32); lo[i] = (uint32_t)key;
-    }
-    uint32_t cur = 0;
-    for (int bit = 30; bit >= 0; --bit) {   // estimates are non-negative floats: bit 31 is clear
-        const uint32_t t = cur | (1u << bit);
-        uint32_t nl = 0;
-#pragma unroll
-        for (int i = 0; i < KPL; ++i) nl += hi[i] < t ? 1u : 0u;
-        nl = __reduce_add_sync(kFull, nl);
-        if (nl < kp) cur = t;
-    }
-    uint32_t nlt = 0, neq = 0;
-#pragma unroll
-    for (int i = 0; i < KPL; ++i) { nlt += hi[i] < cur ? 1u : 0u; neq += hi[i] == cur ? 1u : 0u; }
-    nlt = __reduce_add_sync(kFull, nlt); neq = __reduce_add_sync(kFull, neq);
-    const uint32_t r = kp - nlt;   // 1 <= r <= neq of the keys with this estimate stay
-    uint32_t cutlo = 0xFFFFFFFFu;
-    if (neq != r) {
-        uint32_t cl = 0;
-        for (int bit = 31; bit >= 0; --bit) {
-            const uint32_t t = cl | (1u << bit);
-            uint32_t nl = 0;
-#pragma unroll
-            for (int i = 0; i < KPL; ++i) nl += (hi[i] == cur && lo[i] < t) ? 1u : 0u;
-            nl = __reduce_add_sync(kFull, nl);
-            if (nl < r) cl = t;
-        }
-        cutlo = cl;
-    }
-    uint32_t mine = 0;
-#pragma unroll
-    for (int i = 0; i < KPL; ++i) mine += (hi[i] < cur || (hi[i] == cur && lo[i] <= cutlo)) ? 1u : 0u;
-    uint32_t pos = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(kFull, pos, o); if (lane >= (uint32_t)o) pos += t; }
-    pos -= mine;
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < KPL; ++i)
-        if (hi[i] < cur || (hi[i] == cur && lo[i] <= cutlo)) lst[pos++] = ((unsigned long long)hi[i] << 32) | lo[i];
-    __syncwarp();
-    tau_bits = cur;
-    return kp;
 }
 
 struct TcShared {
@@ -225,17 +93,6 @@ struct TcDrain {
     uint32_t* sums; float* est;
     unsigned long long* lists;
 };
-
-__device__ __forceinline__ uint32_t tc_lds(uint32_t saddr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void tc_enqueue(uint32_t qn_saddr, uint32_t q_saddr, uint32_t rec) {
-    uint32_t pos;
-    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(qn_saddr) : "memory");
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(q_saddr + pos * 4u), "r"(rec) : "memory");
-}
 
 // `wbase` = id of row 0 of the first tile of the current checkpoint window
 template <bool DENSE>
@@ -555,37 +412,21 @@ size_t exhaustive_tc_workspace_bytes(uint32_t nq, uint32_t kprime, int num_sms) 
     return (size_t)64 * nq * (size_t)kprime * 8 + (size_t)num_sms * kTcNQ * kTcCap * 8 + (size_t)nq * 4 + 1024;
 }
 
-// Returns through *nseg the number of per-group segments (the "slices" exhaustive_select_rerank_kernel merges).
-cudaError_t launch_exhaustive_scan_tc(const DevIndex& ix, const ExhaustiveArgs& a, int num_sms, unsigned long long* partial,
-                                      uint32_t* nseg, cudaStream_t stream) {
-    // workspace: partial | lists | taug | vstat
-    uint8_t* ws = reinterpret_cast<uint8_t*>(partial) + (size_t)64 * a.nq * (size_t)a.kprime * 8;
-    unsigned long long* lists = reinterpret_cast<unsigned long long*>(ws);
-    ws += (size_t)num_sms * kTcNQ * kTcCap * 8;
-    uint32_t* taug = reinterpret_cast<uint32_t*>(ws);
-    ws += (((size_t)a.nq * 4 + 15) & ~(size_t)15);
-    float* vstat = reinterpret_cast<float*>(ws);
+cudaError_t launch_exhaustive_tc_prepare(const DevIndex& ix, uint64_t id_begin, uint64_t id_end, uint32_t nq, float* vstat, uint32_t* taug,
+                                         bool reset_tau, int num_sms, cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(vstat, 0, 16, stream);
     if (e != cudaSuccess) return e;
-    exhaustive_tc_prepare_kernel<<<num_sms * 2, 256, 0, stream>>>(ix, a.id_begin, a.id_end, a.nq, vstat, taug);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    // work split: (group, tile) units, group-major, an equal contiguous share per CTA; a group may not be cut into
-    // more segments than one CTA can merge (slices x k' keys sorted in shared memory by the second kernel)
-    const uint64_t m = a.id_end - a.id_begin;
-    const uint32_t ngroups = (a.nq + kTcNQ - 1) / kTcNQ;
-    const uint32_t tiles = (uint32_t)((m + kTcM - 1) / kTcM);
-    const uint64_t units = (uint64_t)ngroups * tiles;
-    uint64_t maxseg = a.kprime ? 16384 / (uint64_t)a.kprime : 64;
-    if (maxseg > 64) maxseg = 64;
-    uint64_t W = (units + num_sms - 1) / num_sms;
-    if (maxseg > 1) { const uint64_t wmin = (tiles + maxseg - 2) / (maxseg - 1); if (W < wmin) W = wmin; }
-    else W = tiles;
-    if (W < 1) W = 1;
-    const uint32_t grid = units ? (uint32_t)((units + W - 1) / W) : 1u;
-    *nseg = tiles ? (uint32_t)((tiles + W - 1) / W) + 1u : 1u;
+    exhaustive_tc_prepare_kernel<<<num_sms * 2, 256, 0, stream>>>(ix, id_begin, id_end, nq, vstat, taug, reset_tau ? 1 : 0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_exhaustive_scan_tc_core(const DevIndex& ix, const ExhaustiveArgs& a, int num_sms, unsigned long long* partial,
+                                           const TcWorkspace& w, uint32_t* nseg, cudaStream_t stream) {
+    const TcSplit sp = tc_split(a.id_end - a.id_begin, a.nq, a.kprime, num_sms);
+    *nseg = sp.nseg;
+    cudaError_t e;
     if (a.kprime) {   // (segment, query) slots nobody writes must read as empty
-        e = cudaMemsetAsync(partial, 0xFF, (size_t)*nseg * a.nq * (size_t)a.kprime * 8, stream);
+        e = cudaMemsetAsync(partial, 0xFF, (size_t)sp.nseg * a.nq * (size_t)a.kprime * 8, stream);
         if (e != cudaSuccess) return e;
     }
     const size_t smem = (size_t)kTcStages * 16384 + (size_t)ix.nch * 32768 + sizeof(TcShared) + (size_t)kTcEpiWarps * kTcQueue * 4 + (size_t)kTcVRing * kTcM * 16 + 1024;
@@ -595,8 +436,17 @@ cudaError_t launch_exhaustive_scan_tc(const DevIndex& ix, const ExhaustiveArgs& 
     const size_t smem_req = smem < (size_t)120 * 1024 ? (size_t)120 * 1024 : smem;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req);
     if (e != cudaSuccess) return e;
-    kern<<<grid, kTcThreads, smem_req, stream>>>(ix, a, tiles, W, ngroups, vstat, taug, lists, partial);
+    kern<<<sp.grid, kTcThreads, smem_req, stream>>>(ix, a, sp.tiles, sp.W, sp.ngroups, w.vstat, w.taug, w.lists, partial);
     return cudaGetLastError();
+}
+
+// Returns through *nseg the number of per-group segments (the "slices" exhaustive_select_rerank_kernel merges).
+cudaError_t launch_exhaustive_scan_tc(const DevIndex& ix, const ExhaustiveArgs& a, int num_sms, unsigned long long* partial,
+                                      uint32_t* nseg, cudaStream_t stream) {
+    const TcWorkspace w = tc_workspace(partial, a.nq, a.kprime, num_sms);
+    cudaError_t e = launch_exhaustive_tc_prepare(ix, a.id_begin, a.id_end, a.nq, w.vstat, w.taug, true, num_sms, stream);
+    if (e != cudaSuccess) return e;
+    return launch_exhaustive_scan_tc_core(ix, a, num_sms, partial, w, nseg, stream);
 }
 
 }  // namespace cpb

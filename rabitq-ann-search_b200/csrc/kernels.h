@@ -83,13 +83,18 @@ struct ExhaustiveArgs {
     uint32_t* sums; float* est;       // optional dense outputs [nq][id_end-id_begin]
     int64_t* ids; float* dists;       // [nq][k]
     void* workspace; size_t workspace_bytes;
-    int use_tensor_cores;             // 1: tcgen05 scan where applicable, 0: popcount scan
+    int use_tensor_cores;             // 2: tcgen05 kind::f16 scan with the screen folded in, 1: tcgen05 kind::i8 scan (each where
+                                      // applicable, else the next), 0: popcount scan
 };
 size_t exhaustive_workspace_bytes(const DevIndex& ix, uint32_t nq, uint64_t m, uint32_t kprime, int num_sms);
 cudaError_t launch_exhaustive(const DevIndex& ix, const ExhaustiveArgs& a, int num_sms, cudaStream_t stream);
 // tensor-core form of the scan stage (exhaustive_tc.cu)
 bool exhaustive_tc_applicable(const DevIndex& ix, uint32_t kprime);
 size_t exhaustive_tc_workspace_bytes(uint32_t nq, uint32_t kprime, int num_sms);
+// threshold folded into a kind::f16 contraction (exhaustive_tc16.cu)
+bool exhaustive_tc16_applicable(const DevIndex& ix, uint32_t kprime);
+cudaError_t launch_exhaustive_scan_tc16(const DevIndex& ix, const ExhaustiveArgs& a, int num_sms, unsigned long long* partial,
+                                        uint32_t* nseg, cudaStream_t stream);
 cudaError_t launch_exhaustive_scan_tc(const DevIndex& ix, const ExhaustiveArgs& a, int num_sms, unsigned long long* partial,
                                       uint32_t* nseg, cudaStream_t stream);
 

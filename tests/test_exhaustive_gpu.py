@@ -19,7 +19,7 @@ def _torch():
     return torch
 
 
-@pytest.mark.parametrize("tc", [1, 0])
+@pytest.mark.parametrize("tc", [2, 1, 0])
 @pytest.mark.parametrize("dim,n", [(128, 5000), (96, 3001), (20, 700), (960, 1200), (256, 900)])
 def test_estimates_match_oracle(oracle, dim, n, tc):
     from cphnsw_b200 import hooks
@@ -27,7 +27,9 @@ def test_estimates_match_oracle(oracle, dim, n, tc):
     torch = _torch()
     fab = common.fabricate(n, dim, 1, seed=dim, degenerate=True, a=1.01, b=0.003)
     ix = common.gpu_index_from(fab)
-    ix.set_option("exhaustive_tensor_cores", tc)   # 1: tcgen05 scan where it applies (D <= 256), 0: popcount scan
+    # 2: tcgen05 kind::f16 scan with the screen folded into the contraction (D <= 128), 1: tcgen05 kind::i8 scan
+    # (D <= 256), each where it applies; 0: popcount scan
+    ix.set_option("exhaustive_tensor_cores", tc)
     view = oracle.index_view(fab)
     q = np.random.default_rng(1).standard_normal((11, dim)).astype(np.float32)
     q[3] = fab.centroid     # |q - c|^2 == 0: the dist_qp_sq < 1e-12 branch
@@ -39,7 +41,7 @@ def test_estimates_match_oracle(oracle, dim, n, tc):
         assert np.array_equal(_bits(est[i]), _bits(oest))
 
 
-@pytest.mark.parametrize("tc", [1, 0])
+@pytest.mark.parametrize("tc", [2, 1, 0])
 @pytest.mark.parametrize("dim,n,k,kprime", [(128, 6000, 10, 100), (128, 6000, 1, 1), (96, 3001, 10, 1000), (64, 40000, 100, 400),
                                             (960, 1500, 20, 60), (32, 300, 10, 512), (64, 40000, 100, 256), (256, 9000, 10, 30)])
 def test_search_matches_oracle(oracle, dim, n, k, kprime, tc):
@@ -74,11 +76,12 @@ def test_tensor_core_scan_equals_popcount_scan_on_a_larger_batch(oracle):
     q = np.random.default_rng(5).standard_normal((700, 128)).astype(np.float32)
     q[5] = fab.centroid
     out = {}
-    for tc in (1, 0):
+    for tc in (2, 1, 0):
         ix.set_option("exhaustive_tensor_cores", tc)
         ids, dists = hooks.exhaustive_search(ix, torch.from_numpy(q), 10, 100)
         out[tc] = (ids.cpu().numpy(), dists.cpu().numpy())
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(_bits(out[0][1]), _bits(out[1][1]))
+    assert np.array_equal(out[0][0], out[2][0]) and np.array_equal(_bits(out[0][1]), _bits(out[2][1]))
     for i in (0, 5, 255, 256, 511, 699):
         oi, od, _, _ = oracle.exhaustive(view, fab, q[i], 10, 100)
         assert np.array_equal(out[1][0][i, :len(oi)], oi.astype(np.int64)), i
