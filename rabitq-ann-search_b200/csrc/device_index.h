@@ -101,7 +101,8 @@ struct cphnsw_b200_index {
     int64_t ctas_per_sm = 4;
     int64_t beam_capacity = 0;        // frontier entries per in-flight query (first attempt); 0 = sized from free HBM
     int64_t collect_stats = 0;        // per-batch counters (costs registers: off on the fast path)
-    int64_t exhaustive_tensor_cores = 1;  // K5 scan on tcgen05 where applicable (0: popcount form)
+    int64_t exhaustive_tensor_cores = 2;  // K5 scan: 2 = tcgen05 kind::f16 with the screen folded in, 1 = tcgen05 kind::i8 (each where
+                                          // applicable, else the next), 0 = popcount form
     // scratch, grown on demand
     void* scratch = nullptr;
     size_t scratch_bytes = 0;

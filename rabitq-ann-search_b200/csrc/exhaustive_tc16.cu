@@ -35,7 +35,7 @@ constexpr uint32_t k16SBO = k16KCores * 128;      // bytes between 8-row groups
 constexpr uint32_t k16StageA = 16 * k16SBO;       // 128 rows: 36 864 B
 constexpr uint32_t k16BytesB = 32 * k16SBO;       // 256 rows: 73 728 B
 constexpr int k16Stages = 2;
-constexpr int k16Queue = 768;                     // passer queue entries per epilogue warp: 16 columns x 32 lanes + half
+constexpr int k16Queue = 1280;                    // passer queue entries (2 B) per epilogue warp: 32 columns x 32 lanes + a quarter
 constexpr float k16Big = 60000.0f;                // representable in f16, above every |thr| the screen admits
 
 __device__ __forceinline__ uint64_t t16_desc(uint32_t saddr) {
@@ -111,15 +111,15 @@ struct T16Shared {
     uint32_t tmem_base;
 };
 
-// queue record: column : 8 | (row | tile-in-window << 7) << 8
+// queue record (16 bits): column : 8 | row : 7 | tile-in-window : 1
 template <bool DENSE>
-__device__ __noinline__ void t16_drain(T16Shared& sh, const uint32_t* __restrict__ wq, uint32_t* qn, uint32_t lane, uint32_t wbase) {
+__device__ __noinline__ void t16_drain(T16Shared& sh, const unsigned short* __restrict__ wq, uint32_t* qn, uint32_t lane, uint32_t wbase) {
     const T16Drain& d = sh.drain;
     __syncwarp();
     const uint32_t n = *qn;
     for (uint32_t i = lane; i < n; i += 32) {
         const uint32_t e = wq[i];
-        const uint32_t col = e & 0xFFu, id = wbase + (e >> 8);
+        const uint32_t col = e & 0xFFu, id = wbase + (e >> 8);   // (row | tile << 7) = offset in the window
         // fs = sum_i bit_i u_i, popcount form (D <= 128: one chunk)
         const uint4 w = __ldg(reinterpret_cast<const uint4*>(d.codes) + id);
         const uint4* u = reinterpret_cast<const uint4*>(d.uplanes + (size_t)(d.q0 + col) * 16);
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc16_kernel(con
     uint8_t* As = smem_raw;                                           // k16Stages x 36 KB
     uint8_t* Bs = smem_raw + (size_t)k16Stages * k16StageA;           // 72 KB
     T16Shared& sh = *reinterpret_cast<T16Shared*>(Bs + k16BytesB);
-    uint32_t* queues = reinterpret_cast<uint32_t*>(Bs + k16BytesB + ((sizeof(T16Shared) + 15) & ~(size_t)15));   // [kTcEpiWarps][k16Queue]
+    unsigned short* queues = reinterpret_cast<unsigned short*>(Bs + k16BytesB + ((sizeof(T16Shared) + 15) & ~(size_t)15));   // [kTcEpiWarps][k16Queue]
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t kp = a.kprime;
@@ -332,13 +332,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc16_kernel(con
             const uint32_t row = quarter * 32 + lane;
             const uint32_t colbase = cg * 64;
             const uint32_t own0 = colbase + quarter * 16;
-            uint32_t* myq = queues + (size_t)e * k16Queue;
+            unsigned short* myq = queues + (size_t)e * k16Queue;
             uint32_t* myqn = &sh.qn[e];
             const uint32_t myq_s = tc_smem_u32(myq), myqn_s = tc_smem_u32(myqn);
             for (uint32_t t = 0; t < ntiles; ++t, ++tcount) {
                 const bool live = vb + (uint64_t)t * kTcM + row < ve;
-                const uint32_t rowtag = (row | ((t % G) << 7)) << 8;
-                const uint32_t wbase = (uint32_t)(vb + (uint64_t)(t - t % G) * kTcM);
+                const uint32_t tw = t & (G - 1u);                                  // G is 1 or 2
+                const uint32_t rowtag = (row | (tw << 7)) << 8;
+                const uint32_t wbase = (uint32_t)(vb + (uint64_t)(t - tw) * kTcM);
                 const uint32_t buf = tcount & 1u;
                 tc_wait_relaxed<1000>(&sh.acc_full[buf], (tcount >> 1) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -362,22 +363,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc16_kernel(con
                         if (lane == 0) tc_arrive(&sh.acc_empty[buf]);
                     }
                     // one compare per pair: acc = fs - thr + margin >= 0 (the sign bit of a float is the sign of the int)
+                    if (tc_lds(myqn_s) > (uint32_t)(k16Queue - 1024)) t16_drain<DENSE>(sh, myq, myqn, lane, wbase);   // room for this half
 #pragma unroll
                     for (int c16 = 0; c16 < 2; ++c16) {
-                        if (tc_lds(myqn_s) > (uint32_t)(k16Queue - 512)) t16_drain<DENSE>(sh, myq, myqn, lane, wbase);
                         uint32_t any = 0x80000000u;
 #pragma unroll
                         for (int jj = 0; jj < 16; ++jj) any &= r[c16 * 16 + jj];      // sign bit survives iff every acc is negative
                         if (live && !(any & 0x80000000u)) {
 #pragma unroll
                             for (int jj = 0; jj < 16; ++jj)
-                                if (!(r[c16 * 16 + jj] & 0x80000000u))
-                                    tc_enqueue(myqn_s, myq_s, (col0 + (uint32_t)(c16 * 16 + jj)) | rowtag);
+                                if (!(r[c16 * 16 + jj] & 0x80000000u)) {
+                                    uint32_t pos;
+                                    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(myqn_s) : "memory");
+                                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(myq_s + pos * 2u), "h"((unsigned short)((col0 + (uint32_t)(c16 * 16 + jj)) | rowtag)) : "memory");
+                                }
                         }
                     }
                 }
 
-                const bool checkpoint = t % G == G - 1 || t + 1 == ntiles;
+                const bool checkpoint = tw == G - 1u || t + 1 == ntiles;
                 if (checkpoint || DENSE) t16_drain<DENSE>(sh, myq, myqn, lane, wbase);
                 if (kp && checkpoint) {
                     tc_group_sync(1 + cg);
@@ -397,7 +401,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc16_kernel(con
                         }
                     }
                     __syncwarp();
-                    const bool refresh = (t / G) % 3u == 2u;
+                    const bool refresh = ((t >> (G - 1u)) & 3u) == 3u;
                     if (lane < 16 && mycol < nqt && (refresh || ((need >> lane) & 1u))) {
                         float tau = sh.tau[mycol];
                         if (refresh) { const float tg = __uint_as_float(taug[q0 + mycol]); if (tg < tau) tau = tg; }
@@ -499,7 +503,7 @@ cudaError_t launch_exhaustive_scan_tc16(const DevIndex& ix, const ExhaustiveArgs
         e = cudaMemsetAsync(partial, 0xFF, (size_t)sp.nseg * a.nq * (size_t)a.kprime * 8, stream);
         if (e != cudaSuccess) return e;
     }
-    const size_t smem = (size_t)k16Stages * k16StageA + k16BytesB + sizeof(T16Shared) + (size_t)kTcEpiWarps * k16Queue * 4 + 1024;
+    const size_t smem = (size_t)k16Stages * k16StageA + k16BytesB + sizeof(T16Shared) + (size_t)kTcEpiWarps * k16Queue * 2 + 1024;
     const bool dense = a.sums || a.est;
     auto kern = dense ? exhaustive_scan_tc16_kernel<true> : exhaustive_scan_tc16_kernel<false>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
