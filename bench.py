@@ -309,6 +309,7 @@ def run_c4(args, rank, world, local):
     del tiny
     ix = _c4_upload(cph, hooks, dim, D, local, sd, raw, norm_sq, cen_np)
     del sd, raw
+    ix.set_option("exhaustive_tensor_cores", args.scan_form)
     info = ix.info()
     log(f"[bench] rank {rank}: shard [{b}, {e}) encoded and on cuda:{local} in {time.time() - t0:.1f} s, {info['device_bytes'] / 2**30:.1f} GiB")
 
@@ -374,19 +375,24 @@ def run_c4(args, rank, world, local):
         pass
     bf16 = float(peaks.get("bf16_tflops", peaks.get("bf16_tfs", 1650.0)))
     achieved = pairs * 2 * D / (scan_ms / 1e3) / 1e12
+    form = {2: ("exhaustive_scan_tc16_kernel (tcgen05.mma kind::f16, M=128 N=256 K=16 x 9: 128 code dimensions + 16 threshold columns, "
+                "f32 accumulators in TMEM)", "f16 x f16 -> f32 (tcgen05 kind::f16)", bf16, "MEASURED_PEAKS bf16 (f16 runs at the same rate)", "TFLOP/s"),
+            1: ("exhaustive_scan_tc_kernel (tcgen05.mma kind::i8, M=128 N=256 K=32)", "u8 x u8 -> s32 (tcgen05 kind::i8) + f32", 2.0 * bf16,
+                "2 x MEASURED_PEAKS bf16 (int8 dense rate is twice bf16)", "TOP/s"),
+            0: ("exhaustive_scan_kernel (popcount form)", "u32 popcount sums + f32", 2.0 * bf16, "2 x MEASURED_PEAKS bf16 (int8 dense rate)", "TOP/s")}[args.scan_form]
     line = {"metric": "QPS (exhaustive batched scan, queries/s over the whole database)", "value": value, "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u8 x u8 -> s32 (tcgen05 kind::i8) + f32", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": form[1], "data": "synthetic",
             "config": {"workload": f"c4: {n}x{dim} synthetic iid N(0,1), 1-bit RaBitQ codes, exhaustive scan, {nq} queries, k={k}, k'={kp}",
                        "parallelism": f"database sharded x{world}, per-shard top-k, NCCL all-gather, device merge",
                        "l2": "the scan streams codes + 256-query operands; candidate lists live in L2 by design"},
             "e2e": {"value": nq * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * k * 12},
-            "gpu_launches": 5 * args.steps,
-            "roofline": {"bound": "tensor", "kernel": "exhaustive_scan_tc_kernel (tcgen05.mma kind::i8, M=128 N=256 K=32)", "achieved": achieved,
-                         "peak": 2.0 * bf16, "peak_source": "2 x MEASURED_PEAKS bf16 (int8 dense rate is twice bf16)", "unit": "TOP/s",
-                         "frac": achieved / (2.0 * bf16), "traffic": None, "pairs_per_s_per_gpu": pairs / (scan_ms / 1e3),
-                         "note": "whole step timed (prep + scan + select/rerank + merge); the scan kernel is > 90% of it; it is bound by "
-                                 "the issue slots of its per-pair candidate screen, not by the tensor pipe (DESIGN.md)"},
+            "gpu_launches": (9 if args.scan_form == 2 else 5) * args.steps,
+            "roofline": {"bound": "tensor", "kernel": form[0], "achieved": achieved, "peak": form[2], "peak_source": form[3], "unit": form[4],
+                         "frac": achieved / form[2], "traffic": None, "pairs_per_s_per_gpu": pairs / (scan_ms / 1e3),
+                         "algorithmic_ops_per_pair": 2 * D,
+                         "note": "whole step timed (prep + threshold prefix pass + scan + select/rerank + merge); the scan kernel is > 90% of it "
+                                 "(DESIGN.md section 4, K5)"},
             "clocks": clocks.summary(), "step_ms": [round(x, 3) for x in step_ms]}
     if rank == 0:
         # recall@10 of the 1-bit estimate + exact rerank against brute force, on a sample of the queries (shard 0's view
@@ -419,6 +425,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
                     help="c2: BASELINE configs[1], graph search (the default and the headline); c4: configs[3], exhaustive scan")
     ap.add_argument("--kprime", type=int, default=100, help="c4: rerank depth")
+    ap.add_argument("--scan-form", type=int, default=2, choices=[0, 1, 2],
+                    help="c4: 2 = tcgen05 kind::f16 scan with the candidate screen folded into the contraction (default), "
+                         "1 = tcgen05 kind::i8 scan + float screen, 0 = popcount scan; results are identical")
     ap.add_argument("--nvec", "--n", dest="n", type=int, default=None)
     ap.add_argument("--dim", type=int, default=128)
     ap.add_argument("--bits", type=int, default=4)
