@@ -111,7 +111,7 @@ __device__ __noinline__ void tc_drain(const TcDrain d, TcShared& sh, const uint3
         }
         if (d.kp && est <= sh.tau[col]) {
             const uint32_t pos = atomicAdd(&sh.cnt[col], 1u);   // < capacity: lists are trimmed G tiles ahead
-            d.lists[(size_t)col * kTcCap + pos] = make_key(est, id);
+            d.lists[(size_t)col * kTcListStride + pos] = make_key(est, id);
         }
     }
     __syncwarp();
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc_kernel(const
     const Calib& cal = ix.calib;
     const uint64_t m = a.id_end - a.id_begin;
     const float dmax = (float)(nch * 128u);
-    unsigned long long* mylists = lists + (size_t)blockIdx.x * kTcNQ * kTcCap;
+    unsigned long long* mylists = lists + (size_t)blockIdx.x * kTcNQ * kTcListStride;
     // tiles between list checks: a list is trimmed when it could overflow before the next check, i.e. at
     // cnt > cap - 128 G; G = 2 leaves room for ~150 new candidates between two trims of a k' = 100 list
     const uint32_t G = kp ? min(2u, (kTcCap - kp) / kTcM) : 1u;
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc_kernel(const
                         todo &= todo - 1;
                         const uint32_t col = own0 + jl;
                         uint32_t tb;
-                        const uint32_t nc = tc_select(mylists + (size_t)col * kTcCap, sh.cnt[col], kp, lane, tb);
+                        const uint32_t nc = tc_select(mylists + (size_t)col * kTcListStride, sh.cnt[col], kp, lane, tb);
                         if (lane == 0) {
                             const uint32_t old = atomicMin(taug + q0 + col, tb);
                             sh.cnt[col] = nc;
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc_kernel(const
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (kp) {
             for (uint32_t col = warp; col < nqt; col += blockDim.x >> 5) {
-                unsigned long long* lst = mylists + (size_t)col * kTcCap;
+                unsigned long long* lst = mylists + (size_t)col * kTcListStride;
                 uint32_t c = sh.cnt[col];
                 if (c > kp) {
                     uint32_t tb;
@@ -409,7 +409,7 @@ bool exhaustive_tc_applicable(const DevIndex& ix, uint32_t kprime) {
 }
 
 size_t exhaustive_tc_workspace_bytes(uint32_t nq, uint32_t kprime, int num_sms) {
-    return (size_t)64 * nq * (size_t)kprime * 8 + (size_t)num_sms * kTcNQ * kTcCap * 8 + (size_t)nq * 4 + 1024;
+    return (size_t)64 * nq * (size_t)kprime * 8 + (size_t)num_sms * kTcNQ * kTcListStride * 8 + (size_t)nq * 4 + 1024;
 }
 
 cudaError_t launch_exhaustive_tc_prepare(const DevIndex& ix, uint64_t id_begin, uint64_t id_end, uint32_t nq, float* vstat, uint32_t* taug,

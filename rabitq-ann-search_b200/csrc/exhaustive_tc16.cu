@@ -111,15 +111,16 @@ struct T16Shared {
     uint32_t tmem_base;
 };
 
-// queue record (16 bits): column : 8 | row : 7 | tile-in-window : 1
+// queue record (16 bits): column : 8 | lane : 5 | tile-in-window : 3   (the rows of a warp are those of its lane quarter)
 template <bool DENSE>
 __device__ __noinline__ void t16_drain(T16Shared& sh, const unsigned short* __restrict__ wq, uint32_t* qn, uint32_t lane, uint32_t wbase) {
+    // wbase = id of this warp's lane 0 in the first tile of the window
     const T16Drain& d = sh.drain;
     __syncwarp();
     const uint32_t n = *qn;
     for (uint32_t i = lane; i < n; i += 32) {
         const uint32_t e = wq[i];
-        const uint32_t col = e & 0xFFu, id = wbase + (e >> 8);   // (row | tile << 7) = offset in the window
+        const uint32_t col = e & 0xFFu, id = wbase + ((e >> 8) & 31u) + (e >> 13) * kTcM;
         // fs = sum_i bit_i u_i, popcount form (D <= 128: one chunk)
         const uint4 w = __ldg(reinterpret_cast<const uint4*>(d.codes) + id);
         const uint4* u = reinterpret_cast<const uint4*>(d.uplanes + (size_t)(d.q0 + col) * 16);
@@ -133,7 +134,7 @@ __device__ __noinline__ void t16_drain(T16Shared& sh, const unsigned short* __re
         }
         if (d.kp && est <= sh.tau[col]) {
             const uint32_t pos = atomicAdd(&sh.cnt[col], 1u);   // < capacity: lists are trimmed G tiles ahead
-            d.lists[(size_t)col * kTcCap + pos] = make_key(est, id);
+            d.lists[(size_t)col * kTcListStride + pos] = make_key(est, id);
         }
     }
     __syncwarp();
@@ -158,8 +159,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc16_kernel(con
     const Calib& cal = ix.calib;
     const uint64_t m = a.id_end - a.id_begin;
     const float dmax = 128.0f;
-    unsigned long long* mylists = lists + (size_t)blockIdx.x * kTcNQ * kTcCap;
-    const uint32_t G = kp ? min(2u, (kTcCap - kp) / kTcM) : 1u;
+    unsigned long long* mylists = lists + (size_t)blockIdx.x * kTcNQ * kTcListStride;
+    // lists of cap = 1024 - k' keys (two register-resident selections trim them); a checkpoint -- drain, trim, tau -- every G
+    // tiles, G = the tiles a just-trimmed list of k' keys can take at 128 appends per tile (at most 7: 3 bits in the queue record)
+    const uint32_t cap = 2u * kTcCap - kp;
+    const uint32_t G = kp ? min(7u, (cap - kp) / kTcM) : 1u;
 
     TcLimits lim;
     T16Scale sc;
@@ -335,11 +339,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc16_kernel(con
             unsigned short* myq = queues + (size_t)e * k16Queue;
             uint32_t* myqn = &sh.qn[e];
             const uint32_t myq_s = tc_smem_u32(myq), myqn_s = tc_smem_u32(myqn);
+            uint32_t tw = 0, nckpt = 0;   // tile within the checkpoint window, checkpoints so far
             for (uint32_t t = 0; t < ntiles; ++t, ++tcount) {
                 const bool live = vb + (uint64_t)t * kTcM + row < ve;
-                const uint32_t tw = t & (G - 1u);                                  // G is 1 or 2
-                const uint32_t rowtag = (row | (tw << 7)) << 8;
-                const uint32_t wbase = (uint32_t)(vb + (uint64_t)(t - tw) * kTcM);
+                const uint32_t rowtag = (lane | (tw << 5)) << 8;
+                const uint32_t wbase = (uint32_t)(vb + (uint64_t)(t - tw) * kTcM) + quarter * 32u;
                 const uint32_t buf = tcount & 1u;
                 tc_wait_relaxed<1000>(&sh.acc_full[buf], (tcount >> 1) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -383,17 +387,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc16_kernel(con
 
                 const bool checkpoint = tw == G - 1u || t + 1 == ntiles;
                 if (checkpoint || DENSE) t16_drain<DENSE>(sh, myq, myqn, lane, wbase);
+                tw = checkpoint ? 0u : tw + 1u;
                 if (kp && checkpoint) {
                     tc_group_sync(1 + cg);
                     const uint32_t mycol = own0 + (lane & 15u);
-                    const uint32_t need = __ballot_sync(kFull, lane < 16 && sh.cnt[mycol] + G * kTcM > (uint32_t)kTcCap);
+                    const uint32_t need = __ballot_sync(kFull, lane < 16 && sh.cnt[mycol] + G * kTcM > cap);
                     uint32_t todo = need;
                     while (todo) {
                         const uint32_t jl = __ffs(todo) - 1;
                         todo &= todo - 1;
                         const uint32_t col = own0 + jl;
                         uint32_t tb;
-                        const uint32_t nc = tc_select(mylists + (size_t)col * kTcCap, sh.cnt[col], kp, lane, tb);
+                        const uint32_t nc = tc_select_long(mylists + (size_t)col * kTcListStride, sh.cnt[col], kp, lane, tb);
                         if (lane == 0) {
                             const uint32_t old = atomicMin(taug + q0 + col, tb);
                             sh.cnt[col] = nc;
@@ -401,7 +406,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc16_kernel(con
                         }
                     }
                     __syncwarp();
-                    const bool refresh = ((t >> (G - 1u)) & 3u) == 3u;
+                    const bool refresh = (++nckpt & 1u) == 0u;
                     if (lane < 16 && mycol < nqt && (refresh || ((need >> lane) & 1u))) {
                         float tau = sh.tau[mycol];
                         if (refresh) { const float tg = __uint_as_float(taug[q0 + mycol]); if (tg < tau) tau = tg; }
@@ -434,11 +439,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc16_kernel(con
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (kp) {
             for (uint32_t col = warp; col < nqt; col += blockDim.x >> 5) {
-                unsigned long long* lst = mylists + (size_t)col * kTcCap;
+                unsigned long long* lst = mylists + (size_t)col * kTcListStride;
                 uint32_t c = sh.cnt[col];
                 if (c > kp) {
                     uint32_t tb;
-                    c = tc_select(lst, c, kp, lane, tb);
+                    c = tc_select_long(lst, c, kp, lane, tb);
                     if (lane == 0) atomicMin(taug + q0 + col, tb);
                 }
                 unsigned long long* out = partial + ((size_t)slice * a.nq + (q0 + col)) * kp;

@@ -9,7 +9,8 @@ constexpr int kTcNQ = 256;           // queries per work item = MMA N
 constexpr int kTcM = 128;            // vertices per tile = MMA M
 constexpr int kTcStages = 3;         // A-operand ring
 constexpr int kTcVRing = 8;          // per-tile vertex screen parameters: ring deeper than expander lead + accumulators in flight
-constexpr int kTcCap = 512;          // candidate slots per (CTA, query)
+constexpr int kTcCap = 512;          // candidate slots per (CTA, query): what one register-resident selection handles
+constexpr int kTcListStride = 1024;  // keys reserved per list in the workspace (the f16 form fills up to 1024 - k')
 constexpr uint32_t kTcMaxKPrime = 256;   // k' + one tile of appends must fit the list
 constexpr int kTcExpWarps = 4, kTcEpiWarps = 16;
 constexpr int kTcThreads = (kTcExpWarps + kTcEpiWarps + 1) * 32;   // + the issuer warp
@@ -137,6 +138,16 @@ __device__ __forceinline__ uint32_t tc_select(unsigned long long* __restrict__ l
     return kp;
 }
 
+// the same for lists of up to 2 kTcCap - k' keys: the k' best of the first kTcCap, the rest moved up behind them, again
+__device__ __forceinline__ uint32_t tc_select_long(unsigned long long* __restrict__ lst, uint32_t c, uint32_t kp, uint32_t lane, uint32_t& tau_bits) {
+    if (c <= (uint32_t)kTcCap) return tc_select(lst, c, kp, lane, tau_bits);
+    tc_select(lst, kTcCap, kp, lane, tau_bits);
+    const uint32_t rest = c - kTcCap;                     // <= kTcCap - k': source [kTcCap, c) and destination [k', k' + rest) do not overlap
+    for (uint32_t i = lane; i < rest; i += 32) lst[kp + i] = lst[kTcCap + i];
+    __syncwarp();
+    return tc_select(lst, kp + rest, kp, lane, tau_bits);
+}
+
 __device__ __forceinline__ uint32_t tc_lds(uint32_t saddr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
@@ -154,7 +165,7 @@ inline TcWorkspace tc_workspace(unsigned long long* partial, uint32_t nq, uint32
     uint8_t* ws = reinterpret_cast<uint8_t*>(partial) + (size_t)64 * nq * (size_t)kprime * 8;
     TcWorkspace w;
     w.lists = reinterpret_cast<unsigned long long*>(ws);
-    ws += (size_t)num_sms * kTcNQ * kTcCap * 8;
+    ws += (size_t)num_sms * kTcNQ * kTcListStride * 8;
     w.taug = reinterpret_cast<uint32_t*>(ws);
     ws += (((size_t)nq * 4 + 15) & ~(size_t)15);
     w.vstat = reinterpret_cast<float*>(ws);
