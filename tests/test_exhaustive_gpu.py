@@ -88,6 +88,35 @@ def test_tensor_core_scan_equals_popcount_scan_on_a_larger_batch(oracle):
         assert np.array_equal(_bits(out[1][1][i, :len(oi)]), _bits(od))
 
 
+@pytest.mark.parametrize("tc", [2, 1])
+@pytest.mark.parametrize("scale", [1e-3, 30.0, 3e3])
+def test_screen_survives_data_scale(oracle, tc, scale):
+    """The tensor-core forms reject pairs with a screen whose margin is derived from magnitudes (and, in the f16
+    form, from power-of-two rescaling of f16 factors): the answer must not depend on the scale of the data.
+    Vectors, per-vertex norms and queries scaled together; clustered queries so thresholds get tight."""
+    from cphnsw_b200 import hooks
+
+    torch = _torch()
+    fab = common.fabricate(30000, 128, 1, seed=11)
+    storage = 64
+    nop = fab.search_data[:, storage:storage + 4].copy().view(np.float32) * np.float32(scale)
+    fab.search_data[:, storage:storage + 4] = nop.view(np.uint8)
+    fab.raw *= np.float32(scale)
+    fab.norm_sq = (fab.norm_sq * np.float32(scale) * np.float32(scale)).astype(np.float32)
+    fab.centroid = (fab.centroid * np.float32(scale)).astype(np.float32)
+    ix = common.gpu_index_from(fab)
+    ix.set_option("exhaustive_tensor_cores", tc)
+    view = oracle.index_view(fab)
+    rng = np.random.default_rng(8)
+    q = (fab.raw[rng.integers(0, fab.n, 40), :128] + rng.standard_normal((40, 128)).astype(np.float32) * np.float32(0.3 * scale)).astype(np.float32)
+    ids, dists = hooks.exhaustive_search(ix, torch.from_numpy(q), 10, 64)
+    ids, dists = ids.cpu().numpy(), dists.cpu().numpy()
+    for i in range(0, 40, 3):
+        oi, od, _, _ = oracle.exhaustive(view, fab, q[i], 10, 64)
+        assert np.array_equal(ids[i, :len(oi)], oi.astype(np.int64)), (i, scale)
+        assert np.array_equal(_bits(dists[i, :len(oi)]), _bits(od))
+
+
 def test_database_shards_merge_to_the_unsharded_answer(oracle):
     """DB-sharded mode on one device: each shard scans its id range, the k-way merge of the shards' top-k
     (by (distance, id)) equals what the oracle gives shard by shard merged the same way."""
