@@ -39,7 +39,9 @@ __device__ __forceinline__ void fs_wait(uint64_t* bar, uint32_t phase) {
     } while (!done);
 }
 
-template <int B>
+// LEAN = the streaming case (a contiguous range of blocks, one query, slack level 0, only est and lower written): no
+// per-block look-ups of which query / which vertex / which outputs.
+template <int B, bool LEAN>
 __global__ void __launch_bounds__(kFsMaxWarps * 32) fastscan_blocks_kernel(const DevIndex ix, const FastScanArgs a,
                                                                             uint32_t ns, uint32_t stage_bytes) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(kFsMaxWarps * 32) fastscan_blocks_kernel(const
     const uint64_t stride = (uint64_t)gridDim.x * nwarps;
     const uint64_t first = (uint64_t)blockIdx.x * nwarps + warp;
     auto block_ptr = [&](uint64_t i) -> const uint8_t* {
-        const uint64_t v = a.vertex_ids ? (uint64_t)__ldg(a.vertex_ids + i) : a.first_vertex + i;
+        const uint64_t v = (!LEAN && a.vertex_ids) ? (uint64_t)__ldg(a.vertex_ids + i) : a.first_vertex + i;
         return ix.blocks + v * ix.block_stride;
     };
     // prologue: fill the ring
@@ -78,10 +80,12 @@ __global__ void __launch_bounds__(kFsMaxWarps * 32) fastscan_blocks_kernel(const
             if (i < a.nblocks) fs_issue(stages + (size_t)s * stage_bytes, block_ptr(i), copy_bytes, mbar + s);
         }
 
-    uint32_t j = 0;
-    for (uint64_t i = first; i < a.nblocks; i += stride, ++j) {
-        const uint32_t s = j % ns, phase = (j / ns) & 1u;
-        const uint32_t q = a.query_of_block ? __ldg(a.query_of_block + i) : 0u;
+    // slack level of blocks without an explicit one: looked up once, not per block (a dynamic index into the
+    // parameter bank is a long-latency load)
+    const float slack0 = cal.num_slack > 0 ? cal.slack[0] : 0.0f;
+    uint32_t s = 0, phase = 0;   // ring position (no division by the runtime stage count in the loop)
+    for (uint64_t i = first; i < a.nblocks; i += stride) {
+        const uint32_t q = (!LEAN && a.query_of_block) ? __ldg(a.query_of_block + i) : 0u;
         if (q != staged_q) {
             __syncwarp();
             const uint4* us = reinterpret_cast<const uint4*>(a.uplanes + (size_t)q * 16 * nch);
@@ -92,9 +96,12 @@ __global__ void __launch_bounds__(kFsMaxWarps * 32) fastscan_blocks_kernel(const
             __syncwarp();
         }
         const float dqp = __ldg(a.dqp + i);
-        int li = a.slack_level ? __ldg(a.slack_level + i) : 0;
-        if (cal.num_slack > 0) { li = li < cal.num_slack - 1 ? li : cal.num_slack - 1; qp.slack = cal.slack[li < 0 ? 0 : li]; }
-        else qp.slack = 0.0f;
+        qp.slack = slack0;
+        if (!LEAN && a.slack_level && cal.num_slack > 0) {
+            int li = __ldg(a.slack_level + i);
+            li = li < cal.num_slack - 1 ? li : cal.num_slack - 1;
+            qp.slack = cal.slack[li < 0 ? 0 : li];
+        }
 
         fs_wait(mbar + s, phase);
         const uint8_t* blk = stages + (size_t)s * stage_bytes;
@@ -119,17 +126,21 @@ __global__ void __launch_bounds__(kFsMaxWarps * 32) fastscan_blocks_kernel(const
             convert_1bit(qp, nbit, nop, ipqo, ipcp, pops & 0xFFFFu, lane, count, dqp, sq, est, lower);
             msb_lower = lower;
         } else {
-            msb_lower = a.msb_lower ? convert_msb<B>(qp, msb2, nop, ipqo, ipcp, pops & 0xFFFFu, dqp, sq) : 0.0f;   // only when asked for
+            msb_lower = (!LEAN && a.msb_lower) ? convert_msb<B>(qp, msb2, nop, ipqo, ipcp, pops & 0xFFFFu, dqp, sq) : 0.0f;   // only when asked for
             convert_nbit<B>(qp, nbit, msb, nop, ipqo, ipcp, pops & 0xFFFFu, pops >> 16, lane, count, dqp, sq, est, lower);
         }
         if (lane >= count) { est = FLT_MAX; lower = FLT_MAX; msb_lower = FLT_MAX; }
         const size_t o = (size_t)i * 32 + lane;
-        if (a.nbit) a.nbit[o] = nbit;
-        if (a.msb) a.msb[o] = msb;
-        if (a.msb2) a.msb2[o] = msb2;
-        if (a.est) a.est[o] = est;
-        if (a.lower) a.lower[o] = lower;
-        if (a.msb_lower) a.msb_lower[o] = msb_lower;
+        if (LEAN) { a.est[o] = est; a.lower[o] = lower; }
+        else {
+            if (a.nbit) a.nbit[o] = nbit;
+            if (a.msb) a.msb[o] = msb;
+            if (a.msb2) a.msb2[o] = msb2;
+            if (a.est) a.est[o] = est;
+            if (a.lower) a.lower[o] = lower;
+            if (a.msb_lower) a.msb_lower[o] = msb_lower;
+        }
+        if (++s == ns) { s = 0; phase ^= 1u; }
     }
 }
 
@@ -146,8 +157,10 @@ cudaError_t launch_fastscan_blocks(const DevIndex& ix, const FastScanArgs& a, in
     int ctas_per_sm = (int)((220u * 1024u) / (per_warp * warps));
     ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 8 ? 8 : ctas_per_sm);
     const size_t smem = per_warp * warps;
+    const bool lean = !a.vertex_ids && !a.query_of_block && !a.slack_level && a.est && a.lower && !a.nbit && !a.msb && !a.msb2 && !a.msb_lower;
     void (*kern)(const DevIndex, const FastScanArgs, uint32_t, uint32_t) =
-        ix.B == 1 ? fastscan_blocks_kernel<1> : ix.B == 2 ? fastscan_blocks_kernel<2> : fastscan_blocks_kernel<4>;
+        lean ? (ix.B == 1 ? fastscan_blocks_kernel<1, true> : ix.B == 2 ? fastscan_blocks_kernel<2, true> : fastscan_blocks_kernel<4, true>)
+             : (ix.B == 1 ? fastscan_blocks_kernel<1, false> : ix.B == 2 ? fastscan_blocks_kernel<2, false> : fastscan_blocks_kernel<4, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const uint64_t want = (a.nblocks + warps - 1) / warps;

@@ -455,3 +455,21 @@ def test_original_ids_and_recall_through_the_drop_in_api():
     assert np.mean([len(set(r.tolist())) for r in pi]) < 10
     raw = np.mean([len(set(ix._id_map[a[a >= 0]].tolist()) & set(b.tolist())) / 10 for a, b in zip(pi, gt)])
     assert recall > raw + 0.1, (recall, raw)
+
+
+@pytest.mark.parametrize("dim,bits", [(128, 4), (128, 1), (64, 2), (960, 2)])
+def test_fastscan_streaming_specialisation_equals_the_general_kernel(dim, bits):
+    """K2 has a lean instantiation for the streaming case (contiguous blocks, one query, slack level 0, est + lower
+    only); it must write exactly what the general kernel writes."""
+    from cphnsw_b200 import hooks
+
+    torch = _torch()
+    fab = common.fabricate(700, dim, bits, seed=dim + bits, counts=(32, 32, 31, 16, 3, 0), degenerate=True, a=1.02, b=0.01)
+    ix = common.gpu_index_from(fab)
+    q = torch.from_numpy(np.random.default_rng(4).standard_normal((1, dim)).astype(np.float32)).cuda()
+    prep = hooks.prepare_queries(ix, q)
+    dqp = torch.from_numpy(np.random.default_rng(5).uniform(0.0, 300.0, fab.n).astype(np.float32))
+    lean = hooks.fastscan_blocks(ix, prep["uplanes"], prep["coeffs"], dqp, first_vertex=0, nblocks=fab.n, want=("est", "lower"))
+    full = hooks.fastscan_blocks(ix, prep["uplanes"], prep["coeffs"], dqp, first_vertex=0, nblocks=fab.n)
+    for name in ("est", "lower"):
+        assert np.array_equal(_bits(lean[name].cpu().numpy()), _bits(full[name].cpu().numpy())), name
