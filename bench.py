@@ -137,7 +137,7 @@ class ClockSampler:
     """SM clock and throttle reasons DURING the timed region, sampled in-process through NVML (spawning
     nvidia-smi in a loop stalls the GPU for tens of ms per query and would distort the measurement)."""
 
-    def __init__(self, gpu, period=0.05):
+    def __init__(self, gpu, period=0.02):
         self.gpu, self.period, self.rows, self.stop = gpu, period, [], False
         self.t = None
 
@@ -162,7 +162,7 @@ class ClockSampler:
         while not self.stop:
             try:
                 self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h),
-                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0, time.time()))
             except Exception:  # noqa: BLE001
                 pass
             time.sleep(self.period)
@@ -171,6 +171,12 @@ class ClockSampler:
         self.stop = True
         if self.t:
             self.t.join(timeout=2)
+
+    def window(self, t0, t1):
+        """Keep only the samples taken inside [t0, t1] (the timed region)."""
+        inside = [r for r in self.rows if t0 <= r[3] <= t1]
+        if inside:
+            self.rows = inside
 
     def summary(self):
         if not self.rows:
@@ -340,17 +346,18 @@ def run_c4(args, rank, world, local):
         dist.all_reduce(t_, op=dist.ReduceOp.MAX)
         return float(t_.item())
 
-    for _ in range(args.warmup):
-        step_dev(q_dev)
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
     with ClockSampler(local) as clocks:
-        time.sleep(0.2)
+        for _ in range(args.warmup):
+            step_dev(q_dev)
+        barrier()
+        t_begin = time.time()
         evs[0].record()
         for i in range(args.steps):
             out_i, out_d = step_dev(q_dev)
             evs[i + 1].record()
         barrier()
+        clocks.window(t_begin, time.time())
     dev_ms = max_over_ranks(evs[0].elapsed_time(evs[-1]))
     step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     value = nq * args.steps / (dev_ms / 1e3)
@@ -545,13 +552,13 @@ def main():
         if rc:
             raise RuntimeError(lib.cphnsw_b200_last_error(h).decode())
 
-    for _ in range(args.warmup):
-        dev_step()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     kernel_ms, prep_ms = [], []
-    barrier()
-    with ClockSampler(local) as clocks:
-        time.sleep(0.2)
+    with ClockSampler(local) as clocks:      # started before the warm-up so the GPU does not idle (and down-clock) before step 1
+        for _ in range(args.warmup):
+            dev_step()
+        barrier()
+        t_begin = time.time()
         with torch.cuda.stream(stream):
             evs[0].record()
             for i in range(args.steps):
@@ -560,6 +567,7 @@ def main():
                 tm = ix.last_timings()
                 kernel_ms.append(tm["search_ms"]); prep_ms.append(tm["prep_ms"])
         barrier()
+        clocks.window(t_begin, time.time())
     step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     dev_ms = max_over_ranks(evs[0].elapsed_time(evs[-1]))
     retries = st["overflow_retries"]
