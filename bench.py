@@ -554,7 +554,7 @@ def main():
 
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     kernel_ms, prep_ms = [], []
-    with ClockSampler(local) as clocks:      # started before the warm-up so the GPU does not idle (and down-clock) before step 1
+    with ClockSampler(local, 0.01) as clocks:      # started before the warm-up so the GPU does not idle (and down-clock) before step 1
         for _ in range(args.warmup):
             dev_step()
         barrier()
