@@ -236,6 +236,64 @@ def time_reference(args, path, q, budget_s, steps, warmup, k=None):
 
 
 # ---------------------------------------------------------------------------------------------------
+# the configuration on which the reference itself reaches the metric's recall gate: 100k x 128, 1-bit codes
+# ---------------------------------------------------------------------------------------------------
+def gate_config(args, local, torch, cph):
+    """BASELINE configs[0] (100k x 128, 1-bit): search k_search results as the reference does, de-duplicate, keep k;
+    smallest k_search with recall@k >= gate; QPS of both arms there.  Returns a dict for the bench line."""
+    import copy
+
+    ga = copy.copy(args)
+    ga.n, ga.bits, ga.clusters = 100_000, 1, 0
+    path, src = obtain_index(ga, 0, 1)
+    ix = cph.CPIndex(ga.dim, ga.bits, device=local)
+    ix.load(str(path))
+    q = make_queries(ga, 0)
+    q_dev = torch.from_numpy(q).cuda()
+    gt = ground_truth(path, q, ga.k, torch.device("cuda", local))
+    out = {"workload": f"{ga.n}x{ga.dim} synthetic iid N(0,1), {ga.bits}-bit RaBitQ CP-HNSW graph search, {ga.nq} queries, k={ga.k}",
+           "index_source": src, "gate": args.gate, "curve": [], "reached": False}
+    for ks in (10, 20, 30, 40):
+        ui, _ = ix.search_batch_unique(q_dev, ga.k, k_search=ks)
+        rec = recall_at_k(ui.cpu().numpy(), gt)
+        out["curve"].append({"k_search": ks, "recall_at_10": rec})
+        log(f"[bench] gate config: k_search={ks}: de-duplicated recall@{ga.k} = {rec:.4f}")
+        if rec >= args.gate:
+            out.update({"reached": True, "k_search": ks, "recall_at_10": rec})
+            break
+    if not out["reached"]:
+        return out
+    ks = out["k_search"]
+    for _ in range(2):
+        ix.search_batch_unique(q_dev, ga.k, k_search=ks)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(args.steps):
+        ix.search_batch_unique(q_dev, ga.k, k_search=ks)
+    ev[1].record()
+    torch.cuda.synchronize()
+    out["value"] = ga.nq * args.steps / (ev[0].elapsed_time(ev[1]) / 1e3)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        hi, _ = ix.search_batch_unique(q, ga.k, k_search=ks)
+    out["e2e"] = ga.nq * args.steps / (time.perf_counter() - t0)
+    out["unit"] = "queries/s"
+    if not args.no_cpu_baseline:
+        r = time_reference(ga, path, q, budget_s=min(args.cpu_budget, 10.0), steps=1, warmup=0, k=ks)
+        if r is not None:
+            ri = np.full((r["m"], ga.k), -1, np.int64)
+            for row, srcrow in enumerate(r["ids"]):
+                u = list(dict.fromkeys(int(x) for x in srcrow if x >= 0))[:ga.k]
+                ri[row, :len(u)] = u
+            out["cpu_baseline"] = {"value": r["value"], "unit": "queries/s", "cores": r["cores"], "kind": "reference",
+                                   "sample": r["sample"] + f" at k={ks}; de-duplication (numpy) not timed",
+                                   "recall_at_10": recall_at_k(ri, gt[:r["m"]]),
+                                   "ids_identical_to_gpu": bool(np.array_equal(np.sort(ri, 1), np.sort(hi[:r["m"]], 1)))}
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
 # workload c4 (BASELINE config 4): exhaustive batched scan over 1-bit per-vertex codes, database sharded over the ranks
 # ---------------------------------------------------------------------------------------------------
 def _c4_calibration() -> bytes:
@@ -616,7 +674,8 @@ def main():
     roofline = {"bound": "hbm", "kernel": f"search_kernel<{B}> (K3: descent + beam search + fused exact-L2 rerank)", "achieved": achieved, "peak": peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s", "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": k_ms, "prep_kernel_ms": float(np.mean(prep_ms)),
-                "expansions_per_query": st["expansions"] / args.nq, "bytes_per_expansion": block_bytes + vec_bytes}
+                "expansions_per_query": st["expansions"] / args.nq, "bytes_per_expansion": block_bytes + vec_bytes,
+                "frac_of_nominal_8tbs": achieved / 8000.0}
 
     line = {"metric": metric, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -653,7 +712,7 @@ def main():
         fs_ms = float(np.mean(times))
         fs_gbs = nblk * fs_bytes / (fs_ms / 1e3) / 1e9
         line["fastscan_stream"] = {"kernel": f"fastscan_blocks_kernel<{B}> (K2, TMA-pipelined stream of all {nblk} blocks, one query, est+lower written)",
-                                   "achieved": fs_gbs, "unit": "GB/s", "peak": peak, "frac": fs_gbs / peak, "ms": fs_ms,
+                                   "achieved": fs_gbs, "unit": "GB/s", "peak": peak, "frac": fs_gbs / peak, "frac_of_nominal_8tbs": fs_gbs / 8000.0, "ms": fs_ms,
                                    "algorithmic_bytes_per_block": fs_bytes, "blocks_per_s": nblk / (fs_ms / 1e3), "codes_per_s": 32 * nblk / (fs_ms / 1e3)}
 
     if rank == 0:
@@ -727,6 +786,11 @@ def main():
                 gate["reached"] = True
                 gate["curve"] = curve
                 line["recall_gate"] = gate
+            try:
+                del ix
+                line["recall_gate_100k_1bit"] = gate_config(args, local, torch, cphnsw_b200)
+            except Exception as e:  # noqa: BLE001 - a secondary figure must not take the bench line down
+                log(f"[bench] gate config skipped: {e}")
         print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
