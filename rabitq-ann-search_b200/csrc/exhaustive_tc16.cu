@@ -486,7 +486,7 @@ cudaError_t launch_exhaustive_scan_tc16(const DevIndex& ix, const ExhaustiveArgs
     const uint64_t m = a.id_end - a.id_begin;
     cudaError_t e;
     // thresholds first: the i8 form over a prefix of the range (its candidate lists are not kept)
-    const uint64_t prefix = m < 16384 ? m : 16384;
+    const uint64_t prefix = m < 65536 ? m : 65536;
     if (a.kprime && prefix) {
         e = launch_exhaustive_tc_prepare(ix, a.id_begin, a.id_begin + prefix, a.nq, w.vstat, w.taug, true, num_sms, stream);
         if (e != cudaSuccess) return e;
