@@ -113,13 +113,16 @@ struct T16Shared {
 
 // queue record (16 bits): column : 8 | lane : 5 | tile-in-window : 3   (the rows of a warp are those of its lane quarter)
 template <bool DENSE>
-__device__ __noinline__ void t16_drain(T16Shared& sh, const unsigned short* __restrict__ wq, uint32_t* qn, uint32_t lane, uint32_t wbase) {
-    // wbase = id of this warp's lane 0 in the first tile of the window
+__device__ __noinline__ void t16_drain(T16Shared& sh, uint32_t wq_s, uint32_t qn_s, uint32_t lane, uint32_t wbase) {
+    // wq_s / qn_s: shared-window addresses of the warp's queue and its fill count (plain 32-bit values: the callers sit in
+    // the compare loop and must not carry generic pointers); wbase = id of this warp's lane 0 in the first tile of the window
     const T16Drain& d = sh.drain;
     __syncwarp();
-    const uint32_t n = *qn;
+    const uint32_t n = tc_lds(qn_s);
     for (uint32_t i = lane; i < n; i += 32) {
-        const uint32_t e = wq[i];
+        unsigned short e16;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(e16) : "r"(wq_s + i * 2u) : "memory");
+        const uint32_t e = e16;
         const uint32_t col = e & 0xFFu, id = wbase + ((e >> 8) & 31u) + (e >> 13) * kTcM;
         // fs = sum_i bit_i u_i, popcount form (D <= 128: one chunk)
         const uint4 w = __ldg(reinterpret_cast<const uint4*>(d.codes) + id);
@@ -138,7 +141,7 @@ __device__ __noinline__ void t16_drain(T16Shared& sh, const unsigned short* __re
         }
     }
     __syncwarp();
-    if (lane == 0) *qn = 0;
+    if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(qn_s), "r"(0u) : "memory");
     __syncwarp();
 }
 
@@ -336,12 +339,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc16_kernel(con
             const uint32_t row = quarter * 32 + lane;
             const uint32_t colbase = cg * 64;
             const uint32_t own0 = colbase + quarter * 16;
-            unsigned short* myq = queues + (size_t)e * k16Queue;
-            uint32_t* myqn = &sh.qn[e];
-            const uint32_t myq_s = tc_smem_u32(myq), myqn_s = tc_smem_u32(myqn);
+            const uint32_t myq_s = tc_smem_u32(queues) + e * (uint32_t)(k16Queue * 2), myqn_s = tc_smem_u32(&sh.qn[0]) + e * 4u;
             uint32_t tw = 0, nckpt = 0;   // tile within the checkpoint window, checkpoints so far
             for (uint32_t t = 0; t < ntiles; ++t, ++tcount) {
-                const bool live = vb + (uint64_t)t * kTcM + row < ve;
+                const bool live = row < (uint32_t)min((uint64_t)kTcM, ve - (vb + (uint64_t)t * kTcM));
                 const uint32_t rowtag = (lane | (tw << 5)) << 8;
                 const uint32_t wbase = (uint32_t)(vb + (uint64_t)(t - tw) * kTcM) + quarter * 32u;
                 const uint32_t buf = tcount & 1u;
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc16_kernel(con
                         if (lane == 0) tc_arrive(&sh.acc_empty[buf]);
                     }
                     // one compare per pair: acc = fs - thr + margin >= 0 (the sign bit of a float is the sign of the int)
-                    if (tc_lds(myqn_s) > (uint32_t)(k16Queue - 1024)) t16_drain<DENSE>(sh, myq, myqn, lane, wbase);   // room for this half
+                    if (tc_lds(myqn_s) > (uint32_t)(k16Queue - 1024)) t16_drain<DENSE>(sh, myq_s, myqn_s, lane, wbase);   // room for this half
 #pragma unroll
                     for (int c16 = 0; c16 < 2; ++c16) {
                         uint32_t any = 0x80000000u;
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc16_kernel(con
                 }
 
                 const bool checkpoint = tw == G - 1u || t + 1 == ntiles;
-                if (checkpoint || DENSE) t16_drain<DENSE>(sh, myq, myqn, lane, wbase);
+                if (checkpoint || DENSE) t16_drain<DENSE>(sh, myq_s, myqn_s, lane, wbase);
                 tw = checkpoint ? 0u : tw + 1u;
                 if (kp && checkpoint) {
                     tc_group_sync(1 + cg);
