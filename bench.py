@@ -192,6 +192,36 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the unmodified reference's search_batch on the host cores
 # ---------------------------------------------------------------------------------------------------
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def reference_one_thread(args, path, k, budget_s=5.0):
+    """QPS of the reference's search_batch with ONE OpenMP thread, in a subprocess because libgomp reads
+    OMP_NUM_THREADS once."""
+    code = (
+        "import sys, time, json, numpy as np; sys.path.insert(0, %r); import cphnsw\n"
+        "ix = cphnsw.CPIndex(dim=%d, bits=%d); ix.load(%r)\n"
+        "q = np.random.default_rng(99).standard_normal((4096, %d)).astype(np.float32)\n"
+        "t = time.perf_counter(); ix.search_batch(q[:8], %d); per = (time.perf_counter() - t) / 8\n"
+        "m = int(max(8, min(4096, %f / max(per, 1e-9))))\n"
+        "t = time.perf_counter(); ix.search_batch(q[:m], %d); dt = time.perf_counter() - t\n"
+        "print(json.dumps({'value': m / dt, 'queries': m}))\n"
+    ) % (str(ROOT / "oracle" / "_ref"), args.dim, args.bits, str(path), args.dim, k, budget_s, k)
+    try:
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, env=dict(os.environ, OMP_NUM_THREADS="1"))
+        return json.loads(r.stdout.strip().split("\n")[-1])
+    except Exception as e:  # noqa: BLE001
+        log(f"[bench] 1-thread reference run skipped: {e}")
+        return None
+
+
 def reference_module():
     # all host cores for the reference's OpenMP loop (src/bindings.cpp:196-200), also under torchrun, which
     # exports OMP_NUM_THREADS=1 to its workers; must be set before libgomp initialises
@@ -725,6 +755,10 @@ def main():
             r = time_reference(args, path, q, budget_s=args.cpu_budget, steps=1, warmup=0)
             if r is not None:
                 line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                line["cpu_baseline"]["cpu_model"] = cpu_model()
+                one = reference_one_thread(args, path, args.k)
+                if one:
+                    line["cpu_baseline"]["one_thread"] = {"value": one["value"], "unit": "queries/s", "sample": f"{one['queries']} queries, OMP_NUM_THREADS=1"}
                 same = np.array_equal(np.sort(r["ids"], 1), np.sort(ids_np[:r["m"]], 1))
                 line["cpu_baseline"]["ids_identical_to_gpu"] = bool(same)
                 if not args.no_recall:
