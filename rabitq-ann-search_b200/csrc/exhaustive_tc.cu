@@ -71,16 +71,6 @@ __global__ void exhaustive_tc_prepare_kernel(const DevIndex ix, uint64_t id_begi
     if ((threadIdx.x & 31) == 0 && c > 0.0f) { atomicAdd(acc + 0, s); atomicAdd(acc + 1, a); atomicAdd(acc + 2, c); }
 }
 
-struct TcShared {
-    float4 qpar[kTcNQ];    // screen constants
-    float4 par[kTcNQ];     // A, Bc, C, |q-c|^2
-    float tau[kTcNQ];
-    uint32_t cnt[kTcNQ];
-    uint64_t a_full[kTcStages], a_empty[kTcStages], acc_full[2], acc_empty[2];
-    uint32_t qn[kTcEpiWarps];   // passer queue fill, per epilogue warp
-    uint32_t tmem_base;
-};
-
 // Pairs that pass the screen are rare and scattered over lanes, so the lane that finds one only queues a 4-byte
 // record {fs : 12 | column : 8 | row : 7 | tile within the checkpoint window : 2} in its warp's shared-memory queue
 // (a handful of divergent instructions); the queue is drained by the whole warp, one pair per lane: the exact
@@ -94,13 +84,27 @@ struct TcDrain {
     unsigned long long* lists;
 };
 
+struct TcShared {
+    float4 qpar[kTcNQ];    // screen constants
+    float4 par[kTcNQ];     // A, Bc, C, |q-c|^2
+    float tau[kTcNQ];
+    uint32_t cnt[kTcNQ];
+    uint64_t a_full[kTcStages], a_empty[kTcStages], acc_full[2], acc_empty[2];
+    uint32_t qn[kTcEpiWarps];   // passer queue fill, per epilogue warp
+    TcDrain drain;              // arguments of tc_drain for the current work item
+    uint32_t tmem_base;
+};
+
 // `wbase` = id of row 0 of the first tile of the current checkpoint window
 template <bool DENSE>
-__device__ __noinline__ void tc_drain(const TcDrain d, TcShared& sh, const uint32_t* __restrict__ wq, uint32_t* qn, uint32_t lane, uint32_t wbase) {
+__device__ __noinline__ void tc_drain(TcShared& sh, uint32_t wq_s, uint32_t qn_s, uint32_t lane, uint32_t wbase) {
+    // (queue and fill count by shared-window address, arguments from shared memory: the callers sit in the screen loop and
+    //  must not carry generic pointers or a parameter block in registers)
+    const TcDrain& d = sh.drain;
     __syncwarp();
-    const uint32_t n = *qn;
+    const uint32_t n = tc_lds(qn_s);
     for (uint32_t i = lane; i < n; i += 32) {
-        const uint32_t e = wq[i];
+        const uint32_t e = tc_lds(wq_s + i * 4u);
         const uint32_t fs = e & 0xFFFu, col = (e >> 12) & 0xFFu, id = wbase + (e >> 20);   // (row | tile << 7) = offset in the window
         const float4 P = sh.par[col];
         const float est = flat_estimate(P.x, P.y, P.z, d.aa, d.ab, d.floor_, P.w, fs, (float)__ldg(d.pop + id), __ldg(d.nop + id), __ldg(d.ipqo + id));
@@ -115,7 +119,7 @@ __device__ __noinline__ void tc_drain(const TcDrain d, TcShared& sh, const uint3
         }
     }
     __syncwarp();
-    if (lane == 0) *qn = 0;
+    if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(qn_s), "r"(0u) : "memory");
     __syncwarp();
 }
 
@@ -211,6 +215,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc_kernel(const
             sh.qpar[i] = DENSE ? make_float4(0.0f, 0.0f, 0.0f, i < nqt ? -kTcBig : kTcBig)
                                : tc_query_params(i < nqt, p.x, p.y, p.z, p.w, tau, lim, dmax);
         }
+        if (tid == 0)
+            sh.drain = TcDrain{ix.flat_nop, ix.flat_ipqo, ix.flat_pop, cal.affine_a, cal.affine_b, cal.ip_qo_floor, kp, q0, a.id_begin, m, a.sums, a.est, mylists};
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
 
@@ -290,10 +296,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc_kernel(const
             const uint32_t row = quarter * 32 + lane;
             const uint32_t colbase = cg * 64;
             const uint32_t own0 = colbase + quarter * 16;     // the 16 lists this warp maintains between tiles
-            uint32_t* myq = queues + (size_t)e * kTcQueue;
-            uint32_t* myqn = &sh.qn[e];
-            const uint32_t myq_s = tc_smem_u32(myq), myqn_s = tc_smem_u32(myqn);
-            const TcDrain dr{ix.flat_nop, ix.flat_ipqo, ix.flat_pop, cal.affine_a, cal.affine_b, cal.ip_qo_floor, kp, q0, a.id_begin, m, a.sums, a.est, mylists};
+            const uint32_t myq_s = tc_smem_u32(queues) + e * (uint32_t)(kTcQueue * 4), myqn_s = tc_smem_u32(&sh.qn[0]) + e * 4u;
             for (uint32_t t = 0; t < ntiles; ++t, ++tcount) {
                 const uint32_t rowtag = (row | ((t % G) << 7)) << 20;                           // queue record: where this vertex is
                 const uint32_t wbase = (uint32_t)(vb + (uint64_t)(t - t % G) * kTcM);           // ... relative to this id
@@ -324,7 +327,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc_kernel(const
                         if (lane == 0) tc_arrive(&sh.acc_empty[buf]);
                     }
                     // room for every pair of this half (32 columns x 32 lanes)?
-                    if (tc_lds(myqn_s) > (uint32_t)(kTcQueue - 1024)) tc_drain<DENSE>(dr, sh, myq, myqn, lane, wbase);
+                    if (tc_lds(myqn_s) > (uint32_t)(kTcQueue - 1024)) tc_drain<DENSE>(sh, myq_s, myqn_s, lane, wbase);
                     // the screen, 7 instructions per pair (LDS.128, LOP3, 3 FFMA, FSETP.OR), branch-free over 8 columns;
                     // only a lane with a hit among its 8 pairs looks at them one by one and queues the passers
 #pragma unroll
@@ -350,7 +353,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc_kernel(const
                 }
 
                 const bool checkpoint = t % G == G - 1 || t + 1 == ntiles;
-                if (checkpoint || DENSE) tc_drain<DENSE>(dr, sh, myq, myqn, lane, wbase);
+                if (checkpoint || DENSE) tc_drain<DENSE>(sh, myq_s, myqn_s, lane, wbase);
                 if (kp && checkpoint) {
                     tc_group_sync(1 + cg);   // the four warps appending to these 64 lists are done with this tile
                     const uint32_t mycol = own0 + (lane & 15u);
