@@ -371,16 +371,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc16_kernel(con
                     if (tc_lds(myqn_s) > (uint32_t)(k16Queue - 1024)) t16_drain<DENSE>(sh, myq_s, myqn_s, lane, wbase);   // room for this half
 #pragma unroll
                     for (int c16 = 0; c16 < 2; ++c16) {
-                        uint32_t any = 0x80000000u;
+                        // the sign bit of an AND survives iff every acc in it is negative: four groups of four columns, then all
+                        uint32_t g4[4];
 #pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) any &= r[c16 * 16 + jj];      // sign bit survives iff every acc is negative
+                        for (int g = 0; g < 4; ++g)
+                            g4[g] = r[c16 * 16 + g * 4] & r[c16 * 16 + g * 4 + 1] & r[c16 * 16 + g * 4 + 2] & r[c16 * 16 + g * 4 + 3];
+                        const uint32_t any = g4[0] & g4[1] & g4[2] & g4[3];
                         if (live && !(any & 0x80000000u)) {
 #pragma unroll
-                            for (int jj = 0; jj < 16; ++jj)
-                                if (!(r[c16 * 16 + jj] & 0x80000000u)) {
-                                    uint32_t pos;
-                                    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(myqn_s) : "memory");
-                                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(myq_s + pos * 2u), "h"((unsigned short)((col0 + (uint32_t)(c16 * 16 + jj)) | rowtag)) : "memory");
+                            for (int g = 0; g < 4; ++g)
+                                if (!(g4[g] & 0x80000000u)) {
+#pragma unroll
+                                    for (int jj = 0; jj < 4; ++jj)
+                                        if (!(r[c16 * 16 + g * 4 + jj] & 0x80000000u)) {
+                                            uint32_t pos;
+                                            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(myqn_s) : "memory");
+                                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(myq_s + pos * 2u),
+                                                         "h"((unsigned short)((col0 + (uint32_t)(c16 * 16 + g * 4 + jj)) | rowtag)) : "memory");
+                                        }
                                 }
                         }
                     }
