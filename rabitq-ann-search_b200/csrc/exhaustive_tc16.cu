@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc16_kernel(con
                     lo8.w = h2bits(-pcf, -pcf);    // columns 6, 7
                 }
                 const uint32_t s = step % k16Stages;
-                tc_wait_relaxed<4000>(&sh.a_empty[s], ((step / k16Stages) & 1u) ^ 1u);
+                tc_wait_sleep<200>(&sh.a_empty[s], ((step / k16Stages) & 1u) ^ 1u);
                 uint8_t* arow = rowoff + (size_t)s * k16StageA;
                 // code bits -> f16 0.0 / 1.0, 8 dimensions (16 bytes) per core row
                 const uint32_t wd[4] = {w.x, w.y, w.z, w.w};
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) exhaustive_scan_tc16_kernel(con
                 const uint32_t rowtag = (lane | (tw << 5)) << 8;
                 const uint32_t wbase = (uint32_t)(vb + (uint64_t)(t - tw) * kTcM) + quarter * 32u;
                 const uint32_t buf = tcount & 1u;
-                tc_wait_relaxed<1000>(&sh.acc_full[buf], (tcount >> 1) & 1u);
+                tc_wait_sleep<100>(&sh.acc_full[buf], (tcount >> 1) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
                 for (uint32_t half = 0; half < 2; ++half) {

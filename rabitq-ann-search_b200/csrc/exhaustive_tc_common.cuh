@@ -49,6 +49,17 @@ __device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t phase) {
     } while (!done);
 }
 // for the roles that run ahead and then wait long (expanders, issuer): do not spin in the epilogue's issue slots
+// poll with a real sleep between polls (ns): for many warps waiting on the same event
+template <int NS>
+__device__ __forceinline__ void tc_wait_sleep(uint64_t* bar, uint32_t phase) {
+    uint32_t done;
+    for (;;) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(tc_smem_u32(bar)), "r"(phase) : "memory");
+        if (done) break;
+        __nanosleep(NS);
+    }
+}
 template <int NS>
 __device__ __forceinline__ void tc_wait_relaxed(uint64_t* bar, uint32_t phase) {
     uint32_t done;
