@@ -55,6 +55,31 @@ def _is_torch(x) -> bool:
     return type(x).__module__.split(".")[0] == "torch"
 
 
+def recover_id_map(save_path: str, vectors, dim: int) -> np.ndarray:
+    """internal id -> row of `vectors`, for a save file (api/hnsw_index.hpp:217-303) built from `vectors`.
+
+    finalize() renumbers the vertices in BFS order (graph/rabitq_graph.hpp:208-278) and keeps no map back, but the
+    file stores every raw vector in internal order, so rows are matched by their bytes."""
+    v = np.ascontiguousarray(np.asarray(vectors), dtype=np.float32)
+    with open(save_path, "rb") as f:
+        hdr = f.read(68)
+    D = int.from_bytes(hdr[12:16], "little")
+    fdim = int.from_bytes(hdr[24:28], "little")
+    n = int.from_bytes(hdr[28:36], "little")
+    if v.ndim != 2 or v.shape[1] != dim or fdim != dim or v.shape[0] != n:
+        raise ValueError("vectors must be the (n, dim) float32 array the index was built from")
+    off = 68 + 248 + 72 + 4 * dim + 8 * n
+    raw = np.memmap(save_path, np.float32, "r", off, (n, D))[:, :dim]
+    key = lambda a: np.ascontiguousarray(a).view(np.dtype((np.void, 4 * dim))).ravel()  # noqa: E731
+    ko, kr = key(v), key(np.ascontiguousarray(raw))
+    order = np.argsort(ko, kind="stable")
+    pos = np.minimum(np.searchsorted(ko[order], kr), n - 1)
+    m = order[pos].astype(np.uint32)
+    if not np.array_equal(ko[m], kr):
+        raise ValueError("the index does not hold these vectors")
+    return m
+
+
 class CPIndex:
     """Drop-in for ``cphnsw.CPIndex`` whose ``search`` / ``search_batch`` run on the GPU."""
 
@@ -230,24 +255,7 @@ class CPIndex:
         section `raw`, internal order: api/hnsw_index.hpp:217-303) against `vectors` (the array the index was
         built from).  Rows of `vectors` that are bit-identical are indistinguishable: any of them is returned."""
         self._require_finalized()
-        v = np.ascontiguousarray(np.asarray(vectors), dtype=np.float32)
-        if v.ndim != 2 or v.shape[1] != self._dim or v.shape[0] != self.size:
-            raise ValueError("vectors must be the (n, dim) float32 array the index was built from")
-        with open(self._source_path, "rb") as f:
-            hdr = f.read(68)
-        D = int.from_bytes(hdr[12:16], "little")
-        n = int.from_bytes(hdr[28:36], "little")
-        off = 68 + 248 + 72 + 4 * self._dim + 8 * n
-        raw = np.memmap(self._source_path, np.float32, "r", off, (n, D))[:, : self._dim]
-        key = lambda a: np.ascontiguousarray(a).view(np.dtype((np.void, 4 * self._dim))).ravel()  # noqa: E731
-        ko, kr = key(v), key(np.ascontiguousarray(raw))
-        order = np.argsort(ko, kind="stable")
-        pos = np.searchsorted(ko[order], kr)
-        pos = np.minimum(pos, n - 1)
-        m = order[pos].astype(np.uint32)
-        if not np.array_equal(ko[m], kr):
-            raise ValueError("the index does not hold these vectors")
-        self._id_map = m
+        self._id_map = recover_id_map(self._source_path, vectors, self._dim)
         self._id_map_dev = None
 
     def _device_id_map(self):

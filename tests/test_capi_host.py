@@ -123,3 +123,21 @@ def test_topk_merge_is_exact():
         cand.sort()
         assert [c[1] for c in cand[:k]] == mi[qi].tolist()
         assert np.array_equal(np.float32([c[0] for c in cand[:k]]), md[qi])
+
+
+def test_internal_to_original_id_map_from_a_reference_save_file():
+    """recover_id_map on the committed reference-written index files: the map is a permutation of the rows the index
+    was built from (tests/golden/make_golden.py: co.synthetic(300, 24, seed=7)) and reproduces the stored vectors."""
+    src = (ROOT / "rabitq-ann-search_b200" / "cphnsw_b200" / "index.py").read_text()
+    ns = {"__name__": "idx_only"}
+    exec(compile(src.replace("from . import _capi", "_capi = None"), "index.py", "exec"), ns)   # the map needs no native code
+    rng = np.random.default_rng(7)
+    base = rng.standard_normal((300, 24)).astype(np.float32)
+    for bits in (1, 2, 4):
+        path = str(ROOT / "tests" / "golden" / f"ref_n300_d24_b{bits}.bin")
+        m = ns["recover_id_map"](path, base, 24)
+        assert sorted(m.tolist()) == list(range(300))
+        raw = np.memmap(path, np.float32, "r", 68 + 248 + 72 + 4 * 24 + 8 * 300, (300, 32))[:, :24]
+        assert np.array_equal(base[m], raw)
+    with pytest.raises(ValueError):
+        ns["recover_id_map"](path, base[::-1] * 2, 24)
