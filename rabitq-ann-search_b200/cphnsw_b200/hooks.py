@@ -41,8 +41,9 @@ def prepare_queries(ix, queries: torch.Tensor, center: bool = False):
 
 
 def fastscan_blocks(ix, uplanes, coeffs, dqp, vertex_ids=None, first_vertex=0, nblocks=None,
-                    query_of_block=None, slack_level=None, want=("nbit", "msb", "msb2", "est", "lower", "msb_lower")):
-    """K2 over the neighbour blocks of `vertex_ids` (or a contiguous range).  Outputs are [nblocks, 32]."""
+                    query_of_block=None, slack_level=None, want=("nbit", "msb", "msb2", "est", "lower", "msb_lower"), out=None):
+    """K2 over the neighbour blocks of `vertex_ids` (or a contiguous range).  Outputs are [nblocks, 32]; `out` may
+    carry pre-allocated output tensors (same names) so that a timed call launches nothing but the kernel."""
     dev = _dev(ix)
     if vertex_ids is not None:
         vertex_ids = vertex_ids.to(dev, torch.int32).contiguous()
@@ -53,11 +54,12 @@ def fastscan_blocks(ix, uplanes, coeffs, dqp, vertex_ids=None, first_vertex=0, n
         query_of_block = query_of_block.to(dev, torch.int32).contiguous()
     if slack_level is not None:
         slack_level = slack_level.to(dev, torch.int32).contiguous()
+    given = out or {}
     out = {}
     for name in ("nbit", "msb", "msb2"):
-        out[name] = torch.empty((nblocks, 32), dtype=torch.int32, device=dev) if name in want else None
+        out[name] = (given.get(name) if name in given else torch.empty((nblocks, 32), dtype=torch.int32, device=dev)) if name in want else None
     for name in ("est", "lower", "msb_lower"):
-        out[name] = torch.empty((nblocks, 32), dtype=torch.float32, device=dev) if name in want else None
+        out[name] = (given.get(name) if name in given else torch.empty((nblocks, 32), dtype=torch.float32, device=dev)) if name in want else None
     _capi.check(ix.handle, ix._lib.cphnsw_b200_fastscan_blocks(
         ix.handle, uplanes.data_ptr(), coeffs.data_ptr(), uplanes.shape[0], _ptr(query_of_block), _ptr(vertex_ids),
         first_vertex, nblocks, dqp.data_ptr(), _ptr(slack_level), _ptr(out["nbit"]), _ptr(out["msb"]),
