@@ -41,13 +41,6 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 __device__ __forceinline__ void tc_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t phase) {
-    uint32_t done;
-    do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(tc_smem_u32(bar)), "r"(phase) : "memory");
-    } while (!done);
-}
 // for the roles that run ahead and then wait long (expanders, issuer): do not spin in the epilogue's issue slots
 // poll with a real sleep between polls (ns): for many warps waiting on the same event
 template <int NS>
