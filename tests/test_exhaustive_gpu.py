@@ -117,6 +117,33 @@ def test_screen_survives_data_scale(oracle, tc, scale):
         assert np.array_equal(_bits(dists[i, :len(oi)]), _bits(od))
 
 
+@pytest.mark.parametrize("tc", [2, 1, 0])
+def test_golden_reference_composition(tc):
+    """All three scan forms against tests/golden/exhaustive_golden.npz -- composed from primitives executed by the
+    unmodified reference (tests/golden/make_exhaustive_golden.py) on the committed reference-built 1-bit index; needs
+    neither the oracle nor oracle/_ref at run time."""
+    import cphnsw_b200
+    from cphnsw_b200 import hooks
+
+    torch = _torch()
+    g = np.load(common.GOLDEN / "exhaustive_golden.npz")
+    ix = cphnsw_b200.CPIndex(24, 1)
+    ix.load(str(common.GOLDEN / "ref_n300_d24_b1.bin"))
+    ix.set_option("exhaustive_tensor_cores", tc)
+    q = torch.from_numpy(g["queries"])
+    sums, est = hooks.exhaustive_estimates(ix, q)
+    sums, est = sums.cpu().numpy().view(np.uint32), est.cpu().numpy()
+    for i in range(len(g["queries"])):
+        assert np.array_equal(sums[i], g[f"sums_{i}"]), i
+        assert np.array_equal(_bits(est[i]), _bits(g[f"est_{i}"])), i
+    for k, kp in ((10, 100), (1, 1), (5, 32), (10, 300)):
+        ids, dists = hooks.exhaustive_search(ix, q, k, kp)
+        ids, dists = ids.cpu().numpy(), dists.cpu().numpy()
+        for i in range(len(g["queries"])):
+            assert np.array_equal(ids[i], g[f"ids_{i}_k{k}_kp{kp}"]), (i, k, kp)
+            assert np.array_equal(_bits(dists[i]), _bits(g[f"dists_{i}_k{k}_kp{kp}"])), (i, k, kp)
+
+
 def test_database_shards_merge_to_the_unsharded_answer(oracle):
     """DB-sharded mode on one device: each shard scans its id range, the k-way merge of the shards' top-k
     (by (distance, id)) equals what the oracle gives shard by shard merged the same way."""

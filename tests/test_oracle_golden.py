@@ -138,3 +138,22 @@ def test_search_vs_reference_module(oracle, bits):
         rid, rd = ref.search_batch(q, k)
         oid, od, _ = oracle.search_batch(oracle.index_view(co.SaveFile(path)), q, k)
         assert np.array_equal(rid, oid) and np.array_equal(_bits(rd), _bits(od))
+
+
+def test_exhaustive_restatement_against_the_reference_composition(oracle):
+    """cpo_exhaustive_search against tests/golden/exhaustive_golden.npz, which was composed in Python from primitives
+    executed by the unmodified reference (tests/golden/make_exhaustive_golden.py): integer sums, estimate bits, and the
+    (k, k') results, on the committed reference-built 1-bit index."""
+    g = np.load(common.GOLDEN / "exhaustive_golden.npz")
+    sf = co.SaveFile(common.GOLDEN / "ref_n300_d24_b1.bin")
+    view = oracle.index_view(sf)
+    q = g["queries"]
+    for i in range(len(q)):
+        for k, kp in ((10, 100), (1, 1), (5, 32), (10, 300)):
+            ids, dists, sums, est = oracle.exhaustive(view, sf, q[i], k, kp)
+            assert np.array_equal(sums, g[f"sums_{i}"]), i
+            assert np.array_equal(est.view(np.uint32), g[f"est_{i}"].view(np.uint32)), i
+            wi, wd = g[f"ids_{i}_k{k}_kp{kp}"], g[f"dists_{i}_k{k}_kp{kp}"]
+            m = int((wi >= 0).sum())
+            assert len(ids) == m and np.array_equal(ids.astype(np.int64), wi[:m]), (i, k, kp)
+            assert np.array_equal(np.asarray(dists, np.float32).view(np.uint32), wd[:m].view(np.uint32))
