@@ -133,6 +133,64 @@ void cpo_encode_query(uint32_t dim, uint32_t D, const float* signs, const float*
 }
 
 /* ======================================================================================
+ * BUILD side (SURVEY section 8f, N3 -- oracle groundwork; no CUDA counterpart yet):
+ * RaBitQEncoder<D>::compute_neighbor_aux, encoder/rabitq_encoder.hpp:138-181, with
+ * rotate_raw_vector (:81-86) and compute_ip_cp (:88-96): the 1-bit code of a neighbour relative to
+ * its parent vertex -- sign bits of the rotated unit offset, nop = |nb - parent|,
+ * ip_qo = |rotated|_1 / sqrt(D), ip_cp = sum_i (+-1)_i rotated_parent_i / sqrt(D).
+ * parent, nb: D floats (zero-padded); code: D/8 bytes, bit i = bit i%8 of byte i/8; aux = nop, ip_qo, ip_cp.
+ * `fused` selects how `nop_sq += d*d` is taken to have been compiled (1: fmaf, 0: mul then add) -- pinned against
+ * the compiled reference by tests/test_oracle_build_side.py: GCC 13.3 -O3 vectorises the squares and adds them one by
+ * one, i.e. fused = 0 is what the reference computes (fused = 1 differs in nop for ~20 % of random inputs).
+ * ==================================================================================== */
+void cpo_neighbor_aux_1bit(uint32_t dim, uint32_t D, const float* signs, const float* parent, const float* nb,
+                           int fused, uint8_t* code, float aux[3]) {
+    float* diff = (float*)malloc(sizeof(float) * D);
+    float* rp = (float*)malloc(sizeof(float) * D);
+    float Df = (float)D;
+    float norm_factor = 1.0f / (Df * sqrtf(Df));
+    float inv_sqrt_d = 1.0f / sqrtf(Df);
+    memset(code, 0, D / 8);
+    /* rotate_raw_vector(parent) */
+    memcpy(rp, parent, sizeof(float) * D);
+    for (uint32_t layer = 0; layer < 3; ++layer) {
+        for (uint32_t i = 0; i < D; ++i) rp[i] = rp[i] * signs[layer * D + i];
+        cpo_fht(rp, D);
+    }
+    for (uint32_t i = 0; i < D; ++i) rp[i] = rp[i] * norm_factor;
+
+    float nop_sq = 0.0f;
+    for (uint32_t i = 0; i < dim; ++i) {
+        diff[i] = nb[i] - parent[i];
+        nop_sq = fused ? fmaf(diff[i], diff[i], nop_sq) : nop_sq + diff[i] * diff[i];
+    }
+    for (uint32_t i = dim; i < D; ++i) diff[i] = 0.0f;
+    float nop = sqrtf(nop_sq);
+    aux[0] = nop; aux[1] = 0.0f; aux[2] = 0.0f;
+    if (nop < 1e-8f / Df) { free(diff); free(rp); return; }   /* constants::norm_epsilon(D) */
+    float inv_nop = 1.0f / nop;
+    for (uint32_t i = 0; i < D; ++i) diff[i] = diff[i] * inv_nop;
+    for (uint32_t layer = 0; layer < 3; ++layer) {
+        for (uint32_t i = 0; i < D; ++i) diff[i] = diff[i] * signs[layer * D + i];
+        cpo_fht(diff, D);
+    }
+    float l1 = 0.0f, ip = 0.0f;
+    for (uint32_t i = 0; i < D; ++i) {
+        float r = diff[i] * norm_factor;
+        if (r >= 0.0f) code[i >> 3] = (uint8_t)(code[i >> 3] | (1u << (i & 7)));
+        l1 = l1 + fabsf(r);
+    }
+    for (uint32_t i = 0; i < D; ++i) {
+        int bit = (code[i >> 3] >> (i & 7)) & 1;
+        ip = bit ? ip + rp[i] : ip - rp[i];
+    }
+    aux[1] = l1 * inv_sqrt_d;
+    aux[2] = ip * inv_sqrt_d;
+    free(diff);
+    free(rp);
+}
+
+/* ======================================================================================
  * FastScan integer sums: distance/fastscan_kernel.hpp:17-87 (one plane), :197-217 (N-bit),
  * :349-368 (top-two-planes "msb2").  Layout distance/fastscan_layout.hpp:10-49:
  * packed[sp][v] = (nibble(seg 2sp+1) << 4) | nibble(seg 2sp).  The AVX2 u8/u16 staging can

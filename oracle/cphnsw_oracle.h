@@ -28,6 +28,10 @@ void cpo_fht(float* x, uint32_t D);
 void cpo_encode_query(uint32_t dim, uint32_t D, const float* signs, const float* q,
                       uint8_t* lut /* [D/4][16] */, float coeffs[3], float* rotated);
 
+/* BUILD side (oracle groundwork): RaBitQEncoder<D>::compute_neighbor_aux (encoder/rabitq_encoder.hpp:138-181) */
+void cpo_neighbor_aux_1bit(uint32_t dim, uint32_t D, const float* signs, const float* parent, const float* nb,
+                           int fused, uint8_t* code, float aux[3]);
+
 /* ---- FastScan ------------------------------------------------------------------------ */
 void cpo_fastscan_plane(uint32_t D, const uint8_t* lut, const uint8_t* packed /* [D/8][32] */,
                         uint32_t out[32]);

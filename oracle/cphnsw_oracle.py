@@ -256,6 +256,28 @@ class Oracle:
         assert self.shim.refshim_rotate(C.c_uint32(dim), C.c_uint64(nq), _ptr(q, c_f32p), _ptr(out, c_f32p)) == 0
         return out
 
+    # ---- build side: neighbour codes relative to a parent (oracle groundwork) --------
+    def neighbor_aux(self, dim, B, parent, nbrs, ref=False, fused=0):
+        """codes u8 [n, B, D/8] (planes MSB first; B = 1: sign bits) and aux f32 [n, 3] = nop, ip_qo, ip_cp of the
+        neighbours `nbrs` [n, dim] of `parent` [dim].  ref=True: the unmodified reference through the shim
+        (compute_neighbor_aux / compute_neighbor_aux_nbit); else the C restatement (1-bit only so far)."""
+        D = 1 << (dim - 1).bit_length()
+        par = np.zeros(D, np.float32); par[:dim] = parent
+        nb = np.zeros((len(nbrs), D), np.float32); nb[:, :dim] = nbrs
+        codes = np.zeros((len(nbrs), B, D // 8), np.uint8)
+        aux = np.zeros((len(nbrs), 3), np.float32)
+        if ref:
+            rc = self.shim.refshim_neighbor_aux(C.c_uint32(D), C.c_uint32(B), C.c_uint32(dim), C.c_uint64(len(nbrs)),
+                                                _ptr(par, c_f32p), _ptr(nb, c_f32p), _ptr(codes, c_u8p), _ptr(aux, c_f32p))
+            assert rc == 0, "the shim offers D >= 64, B in {1, 2, 4}"
+        else:
+            assert B == 1, "the restatement covers the 1-bit encoder so far"
+            signs = self.rotation_signs(D)
+            for i in range(len(nbrs)):
+                self.lib.cpo_neighbor_aux_1bit(C.c_uint32(dim), C.c_uint32(D), _ptr(signs, c_f32p), _ptr(par, c_f32p), _ptr(nb[i], c_f32p),
+                                               C.c_int(fused), _ptr(codes[i, 0], c_u8p), _ptr(aux[i], c_f32p))
+        return codes, aux
+
     # ---- fastscan --------------------------------------------------------------------------
     def fastscan(self, D, B, lut, planes, ref=False):
         lut = np.ascontiguousarray(lut, np.uint8)

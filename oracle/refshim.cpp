@@ -12,6 +12,10 @@
 //   refshim_convert          -> fastscan::convert_to_distances_with_bounds / convert_msb_to_lower_bounds /
 //                               convert_nbit_to_distances_with_bounds    (distance/fastscan_kernel.hpp:89-194,371-425,220-346)
 //   refshim_dot / refshim_l2 -> dot_product_simd<D> / l2_distance_simd<D> (core/memory.hpp:65-96)
+//   refshim_neighbor_aux     -> RaBitQEncoder<D>::compute_neighbor_aux / NbitRaBitQEncoder<D,B>::compute_neighbor_aux_nbit
+//                               after rotate_raw_vector(parent)            (encoder/rabitq_encoder.hpp:81-86,138-181,287-323,
+//                               371-467; called by prune_and_write, graph/graph_refinement.hpp:46-67) -- BUILD side
+//                               (SURVEY section 8f, N3): oracle groundwork for the next round, no CUDA counterpart yet
 //
 // Built by oracle/Makefile into oracle/_ref/libcphnsw_refshim.so (git-ignored).
 #include <cphnsw/core/codes.hpp>
@@ -96,6 +100,34 @@ int convert_t(const QParams& p, const uint32_t* nbit, const uint32_t* msb, const
     return 0;
 }
 
+// build side: one parent vertex, n candidate neighbours (all vectors zero-padded to D floats, as RaBitQGraph stores them)
+template <size_t D>
+int neighbor_aux_1bit_t(uint32_t dim, uint64_t n, const float* parent, const float* nbrs, uint8_t* codes, float* aux) {
+    RaBitQEncoder<D> enc(dim, constants::kDefaultRotationSeed);
+    alignas(32) float rp[D];
+    enc.rotate_raw_vector(parent, rp);
+    for (uint64_t i = 0; i < n; ++i) {
+        BinaryCodeStorage<D> c;
+        VertexAuxData a = enc.compute_neighbor_aux(parent, nbrs + i * D, rp, c);
+        std::memcpy(codes + i * (D / 8), c.signs, D / 8);
+        aux[3 * i + 0] = a.nop; aux[3 * i + 1] = a.ip_qo; aux[3 * i + 2] = a.ip_cp;
+    }
+    return 0;
+}
+
+template <size_t D, size_t B>
+int neighbor_aux_nbit_t(uint32_t dim, uint64_t n, const float* parent, const float* nbrs, uint8_t* codes, float* aux) {
+    NbitRaBitQEncoder<D, B> enc(dim, constants::kDefaultRotationSeed);
+    alignas(32) float rp[D];
+    enc.rotate_raw_vector(parent, rp);
+    for (uint64_t i = 0; i < n; ++i) {
+        auto r = enc.compute_neighbor_aux_nbit(parent, nbrs + i * D, rp);
+        for (size_t b = 0; b < B; ++b) std::memcpy(codes + (i * B + b) * (D / 8), r.code.planes[b], D / 8);   // planes, MSB first
+        aux[3 * i + 0] = r.aux.nop; aux[3 * i + 1] = r.aux.ip_qo; aux[3 * i + 2] = r.aux.ip_cp;
+    }
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -163,6 +195,19 @@ float refshim_l2(uint32_t D, const float* a, const float* b) {
 #undef X
     }
     return -1.0f;
+}
+
+// codes: [n][B][D/8] bytes (bit i of a plane = bit i%8 of byte i/8; planes MSB first; B = 1: the sign bits);
+// aux: [n][3] = nop, ip_qo, ip_cp.  D < 64 is not offered (the code storage is then a partial word).
+int refshim_neighbor_aux(uint32_t D, uint32_t B, uint32_t dim, uint64_t n, const float* parent, const float* nbrs,
+                         uint8_t* codes, float* aux) {
+#define X(DD) if (D == DD && DD >= 64) { \
+        if (B == 1) return neighbor_aux_1bit_t<DD>(dim, n, parent, nbrs, codes, aux); \
+        if (B == 2) return neighbor_aux_nbit_t<DD, 2>(dim, n, parent, nbrs, codes, aux); \
+        if (B == 4) return neighbor_aux_nbit_t<DD, 4>(dim, n, parent, nbrs, codes, aux); }
+    FOR_EACH_D(X)
+#undef X
+    return -1;
 }
 
 }  // extern "C"
