@@ -191,6 +191,144 @@ void cpo_neighbor_aux_1bit(uint32_t dim, uint32_t D, const float* signs, const f
 }
 
 /* ======================================================================================
+ * BUILD side, N-bit: NbitRaBitQEncoder<D,B>::compute_neighbor_aux_nbit (encoder/rabitq_encoder.hpp:287-323) and the
+ * coordinate-descent quantiser caq_quantize (:371-467).  All of it is scalar code whose `a*b + c` the compiler may or
+ * may not fuse; `flags` says which (bit set = fused), one bit per expression, so that the combination the compiled
+ * reference uses can be found by search (tests/test_oracle_build_side.py) and then pinned:
+ *   bit 0  u = (int)((x - min) * inv_delta + 0.5f)          bit 1  dot_co   += c * x        (initial pass)
+ *   bit 2  norm_c_sq += c * c                                bit 3  dot_without  = dot_co - old_c * x
+ *   bit 4  norm_without = norm_c_sq - old_c * old_c          bit 5  new_dot  = dot_without + c * x   (trial and update)
+ *   bit 6  new_norm = norm_without + c * c                   bit 7  ip_qo += c * x           (final pass)
+ *   bit 8  ip_cp += c * rotated_parent                       bit 9  nop_sq += d * d
+ * Pinned (CPO_CAQ_FLAGS = 0x1F9) against oracle/_ref on random (parent, neighbour) pairs, dims 64..960, B = 2, 4:
+ *   decided by the search (any other value differs from the reference on some pair, B = 4): bits 1, 2, 9 unfused (the
+ *   initial pass and the residual norm were vectorised: separate multiply, scalar reduction), bits 3, 5, 7, 8 fused;
+ *   NOT decided by it (either value gave the reference's bits on all 1.6M pairs tried): bits 0, 4, 6 -- set to fused, which
+ *   is what the same compiler did to the same-shaped expression next to each (bit 0: the query quantiser's
+ *   (int)fma(x - vl, inv_delta, 0.5f), cpo_encode_query; bits 4, 6: the sibling of bits 3, 5 in the same statement pair).
+ * codes: B planes of D/8 bytes, MSB first (NbitCodeStorage::set_value, core/codes.hpp:107-116).
+ * ==================================================================================== */
+static inline float caq_madd(int fused, float a, float b, float c) { return fused ? fmaf(a, b, c) : a * b + c; }
+static inline float caq_msub(int fused, float c, float a, float b) { return fused ? fmaf(-a, b, c) : c - a * b; }
+
+static float caq_quantize(uint32_t D, uint32_t B, const float* x, const float* rp, uint32_t flags, uint8_t* planes,
+                          float inv_sqrt_d, float* out_ip_cp) {
+    const int K_INT = (1 << B) - 1;
+    const float K = (float)K_INT;
+    const float Df = (float)D;
+    float mn = x[0], mx = x[0];
+    for (uint32_t i = 1; i < D; ++i) {
+        if (x[i] < mn) mn = x[i];
+        if (x[i] > mx) mx = x[i];
+    }
+    float delta = (mx - mn) / K;
+    if (delta < 1e-10f / Df) delta = 1e-10f / Df;   /* constants::coordinate_epsilon(D) */
+    const float inv_delta = 1.0f / delta;
+    int* u = (int*)malloc(sizeof(int) * D);
+    float dot_co = 0.0f, norm_c_sq = 0.0f;
+    for (uint32_t i = 0; i < D; ++i) {
+        const float t = caq_madd(flags & 1u, x[i] - mn, inv_delta, 0.5f);
+        int v = (int)t;
+        if (v < 0) v = 0;
+        if (v > K_INT) v = K_INT;
+        u[i] = v;
+        const float c = (2.0f * (float)v - K) / K;
+        dot_co = caq_madd(flags & 2u, c, x[i], dot_co);
+        norm_c_sq = caq_madd(flags & 4u, c, c, norm_c_sq);
+    }
+    float prev_cos_sq = 0.0f;
+    for (int iter = 0; iter < 10; ++iter) {
+        int changed = 0;
+        for (uint32_t i = 0; i < D; ++i) {
+            const int old_u = u[i];
+            const float old_c = (2.0f * (float)old_u - K) / K;
+            const float dot_without = caq_msub(flags & 8u, dot_co, old_c, x[i]);
+            const float norm_without = caq_msub(flags & 16u, norm_c_sq, old_c, old_c);
+            int best_u = old_u;
+            float best_dot = dot_co, best_norm = norm_c_sq;
+            if (B >= 4) {
+                for (int s = -1; s <= 1; s += 2) {
+                    const int ut = old_u + s;
+                    if (ut < 0 || ut > K_INT) continue;
+                    const float c = (2.0f * (float)ut - K) / K;
+                    const float nd = caq_madd(flags & 32u, c, x[i], dot_without);
+                    const float nn = caq_madd(flags & 64u, c, c, norm_without);
+                    if (nd * nd * best_norm > best_dot * best_dot * nn) { best_u = ut; best_dot = nd; best_norm = nn; }
+                }
+            } else {
+                for (int ut = 0; ut <= K_INT; ++ut) {
+                    if (ut == old_u) continue;
+                    const float c = (2.0f * (float)ut - K) / K;
+                    const float nd = caq_madd(flags & 32u, c, x[i], dot_without);
+                    const float nn = caq_madd(flags & 64u, c, c, norm_without);
+                    if (nd * nd * best_norm > best_dot * best_dot * nn) { best_u = ut; best_dot = nd; best_norm = nn; }
+                }
+            }
+            if (best_u != old_u) {
+                const float nc = (2.0f * (float)best_u - K) / K;
+                dot_co = caq_madd(flags & 32u, nc, x[i], dot_without);
+                norm_c_sq = caq_madd(flags & 64u, nc, nc, norm_without);
+                u[i] = best_u;
+                changed = 1;
+            }
+        }
+        if (!changed) break;
+        const float cos_sq = norm_c_sq > 0.0f ? (dot_co * dot_co / norm_c_sq) : 0.0f;
+        if (iter > 0 && (cos_sq - prev_cos_sq) < 1e-4f) break;   /* constants::kCaqEarlyExitTol */
+        prev_cos_sq = cos_sq;
+    }
+    float ip_qo = 0.0f, ip_cp = 0.0f;
+    memset(planes, 0, (size_t)B * (D / 8));
+    for (uint32_t i = 0; i < D; ++i) {
+        for (uint32_t b = 0; b < B; ++b)
+            if ((u[i] >> (B - 1 - b)) & 1) planes[b * (D / 8) + (i >> 3)] |= (uint8_t)(1u << (i & 7));
+        const float c = (2.0f * (float)u[i] - K) / K;
+        ip_qo = caq_madd(flags & 128u, c, x[i], ip_qo);
+        ip_cp = caq_madd(flags & 256u, c, rp[i], ip_cp);
+    }
+    free(u);
+    *out_ip_cp = ip_cp * inv_sqrt_d;
+    return ip_qo * inv_sqrt_d;
+}
+
+void cpo_neighbor_aux_nbit(uint32_t dim, uint32_t D, uint32_t B, const float* signs, const float* parent, const float* nb,
+                           uint32_t flags, uint8_t* planes, float aux[3]) {
+    float* diff = (float*)malloc(sizeof(float) * D);
+    float* rp = (float*)malloc(sizeof(float) * D);
+    const float Df = (float)D;
+    const float norm_factor = 1.0f / (Df * sqrtf(Df));
+    const float inv_sqrt_d = 1.0f / sqrtf(Df);
+    memset(planes, 0, (size_t)B * (D / 8));
+    memcpy(rp, parent, sizeof(float) * D);
+    for (uint32_t layer = 0; layer < 3; ++layer) {
+        for (uint32_t i = 0; i < D; ++i) rp[i] = rp[i] * signs[layer * D + i];
+        cpo_fht(rp, D);
+    }
+    for (uint32_t i = 0; i < D; ++i) rp[i] = rp[i] * norm_factor;
+    float nop_sq = 0.0f;
+    for (uint32_t i = 0; i < dim; ++i) {
+        diff[i] = nb[i] - parent[i];
+        nop_sq = caq_madd(flags & 512u, diff[i], diff[i], nop_sq);
+    }
+    for (uint32_t i = dim; i < D; ++i) diff[i] = 0.0f;
+    const float nop = sqrtf(nop_sq);
+    aux[0] = nop; aux[1] = 0.0f; aux[2] = 0.0f;
+    if (nop < 1e-8f / Df) { free(diff); free(rp); return; }
+    const float inv_nop = 1.0f / nop;
+    for (uint32_t i = 0; i < D; ++i) diff[i] = diff[i] * inv_nop;
+    for (uint32_t layer = 0; layer < 3; ++layer) {
+        for (uint32_t i = 0; i < D; ++i) diff[i] = diff[i] * signs[layer * D + i];
+        cpo_fht(diff, D);
+    }
+    for (uint32_t i = 0; i < D; ++i) diff[i] = diff[i] * norm_factor;
+    float ip_cp = 0.0f;
+    aux[1] = caq_quantize(D, B, diff, rp, flags, planes, inv_sqrt_d, &ip_cp);
+    aux[2] = ip_cp;
+    free(diff);
+    free(rp);
+}
+
+/* ======================================================================================
  * FastScan integer sums: distance/fastscan_kernel.hpp:17-87 (one plane), :197-217 (N-bit),
  * :349-368 (top-two-planes "msb2").  Layout distance/fastscan_layout.hpp:10-49:
  * packed[sp][v] = (nibble(seg 2sp+1) << 4) | nibble(seg 2sp).  The AVX2 u8/u16 staging can

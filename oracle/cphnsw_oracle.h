@@ -31,6 +31,10 @@ void cpo_encode_query(uint32_t dim, uint32_t D, const float* signs, const float*
 /* BUILD side (oracle groundwork): RaBitQEncoder<D>::compute_neighbor_aux (encoder/rabitq_encoder.hpp:138-181) */
 void cpo_neighbor_aux_1bit(uint32_t dim, uint32_t D, const float* signs, const float* parent, const float* nb,
                            int fused, uint8_t* code, float aux[3]);
+/* NbitRaBitQEncoder<D,B>::compute_neighbor_aux_nbit + caq_quantize (:287-323, :371-467); flags: see cphnsw_oracle.c */
+#define CPO_CAQ_FLAGS 0x1F9u   /* the contraction pattern of the compiled reference; see cphnsw_oracle.c */
+void cpo_neighbor_aux_nbit(uint32_t dim, uint32_t D, uint32_t B, const float* signs, const float* parent, const float* nb,
+                           uint32_t flags, uint8_t* planes, float aux[3]);
 
 /* ---- FastScan ------------------------------------------------------------------------ */
 void cpo_fastscan_plane(uint32_t D, const uint8_t* lut, const uint8_t* packed /* [D/8][32] */,

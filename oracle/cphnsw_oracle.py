@@ -257,10 +257,13 @@ class Oracle:
         return out
 
     # ---- build side: neighbour codes relative to a parent (oracle groundwork) --------
-    def neighbor_aux(self, dim, B, parent, nbrs, ref=False, fused=0):
+    CAQ_FLAGS = 0x1F9          # CPO_CAQ_FLAGS (cphnsw_oracle.h): which a*b+c of the N-bit encoder the reference's compiler fused
+
+    def neighbor_aux(self, dim, B, parent, nbrs, ref=False, fused=None):
         """codes u8 [n, B, D/8] (planes MSB first; B = 1: sign bits) and aux f32 [n, 3] = nop, ip_qo, ip_cp of the
         neighbours `nbrs` [n, dim] of `parent` [dim].  ref=True: the unmodified reference through the shim
-        (compute_neighbor_aux / compute_neighbor_aux_nbit); else the C restatement (1-bit only so far)."""
+        (compute_neighbor_aux / compute_neighbor_aux_nbit); else the C restatement.  `fused` overrides the pinned
+        contraction pattern (B = 1: 0/1 for `nop_sq += d * d`; B > 1: the flag word of cpo_neighbor_aux_nbit)."""
         D = 1 << (dim - 1).bit_length()
         par = np.zeros(D, np.float32); par[:dim] = parent
         nb = np.zeros((len(nbrs), D), np.float32); nb[:, :dim] = nbrs
@@ -271,9 +274,14 @@ class Oracle:
                                                 _ptr(par, c_f32p), _ptr(nb, c_f32p), _ptr(codes, c_u8p), _ptr(aux, c_f32p))
             assert rc == 0, "the shim offers D >= 64, B in {1, 2, 4}"
         else:
-            assert B == 1, "the restatement covers the 1-bit encoder so far"
             signs = self.rotation_signs(D)
+            if fused is None:
+                fused = 0 if B == 1 else self.CAQ_FLAGS
             for i in range(len(nbrs)):
+                if B > 1:
+                    self.lib.cpo_neighbor_aux_nbit(C.c_uint32(dim), C.c_uint32(D), C.c_uint32(B), _ptr(signs, c_f32p), _ptr(par, c_f32p),
+                                                   _ptr(nb[i], c_f32p), C.c_uint32(fused), _ptr(codes[i], c_u8p), _ptr(aux[i], c_f32p))
+                    continue
                 self.lib.cpo_neighbor_aux_1bit(C.c_uint32(dim), C.c_uint32(D), _ptr(signs, c_f32p), _ptr(par, c_f32p), _ptr(nb[i], c_f32p),
                                                C.c_int(fused), _ptr(codes[i, 0], c_u8p), _ptr(aux[i], c_f32p))
         return codes, aux

@@ -1,6 +1,6 @@
 """Build-side oracle groundwork: the neighbour-code encoder of prune_and_write
 (graph/graph_refinement.hpp:46-67 -> RaBitQEncoder::compute_neighbor_aux, encoder/rabitq_encoder.hpp:138-181).
-No CUDA counterpart exists yet; this pins the C restatement of the 1-bit encoder against the unmodified reference
+No CUDA counterpart exists yet; this pins the C restatements of the 1-bit and N-bit (CAQ) encoders against the unmodified reference
 (live where oracle/_ref exists, and through a committed fixture written by it) so the kernel can be built against it."""
 import numpy as np
 import pytest
@@ -41,8 +41,37 @@ def test_neighbor_aux_1bit_against_the_committed_fixture(oracle):
 
 
 @needs_ref
+@pytest.mark.parametrize("B", [2, 4])
+@pytest.mark.parametrize("dim", [64, 96, 128, 300, 960])
+def test_neighbor_aux_nbit_restatement_equals_the_reference(oracle, dim, B):
+    parent, nbrs = _cases(dim, 200 if dim < 900 else 60, dim + B)
+    rc, ra = oracle.neighbor_aux(dim, B, parent, nbrs, ref=True)
+    oc, oa = oracle.neighbor_aux(dim, B, parent, nbrs)
+    assert np.array_equal(rc, oc)
+    assert np.array_equal(ra.view(np.uint32), oa.view(np.uint32))
+
+
+@needs_ref
+def test_nbit_contraction_bits_the_search_decides(oracle):
+    """Flipping any of the decided bits (1, 2, 3, 5, 7, 8, 9; cphnsw_oracle.c) moves some output off the reference's."""
+    parent, nbrs = _cases(128, 3000, 77)
+    rc, ra = oracle.neighbor_aux(128, 4, parent, nbrs, ref=True)
+    for bit in (1, 2, 3, 5, 7, 8, 9):
+        uc, ua = oracle.neighbor_aux(128, 4, parent, nbrs, fused=oracle.CAQ_FLAGS ^ (1 << bit))
+        assert not (np.array_equal(rc, uc) and np.array_equal(ra.view(np.uint32), ua.view(np.uint32))), bit
+
+
+@pytest.mark.parametrize("B", [2, 4])
+def test_neighbor_aux_nbit_against_the_committed_fixture(oracle, B):
+    g = np.load(common.GOLDEN / "nbaux_golden.npz")
+    for dim in (96, 128):
+        oc, oa = oracle.neighbor_aux(dim, B, g[f"parent_{dim}"], g[f"nbrs_{dim}"])
+        assert np.array_equal(oc, g[f"codes_{dim}_b{B}"])
+        assert np.array_equal(oa.view(np.uint32), g[f"aux_{dim}_b{B}"].view(np.uint32))
+
+
+@needs_ref
 def test_fixture_is_what_the_reference_writes(oracle):
-    """The committed fixture also carries the reference's 2- and 4-bit codes (CAQ quantiser) for the next round."""
     g = np.load(common.GOLDEN / "nbaux_golden.npz")
     for dim in (96, 128):
         for B in (1, 2, 4):
