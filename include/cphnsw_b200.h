@@ -165,6 +165,22 @@ int cphnsw_b200_unique_topk(cphnsw_b200_index* ix, const int64_t* d_ids_in, cons
                             uint64_t nq, uint64_t k_in, uint64_t k_out, const uint32_t* d_id_map,
                             uint64_t map_size, int64_t* d_ids_out, float* d_dists_out, void* stream);
 
+/* ---- build side: neighbour codes relative to a parent vertex ------------------ */
+/* What prune_and_write (graph/graph_refinement.hpp:46-67) stores for each selected neighbour of a
+ * vertex: RaBitQEncoder<D>::compute_neighbor_aux (encoder/rabitq_encoder.hpp:138-181) for bits == 1,
+ * NbitRaBitQEncoder<D,B>::compute_neighbor_aux_nbit (:287-323, quantiser caq_quantize :371-467) for
+ * bits 2, 4 -- bit for bit.  The handle supplies the device and the error string; it need not hold
+ * an index (the build side runs before one exists).  rotation_seed: the encoder's (42 in
+ * api/hnsw_index.hpp).  d_vectors: n_vectors rows of row_stride floats, the first dim of each the
+ * vector.  d_parent_ids [n_parents] (NULL = 0, 1, 2, ...) and d_nbr_ids [n_parents][32]: row ids;
+ * an id >= n_vectors (0xFFFFFFFF) is an empty slot and yields zeros.  Outputs, D = next_pow2(dim)
+ * (at least 16): d_codes u8 [n_parents][32][bits][D/8], planes MSB first, bit i%8 of byte i/8 =
+ * dimension i (core/codes.hpp:107-116); d_aux f32 [n_parents][32][3] = nop, ip_qo, ip_cp. */
+int cphnsw_b200_neighbor_codes(cphnsw_b200_index* ix, uint32_t dim, uint32_t bits, uint64_t rotation_seed,
+                               const float* d_vectors, uint64_t row_stride, uint64_t n_vectors,
+                               const uint32_t* d_parent_ids, const uint32_t* d_nbr_ids, uint64_t n_parents,
+                               uint8_t* d_codes, float* d_aux, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

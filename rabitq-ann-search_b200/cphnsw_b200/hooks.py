@@ -110,6 +110,28 @@ def exhaustive_search(ix, queries: torch.Tensor, k: int, kprime: int, id_begin: 
     return ids, dists
 
 
+def neighbor_codes(ix, vectors: torch.Tensor, nbr_ids: torch.Tensor, parent_ids: torch.Tensor | None = None,
+                   rotation_seed: int = 42):
+    """N3 (build side).  vectors f32 [n, dim], nbr_ids i32 [n_parents, 32] (-1 = empty slot), parent_ids i32 [n_parents]
+    (None = 0, 1, ...) -> (codes u8 [n_parents, 32, bits, D/8], aux f32 [n_parents, 32, 3] = nop, ip_qo, ip_cp) for the
+    dim and bits `ix` was created with.  The index needs no data on the device."""
+    dev = _dev(ix)
+    dim, bits = ix.dim, ix._bits
+    D = max(16, 1 << (dim - 1).bit_length())
+    v = vectors.to(dev, torch.float32).contiguous()
+    assert v.dim() == 2 and v.shape[1] == dim
+    nb = nbr_ids.to(dev, torch.int32).contiguous()
+    assert nb.dim() == 2 and nb.shape[1] == 32
+    pid = None if parent_ids is None else parent_ids.to(dev, torch.int32).contiguous()
+    assert pid is None or pid.numel() == nb.shape[0]
+    codes = torch.empty((nb.shape[0], 32, bits, D // 8), dtype=torch.uint8, device=dev)
+    aux = torch.empty((nb.shape[0], 32, 3), dtype=torch.float32, device=dev)
+    _capi.check(ix.handle, ix._lib.cphnsw_b200_neighbor_codes(
+        ix.handle, dim, bits, rotation_seed, v.data_ptr(), v.shape[1], v.shape[0], _ptr(pid), nb.data_ptr(), nb.shape[0],
+        codes.data_ptr(), aux.data_ptr(), _stream(ix)))
+    return codes, aux
+
+
 def upload_arrays(ix, *, D, bits, dim, search_data, raw, norm_sq, calibration, centroid=None, max_level=0,
                   entry_point=0, graph_entry_point=0, rotation_seed=42, layers=()):
     """cphnsw_b200_upload from numpy arrays laid out like the reference's in-memory index.

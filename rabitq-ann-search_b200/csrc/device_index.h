@@ -117,6 +117,9 @@ struct cphnsw_b200_index {
     size_t h_stage_bytes = 0;
     cpb::Stats* d_stats = nullptr;
     uint32_t* d_counters = nullptr;  // [0] work counter, [1] overflow count
+    float* enc_signs = nullptr;      // rotation sign diagonals of the build-side encoder (neighbor_codes), [3][enc_signs_D]
+    uint32_t enc_signs_D = 0;
+    uint64_t enc_signs_seed = 0;
     cphnsw_b200_stats last_stats{};
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[6] = {};  // prep begin/end, search begin/end, re-run begin/end

@@ -102,4 +102,22 @@ cudaError_t launch_exhaustive_scan_tc(const DevIndex& ix, const ExhaustiveArgs& 
 cudaError_t launch_unique_topk(const int64_t* ids_in, const float* dists_in, uint64_t nq, uint32_t kin, uint32_t kout,
                                const uint32_t* id_map, uint64_t map_size, int64_t* ids_out, float* dists_out, cudaStream_t stream);
 
+// ---- N3 build side: neighbour codes relative to a parent vertex (neighbor_codes.cu) ---------------------
+struct NeighborCodesArgs {
+    uint32_t D, dim;
+    const float* signs;          // [3][D] rotation sign diagonals
+    const float* vectors;        // [n_vectors] rows of row_stride floats (the first dim are the vector)
+    uint64_t row_stride, n_vectors;
+    const uint32_t* parent_ids;  // [n_parents]; NULL = 0, 1, 2, ...
+    const uint32_t* nbr_ids;     // [n_parents][32]; ids >= n_vectors (kInvalid) are empty slots
+    uint64_t n_parents;
+    uint8_t* codes;              // [n_parents][32][B][D/8]
+    float* aux;                  // [n_parents][32][3] nop, ip_qo, ip_cp
+    // filled in by the launcher
+    uint32_t rows, warp_floats;
+    float norm_factor, inv_sqrt_d, norm_eps, coord_eps;
+};
+cudaError_t neighbor_codes_plan(NeighborCodesArgs& a, uint32_t B, uint32_t* warps, size_t* smem_bytes);
+cudaError_t launch_neighbor_codes(NeighborCodesArgs a, uint32_t B, cudaStream_t stream);
+
 }  // namespace cpb

@@ -1,0 +1,311 @@
+// N3 -- build side: the codes of a vertex's neighbours relative to the vertex ("parent"), i.e. what
+// prune_and_write stores in a neighbour block (graph/graph_refinement.hpp:46-67):
+//   1-bit  RaBitQEncoder<D>::compute_neighbor_aux          (encoder/rabitq_encoder.hpp:138-181)
+//   N-bit  NbitRaBitQEncoder<D,B>::compute_neighbor_aux_nbit (:287-323) with the coordinate-descent quantiser
+//          caq_quantize (:371-467)
+// both over rotate_raw_vector (:81-86) = the 3-layer sign/Hadamard rotation of K1.
+//
+// One warp per parent vertex, one LANE per neighbour: everything after the rotation is a strictly sequential
+// float recurrence per (parent, neighbour) pair in the reference (running sums over the D coordinates; the
+// coordinate descent updates two running sums coordinate by coordinate), so the parallelism is across pairs.
+// Each lane owns one row of a [rows][D+1] shared-memory tile (the +1 makes "same coordinate, 32 rows" hit 32
+// banks); all lanes walk the coordinates in step, so the sign diagonals, the rotated parent and the value table
+// are broadcast reads.  Where the compiled reference fused a multiply-add and where it did not was found by
+// search against it; every operation below is an explicit _rn intrinsic.
+//
+// The kernel uses no PTX and only warp-level primitives, so tests/native/ also compiles this file for the host
+// (CPB_HOST_EMULATION: one thread per lane, barriers for the warp primitives) and checks it on the CPU.
+#include "kernels.h"
+
+namespace cpb {
+
+namespace {
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+// unnormalised Walsh-Hadamard transform of one row by one thread; butterfly convention of K1
+__device__ __forceinline__ void fht_row(float* x, uint32_t D) {
+    for (uint32_t h = 1; h < D; h <<= 1) {
+        for (uint32_t p = 0; p < D / 2; ++p) {
+            const uint32_t i = ((p & ~(h - 1)) << 1) | (p & (h - 1));
+            const float a = x[i], b = x[i + h];
+            x[i] = __fadd_rn(a, b);
+            x[i + h] = (h < 8) ? __fsub_rn(b, a) : __fsub_rn(a, b);
+        }
+    }
+}
+
+template <int B>
+__global__ void __launch_bounds__(256)
+neighbor_codes_kernel(NeighborCodesArgs a) {
+    extern __shared__ float smem[];
+    constexpr int K_INT = (1 << B) - 1;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t D = a.D, dim = a.dim, rows = a.rows;
+    const uint32_t xs = D + 1;                       // row stride of the tile, floats
+    const uint32_t us = D + 4;                       // row stride of the value tile, bytes (a multiple of 4, odd in words)
+    float* ctab = smem;                              // the 2^B reconstruction values (2u - K) / K
+    float* wbase = smem + 16 + (size_t)warp * a.warp_floats;
+    float* praw = wbase;                             // the parent, zero-padded
+    float* rp = wbase + D;                           // rotated and scaled parent
+    float* x = wbase + 2 * D;                        // [rows][D+1]
+    uint8_t* u8 = reinterpret_cast<uint8_t*>(x + (size_t)rows * xs);   // [rows][D+4]  (B > 1)
+
+    if (threadIdx.x <= (unsigned)K_INT)
+        ctab[threadIdx.x] = __fdiv_rn(__fsub_rn(__fmul_rn(2.0f, (float)threadIdx.x), (float)K_INT), (float)K_INT);
+    __syncthreads();
+
+    const uint64_t p = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (p >= a.n_parents) return;
+    const uint32_t pid = a.parent_ids ? a.parent_ids[p] : (uint32_t)p;
+    const bool parent_ok = pid < a.n_vectors;
+
+    // the parent: raw copy for the offsets, and rotate_raw_vector(parent) for ip_cp
+    {
+        const float* src = a.vectors + (size_t)(parent_ok ? pid : 0) * a.row_stride;
+        for (uint32_t i = lane; i < D; i += 32) {
+            const float v = (parent_ok && i < dim) ? src[i] : 0.0f;
+            praw[i] = v;
+            rp[i] = v;
+        }
+        __syncwarp();
+        for (int layer = 0; layer < 3; ++layer) {
+            const float* sg = a.signs + (size_t)layer * D;
+            for (uint32_t i = lane; i < D; i += 32) rp[i] = __fmul_rn(rp[i], sg[i]);
+            __syncwarp();
+            for (uint32_t h = 1; h < D; h <<= 1) {
+                for (uint32_t q = lane; q < D / 2; q += 32) {
+                    const uint32_t i = ((q & ~(h - 1)) << 1) | (q & (h - 1));
+                    const float va = rp[i], vb = rp[i + h];
+                    rp[i] = __fadd_rn(va, vb);
+                    rp[i + h] = (h < 8) ? __fsub_rn(vb, va) : __fsub_rn(va, vb);
+                }
+                __syncwarp();
+            }
+        }
+        for (uint32_t i = lane; i < D; i += 32) rp[i] = __fmul_rn(rp[i], a.norm_factor);
+        __syncwarp();
+    }
+
+    const uint32_t code_bytes = B * (D / 8);
+    for (uint32_t v0 = 0; v0 < kR; v0 += rows) {
+        // offsets nb - parent of `rows` neighbours, written cooperatively (coalesced reads)
+        const uint32_t my_slot = v0 + lane;
+        const uint32_t my_nid = (lane < rows && parent_ok) ? a.nbr_ids[p * kR + my_slot] : kInvalid;
+        const bool valid = my_nid < a.n_vectors;     // kInvalid marks an empty slot (fastscan_layout.hpp:51-92)
+        for (uint32_t r = 0; r < rows; ++r) {
+            const uint32_t nid = __shfl_sync(kFull, my_nid, r);
+            if (nid >= a.n_vectors) continue;
+            const float* src = a.vectors + (size_t)nid * a.row_stride;
+            float* xr = x + (size_t)r * xs;
+            for (uint32_t i = lane; i < D; i += 32) xr[i] = i < dim ? __fsub_rn(src[i], praw[i]) : 0.0f;
+        }
+        __syncwarp();
+
+        float* xr = x + (size_t)lane * xs;
+        uint8_t* ur = u8 + (size_t)lane * us;
+        float nop = 0.0f, ip_qo = 0.0f, ip_cp = 0.0f;
+        bool live = false;
+        if (valid) {
+            float nop_sq = 0.0f;                     // nop_sq += d * d: multiply, then add (not fused)
+            for (uint32_t i = 0; i < dim; ++i) { const float d = xr[i]; nop_sq = __fadd_rn(nop_sq, __fmul_rn(d, d)); }
+            nop = __fsqrt_rn(nop_sq);
+            live = !(nop < a.norm_eps);
+        }
+        if (live) {
+            const float inv_nop = __fdiv_rn(1.0f, nop);
+            for (uint32_t i = 0; i < D; ++i) xr[i] = __fmul_rn(xr[i], inv_nop);
+            for (int layer = 0; layer < 3; ++layer) {
+                const float* sg = a.signs + (size_t)layer * D;
+                for (uint32_t i = 0; i < D; ++i) xr[i] = __fmul_rn(xr[i], sg[i]);
+                fht_row(xr, D);
+            }
+        }
+
+        uint8_t* out_code = a.codes + ((size_t)p * kR + my_slot) * code_bytes;
+        if (B == 1) {
+            // sign bits, |rotated|_1 and the signed sum of the rotated parent, coordinate by coordinate
+            float l1 = 0.0f, ip = 0.0f;
+            if (lane < rows) {
+                for (uint32_t j = 0; j < D / 8; ++j) {
+                    uint32_t byte = 0;
+                    if (live) {
+#pragma unroll
+                        for (uint32_t t = 0; t < 8; ++t) {
+                            const uint32_t i = 8 * j + t;
+                            const float r = __fmul_rn(xr[i], a.norm_factor);
+                            const bool bit = r >= 0.0f;
+                            byte |= (bit ? 1u : 0u) << t;
+                            l1 = __fadd_rn(l1, fabsf(r));
+                            ip = bit ? __fadd_rn(ip, rp[i]) : __fsub_rn(ip, rp[i]);
+                        }
+                    }
+                    out_code[j] = (uint8_t)byte;
+                }
+                ip_qo = __fmul_rn(l1, a.inv_sqrt_d);
+                ip_cp = __fmul_rn(ip, a.inv_sqrt_d);
+            }
+        } else {
+            if (live) {
+                const float K = (float)K_INT;
+                float mn, mx;
+                {
+                    const float v = __fmul_rn(xr[0], a.norm_factor);
+                    xr[0] = v; mn = v; mx = v;
+                }
+                for (uint32_t i = 1; i < D; ++i) {
+                    const float v = __fmul_rn(xr[i], a.norm_factor);
+                    xr[i] = v;
+                    if (v < mn) mn = v;
+                    if (v > mx) mx = v;
+                }
+                float delta = __fdiv_rn(__fsub_rn(mx, mn), K);
+                if (delta < a.coord_eps) delta = a.coord_eps;
+                const float inv_delta = __fdiv_rn(1.0f, delta);
+                // initial rounding; dot_co and norm_c_sq start as plain multiply-then-add sums
+                float dot_co = 0.0f, norm_c_sq = 0.0f;
+                for (uint32_t i = 0; i < D; ++i) {
+                    const float xi = xr[i];
+                    int u = __float2int_rz(__fmaf_rn(__fsub_rn(xi, mn), inv_delta, 0.5f));
+                    u = u < 0 ? 0 : (u > K_INT ? K_INT : u);
+                    ur[i] = (uint8_t)u;
+                    const float c = ctab[u];
+                    dot_co = __fadd_rn(__fmul_rn(c, xi), dot_co);
+                    norm_c_sq = __fadd_rn(__fmul_rn(c, c), norm_c_sq);
+                }
+                // coordinate descent on cos^2(x, c) = dot_co^2 / norm_c_sq: at most 10 sweeps (rabitq_encoder.hpp:400-455)
+                float prev_cos_sq = 0.0f;
+                for (int iter = 0; iter < 10; ++iter) {
+                    bool changed = false;
+                    for (uint32_t i = 0; i < D; ++i) {
+                        const int old_u = ur[i];
+                        const float xi = xr[i];
+                        const float old_c = ctab[old_u];
+                        const float dot_without = __fmaf_rn(-old_c, xi, dot_co);
+                        const float norm_without = __fmaf_rn(-old_c, old_c, norm_c_sq);
+                        int best_u = old_u;
+                        float best_dot = dot_co, best_norm = norm_c_sq;
+                        if (B >= 4) {                // neighbours of the current value only
+#pragma unroll
+                            for (int s = -1; s <= 1; s += 2) {
+                                const int ut = old_u + s;
+                                if (ut < 0 || ut > K_INT) continue;
+                                const float c = ctab[ut];
+                                const float nd = __fmaf_rn(c, xi, dot_without), nn = __fmaf_rn(c, c, norm_without);
+                                if (__fmul_rn(__fmul_rn(nd, nd), best_norm) > __fmul_rn(__fmul_rn(best_dot, best_dot), nn)) {
+                                    best_u = ut; best_dot = nd; best_norm = nn;
+                                }
+                            }
+                        } else {                     // every other value
+#pragma unroll
+                            for (int ut = 0; ut <= K_INT; ++ut) {
+                                if (ut == old_u) continue;
+                                const float c = ctab[ut];
+                                const float nd = __fmaf_rn(c, xi, dot_without), nn = __fmaf_rn(c, c, norm_without);
+                                if (__fmul_rn(__fmul_rn(nd, nd), best_norm) > __fmul_rn(__fmul_rn(best_dot, best_dot), nn)) {
+                                    best_u = ut; best_dot = nd; best_norm = nn;
+                                }
+                            }
+                        }
+                        if (best_u != old_u) {       // the accepted trial's sums are the new running sums
+                            dot_co = best_dot;
+                            norm_c_sq = best_norm;
+                            ur[i] = (uint8_t)best_u;
+                            changed = true;
+                        }
+                    }
+                    if (!changed) break;
+                    const float cos_sq = norm_c_sq > 0.0f ? __fdiv_rn(__fmul_rn(dot_co, dot_co), norm_c_sq) : 0.0f;
+                    if (iter > 0 && __fsub_rn(cos_sq, prev_cos_sq) < 1e-4f) break;   // constants::kCaqEarlyExitTol
+                    prev_cos_sq = cos_sq;
+                }
+            }
+            // bit planes, MSB first (NbitCodeStorage::set_value, core/codes.hpp:107-116), and the two inner products
+            if (lane < rows) {
+                float sq = 0.0f, sc = 0.0f;
+                for (uint32_t j = 0; j < D / 8; ++j) {
+                    uint32_t bytes[B];
+#pragma unroll
+                    for (int b = 0; b < B; ++b) bytes[b] = 0;
+                    if (live) {
+#pragma unroll
+                        for (uint32_t t = 0; t < 8; ++t) {
+                            const uint32_t i = 8 * j + t;
+                            const uint32_t u = ur[i];
+                            const float c = ctab[u];
+                            sq = __fmaf_rn(c, xr[i], sq);
+                            sc = __fmaf_rn(c, rp[i], sc);
+#pragma unroll
+                            for (int b = 0; b < B; ++b) bytes[b] |= ((u >> (B - 1 - b)) & 1u) << t;
+                        }
+                    }
+#pragma unroll
+                    for (int b = 0; b < B; ++b) out_code[(size_t)b * (D / 8) + j] = (uint8_t)bytes[b];
+                }
+                ip_qo = __fmul_rn(sq, a.inv_sqrt_d);
+                ip_cp = __fmul_rn(sc, a.inv_sqrt_d);
+            }
+        }
+        if (lane < rows) {
+            float* o = a.aux + ((size_t)p * kR + my_slot) * 3;
+            o[0] = nop;
+            o[1] = live ? ip_qo : 0.0f;
+            o[2] = live ? ip_cp : 0.0f;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+size_t neighbor_codes_warp_bytes(uint32_t D, uint32_t B, uint32_t rows) {
+    return sizeof(float) * (2 * (size_t)D + (size_t)rows * (D + 1)) + (B > 1 ? (size_t)rows * (D + 4) : 0);
+}
+
+// rows per pass, warps per CTA, dynamic shared memory and the encoder's constants for (a.D, B)
+cudaError_t neighbor_codes_plan(NeighborCodesArgs& a, uint32_t B, uint32_t* warps_out, size_t* smem_out) {
+    if (B != 1 && B != 2 && B != 4) return cudaErrorInvalidValue;
+    constexpr size_t kBudget = 200 * 1024;
+    uint32_t rows = kR;
+    while (rows > 1 && neighbor_codes_warp_bytes(a.D, B, rows) + 64 > kBudget) rows >>= 1;
+    size_t per_warp = (neighbor_codes_warp_bytes(a.D, B, rows) + 15) & ~(size_t)15;
+    if (per_warp + 64 > kBudget) return cudaErrorInvalidValue;
+    uint32_t warps = (uint32_t)((kBudget - 64) / per_warp);
+    warps = warps > 8 ? 8 : warps;
+    if ((uint64_t)warps > a.n_parents) warps = (uint32_t)a.n_parents;
+    a.rows = rows;
+    a.warp_floats = (uint32_t)(per_warp / sizeof(float));
+    const float Df = (float)a.D;
+    // constants of RaBitQEncoderBase's constructor (encoder/rabitq_encoder.hpp:37-39) and core/constants.hpp, host floats
+    a.norm_factor = 1.0f / (Df * sqrtf(Df));
+    a.inv_sqrt_d = 1.0f / sqrtf(Df);
+    a.norm_eps = 1e-8f / Df;
+    a.coord_eps = 1e-10f / Df;
+    *warps_out = warps;
+    *smem_out = 64 + (size_t)warps * per_warp;
+    return cudaSuccess;
+}
+
+#ifndef CPB_HOST_EMULATION
+cudaError_t launch_neighbor_codes(NeighborCodesArgs a, uint32_t B, cudaStream_t stream) {
+    if (a.n_parents == 0) return cudaSuccess;
+    uint32_t warps = 0;
+    size_t smem = 0;
+    cudaError_t pe = neighbor_codes_plan(a, B, &warps, &smem);
+    if (pe != cudaSuccess) return pe;
+    const unsigned grid = (unsigned)((a.n_parents + warps - 1) / warps);
+    auto go = [&](auto kernel) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<grid, warps * 32, smem, stream>>>(a);
+        return cudaGetLastError();
+    };
+    switch (B) {
+        case 1: return go(neighbor_codes_kernel<1>);
+        case 2: return go(neighbor_codes_kernel<2>);
+        default: return go(neighbor_codes_kernel<4>);
+    }
+}
+#endif
+
+}  // namespace cpb

@@ -208,3 +208,35 @@ def sorted_rows(ids, dists):
     """Rows as sorted (dist, id) pairs: the reference's tie order between equal distances is unspecified."""
     order = np.lexsort((ids, dists), axis=1)
     return np.take_along_axis(ids, order, 1), np.take_along_axis(dists, order, 1)
+
+
+# ---- N3 (build side): neighbour codes ------------------------------------------------------------
+def neighbor_code_case(dim, n_parents, seed, holes=True):
+    """vectors f32 [n, dim] (the second half are near-duplicates of the first: short offsets), parent ids u32
+    [n_parents], neighbour ids u32 [n_parents, 32] with empty slots (0xFFFFFFFF) and one neighbour equal to its
+    parent (nop == 0, the norm_epsilon branch)."""
+    rng = np.random.default_rng(seed)
+    n = n_parents * 8 + 40
+    vec = rng.standard_normal((n, dim)).astype(np.float32)
+    vec[n // 2:] = vec[:n - n // 2] + 0.05 * rng.standard_normal((n - n // 2, dim)).astype(np.float32)
+    pids = rng.choice(n, n_parents, replace=False).astype(np.uint32)
+    nbr = rng.integers(0, n, (n_parents, 32)).astype(np.uint32)
+    if holes:
+        nbr[rng.random((n_parents, 32)) < 0.15] = 0xFFFFFFFF
+        nbr[0, 3] = pids[0]
+    return vec, pids, nbr
+
+
+def expected_neighbor_codes(oracle, dim, bits, vec, pids, nbr, ref=False):
+    """What the oracle (ref=True: the compiled reference) writes for the case: codes u8 [np, 32, bits, D/8], aux f32 [np, 32, 3]."""
+    D = max(16, 1 << (dim - 1).bit_length())
+    codes = np.zeros((len(pids), 32, bits, D // 8), np.uint8)
+    aux = np.zeros((len(pids), 32, 3), np.float32)
+    for p in range(len(pids)):
+        ok = nbr[p] < len(vec)
+        nb = np.zeros((32, dim), np.float32)
+        nb[ok] = vec[nbr[p][ok]]
+        c, a = oracle.neighbor_aux(dim, bits, vec[pids[p]], nb, ref=ref)
+        codes[p][ok] = c[ok]
+        aux[p][ok] = a[ok]
+    return codes, aux

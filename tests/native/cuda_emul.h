@@ -1,0 +1,99 @@
+// Host emulation of the few CUDA device facilities a warp-synchronous kernel WITHOUT PTX needs, so that the
+// kernel's own source can be compiled by g++ and checked on a machine with no GPU (test infrastructure only).
+//
+// One std::thread per CUDA thread of ONE block at a time.  threadIdx / blockIdx / blockDim are thread_local;
+// __syncwarp / __shfl_sync / __ballot_sync meet at a per-warp std::barrier, __syncthreads at a per-block one;
+// the *_rn intrinsics are the IEEE operations they name (compile with -ffp-contract=off so that g++ neither
+// fuses nor splits anything).  Dynamic shared memory is the array the including file defines under the name
+// the kernel declares (`extern __shared__ float smem[]` becomes a block-scope extern declaration).
+#pragma once
+#include <cuda_runtime.h>   // host side of the runtime headers: uint3/dim3, cudaError_t; __global__ etc. expand to nothing
+
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#ifndef __launch_bounds__
+#define __launch_bounds__(...)
+#endif
+
+namespace cuda_emul {
+struct Warp {
+    std::barrier<> bar{32};
+    uint32_t slot[32];
+};
+struct Block {
+    std::unique_ptr<std::barrier<>> bar;
+    std::vector<std::unique_ptr<Warp>> warps;
+};
+inline thread_local Warp* t_warp = nullptr;
+inline thread_local Block* t_block = nullptr;
+}  // namespace cuda_emul
+
+inline thread_local uint3 threadIdx, blockIdx;
+inline thread_local dim3 blockDim, gridDim;
+
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+inline float __fsqrt_rn(float a) { return std::sqrt(a); }
+inline int __float2int_rz(float a) { return (int)a; }
+
+inline void __syncwarp(unsigned = 0xFFFFFFFFu) { cuda_emul::t_warp->bar.arrive_and_wait(); }
+inline void __syncthreads() { cuda_emul::t_block->bar->arrive_and_wait(); }
+
+template <typename T>
+inline T __shfl_sync(unsigned, T v, int src) {
+    static_assert(sizeof(T) == 4, "32-bit shuffles only");
+    cuda_emul::Warp* w = cuda_emul::t_warp;
+    std::memcpy(&w->slot[threadIdx.x & 31], &v, 4);
+    w->bar.arrive_and_wait();
+    T r;
+    std::memcpy(&r, &w->slot[src & 31], 4);
+    w->bar.arrive_and_wait();
+    return r;
+}
+
+inline unsigned __ballot_sync(unsigned, int pred) {
+    cuda_emul::Warp* w = cuda_emul::t_warp;
+    w->slot[threadIdx.x & 31] = pred ? 1u : 0u;
+    w->bar.arrive_and_wait();
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l) m |= w->slot[l] << l;
+    w->bar.arrive_and_wait();
+    return m;
+}
+
+namespace cuda_emul {
+
+// Runs kernel(args) for every block of the grid, one block after the other.  `smem`/`smem_floats`: the shared-memory
+// array, re-filled with signalling garbage (NaNs) before each block so that a read of unwritten memory shows.
+template <typename Kernel, typename Args>
+void launch(Kernel kernel, unsigned grid, unsigned block, float* smem, size_t smem_floats, const Args& args) {
+    for (unsigned b = 0; b < grid; ++b) {
+        std::memset(smem, 0xFF, smem_floats * sizeof(float));
+        Block blk;
+        blk.bar = std::make_unique<std::barrier<>>(block);
+        for (unsigned w = 0; w < (block + 31) / 32; ++w) blk.warps.push_back(std::make_unique<Warp>());
+        std::vector<std::thread> threads;
+        for (unsigned t = 0; t < block; ++t)
+            threads.emplace_back([&, t] {
+                threadIdx = uint3{t, 0, 0};
+                blockIdx = uint3{b, 0, 0};
+                blockDim = dim3(block, 1, 1);
+                gridDim = dim3(grid, 1, 1);
+                t_block = &blk;
+                t_warp = blk.warps[t / 32].get();
+                kernel(args);
+            });
+        for (auto& th : threads) th.join();
+    }
+}
+
+}  // namespace cuda_emul
