@@ -175,11 +175,18 @@ int cphnsw_b200_unique_topk(cphnsw_b200_index* ix, const int64_t* d_ids_in, cons
  * vector.  d_parent_ids [n_parents] (NULL = 0, 1, 2, ...) and d_nbr_ids [n_parents][32]: row ids;
  * an id >= n_vectors (0xFFFFFFFF) is an empty slot and yields zeros.  Outputs, D = next_pow2(dim)
  * (at least 16): d_codes u8 [n_parents][32][bits][D/8], planes MSB first, bit i%8 of byte i/8 =
- * dimension i (core/codes.hpp:107-116); d_aux f32 [n_parents][32][3] = nop, ip_qo, ip_cp. */
+ * dimension i (core/codes.hpp:107-116); d_aux f32 [n_parents][32][3] = nop, ip_qo, ip_cp; d_blocks:
+ * one FastScanNeighborBlock / NbitFastScanNeighborBlock per parent in the reference's own layout
+ * (distance/fastscan_layout.hpp:51-92, 114-155: packed planes, nop, ip_qo, ip_cp, popcounts,
+ * [weighted_popcounts,] neighbor_ids, count = one past the last occupied slot), block_stride bytes
+ * apart (>= the struct's size, a multiple of 4; bytes past `count` + 4 are left alone) -- i.e.
+ * what nb.set_neighbor wrote, ready to be copied into search_data_[id].neighbors.  Any of the three
+ * outputs may be NULL. */
 int cphnsw_b200_neighbor_codes(cphnsw_b200_index* ix, uint32_t dim, uint32_t bits, uint64_t rotation_seed,
                                const float* d_vectors, uint64_t row_stride, uint64_t n_vectors,
                                const uint32_t* d_parent_ids, const uint32_t* d_nbr_ids, uint64_t n_parents,
-                               uint8_t* d_codes, float* d_aux, void* stream);
+                               uint8_t* d_codes, float* d_aux, uint8_t* d_blocks, uint64_t block_stride,
+                               void* stream);
 
 #ifdef __cplusplus
 }

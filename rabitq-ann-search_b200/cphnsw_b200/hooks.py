@@ -110,11 +110,17 @@ def exhaustive_search(ix, queries: torch.Tensor, k: int, kprime: int, id_begin: 
     return ids, dists
 
 
+def neighbor_block_bytes(D: int, bits: int) -> int:
+    """sizeof(FastScanNeighborBlock<D>) / sizeof(NbitFastScanNeighborBlock<D, 32, bits>)."""
+    return -(-(4 * D * bits + 384 + 64 * (2 if bits > 1 else 1) + 128 + 4) // 64) * 64
+
+
 def neighbor_codes(ix, vectors: torch.Tensor, nbr_ids: torch.Tensor, parent_ids: torch.Tensor | None = None,
-                   rotation_seed: int = 42):
+                   rotation_seed: int = 42, blocks: bool = False):
     """N3 (build side).  vectors f32 [n, dim], nbr_ids i32 [n_parents, 32] (-1 = empty slot), parent_ids i32 [n_parents]
     (None = 0, 1, ...) -> (codes u8 [n_parents, 32, bits, D/8], aux f32 [n_parents, 32, 3] = nop, ip_qo, ip_cp) for the
-    dim and bits `ix` was created with.  The index needs no data on the device."""
+    dim and bits `ix` was created with; blocks=True: also the neighbour blocks in the reference's layout, u8
+    [n_parents, neighbor_block_bytes(D, bits)] (zero-filled first).  The index needs no data on the device."""
     dev = _dev(ix)
     dim, bits = ix.dim, ix._bits
     D = max(16, 1 << (dim - 1).bit_length())
@@ -126,10 +132,11 @@ def neighbor_codes(ix, vectors: torch.Tensor, nbr_ids: torch.Tensor, parent_ids:
     assert pid is None or pid.numel() == nb.shape[0]
     codes = torch.empty((nb.shape[0], 32, bits, D // 8), dtype=torch.uint8, device=dev)
     aux = torch.empty((nb.shape[0], 32, 3), dtype=torch.float32, device=dev)
+    blk = torch.zeros((nb.shape[0], neighbor_block_bytes(D, bits)), dtype=torch.uint8, device=dev) if blocks else None
     _capi.check(ix.handle, ix._lib.cphnsw_b200_neighbor_codes(
         ix.handle, dim, bits, rotation_seed, v.data_ptr(), v.shape[1], v.shape[0], _ptr(pid), nb.data_ptr(), nb.shape[0],
-        codes.data_ptr(), aux.data_ptr(), _stream(ix)))
-    return codes, aux
+        codes.data_ptr(), aux.data_ptr(), _ptr(blk), 0 if blk is None else blk.shape[1], _stream(ix)))
+    return (codes, aux, blk) if blocks else (codes, aux)
 
 
 def upload_arrays(ix, *, D, bits, dim, search_data, raw, norm_sq, calibration, centroid=None, max_level=0,

@@ -734,17 +734,20 @@ int cphnsw_b200_unique_topk(cphnsw_b200_index* ix, const int64_t* d_ids_in, cons
 int cphnsw_b200_neighbor_codes(cphnsw_b200_index* ix, uint32_t dim, uint32_t bits, uint64_t rotation_seed,
                                const float* d_vectors, uint64_t row_stride, uint64_t n_vectors,
                                const uint32_t* d_parent_ids, const uint32_t* d_nbr_ids, uint64_t n_parents,
-                               uint8_t* d_codes, float* d_aux, void* stream) {
+                               uint8_t* d_codes, float* d_aux, uint8_t* d_blocks, uint64_t block_stride, void* stream) {
     if (!ix) return CPHNSW_B200_EINVAL;
     // the checks of the reference's factory (src/bindings.cpp:77-113)
     if (dim == 0 || dim > 2048) return fail(ix, CPHNSW_B200_EINVAL, "dim must be in [1, 2048]");
     if (bits != 1 && bits != 2 && bits != 4) return fail(ix, CPHNSW_B200_EINVAL, "bits must be 1, 2 or 4");
     if (n_parents == 0) return 0;
-    if (!d_vectors || !d_nbr_ids || !d_codes || !d_aux) return fail(ix, CPHNSW_B200_EINVAL, "null buffer");
+    if (!d_vectors || !d_nbr_ids || (!d_codes && !d_aux && !d_blocks)) return fail(ix, CPHNSW_B200_EINVAL, "null buffer");
     if (row_stride < dim) return fail(ix, CPHNSW_B200_EINVAL, "row_stride is smaller than dim");
     if (n_vectors >= kInvalid || n_parents > 0x7FFFFFFFull * 8) return fail(ix, CPHNSW_B200_EINVAL, "argument too large");
     CUDA_TRY(ix, cudaSetDevice(ix->device));
     const uint32_t D = next_pow2(dim) < 16 ? 16 : next_pow2(dim);
+    if (d_blocks && (block_stride < nb_bytes(D, bits) || block_stride % 4 != 0 || reinterpret_cast<uintptr_t>(d_blocks) % 4 != 0))
+        return fail(ix, CPHNSW_B200_EINVAL, "block_stride must be a multiple of 4 and at least the block size (" +
+                                                std::to_string(nb_bytes(D, bits)) + " bytes), d_blocks 4-byte aligned");
     if (!ix->enc_signs || ix->enc_signs_D != D || ix->enc_signs_seed != rotation_seed) {
         if (ix->enc_signs) { cudaFree(ix->enc_signs); ix->enc_signs = nullptr; }
         const std::vector<float> signs = rotation_signs(D, rotation_seed);
@@ -758,7 +761,7 @@ int cphnsw_b200_neighbor_codes(cphnsw_b200_index* ix, uint32_t dim, uint32_t bit
     a.D = D; a.dim = dim; a.signs = ix->enc_signs;
     a.vectors = d_vectors; a.row_stride = row_stride; a.n_vectors = n_vectors;
     a.parent_ids = d_parent_ids; a.nbr_ids = d_nbr_ids; a.n_parents = n_parents;
-    a.codes = d_codes; a.aux = d_aux;
+    a.codes = d_codes; a.aux = d_aux; a.blocks = d_blocks; a.block_stride = block_stride;
     CUDA_TRY(ix, launch_neighbor_codes(a, bits, static_cast<cudaStream_t>(stream)));
     return 0;
 }

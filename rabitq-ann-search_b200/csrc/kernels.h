@@ -111,10 +111,13 @@ struct NeighborCodesArgs {
     const uint32_t* parent_ids;  // [n_parents]; NULL = 0, 1, 2, ...
     const uint32_t* nbr_ids;     // [n_parents][32]; ids >= n_vectors (kInvalid) are empty slots
     uint64_t n_parents;
-    uint8_t* codes;              // [n_parents][32][B][D/8]
-    float* aux;                  // [n_parents][32][3] nop, ip_qo, ip_cp
+    uint8_t* codes;              // [n_parents][32][B][D/8]; may be NULL
+    float* aux;                  // [n_parents][32][3] nop, ip_qo, ip_cp; may be NULL
+    uint8_t* blocks;             // [n_parents] neighbour blocks in the reference's layout, block_stride apart; may be NULL
+    uint64_t block_stride;
     // filled in by the launcher
     uint32_t rows, warp_floats;
+    uint32_t nop_off, ids_off;   // field offsets inside a block
     float norm_factor, inv_sqrt_d, norm_eps, coord_eps;
 };
 cudaError_t neighbor_codes_plan(NeighborCodesArgs& a, uint32_t B, uint32_t* warps, size_t* smem_bytes);

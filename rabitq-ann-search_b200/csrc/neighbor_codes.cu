@@ -88,6 +88,7 @@ neighbor_codes_kernel(NeighborCodesArgs a) {
     }
 
     const uint32_t code_bytes = B * (D / 8);
+    uint32_t count = 0;   // one past the last occupied slot
     for (uint32_t v0 = 0; v0 < kR; v0 += rows) {
         // offsets nb - parent of `rows` neighbours, written cooperatively (coalesced reads)
         const uint32_t my_slot = v0 + lane;
@@ -122,7 +123,11 @@ neighbor_codes_kernel(NeighborCodesArgs a) {
             }
         }
 
-        uint8_t* out_code = a.codes + ((size_t)p * kR + my_slot) * code_bytes;
+        uint8_t* out_code = a.codes ? a.codes + ((size_t)p * kR + my_slot) * code_bytes : nullptr;
+        // the reference's own block: plane b is packed[sp][slot] = the code byte of dimensions 8sp..8sp+7
+        // (FastScanCodeBlock::store, distance/fastscan_layout.hpp:10-49), so the 32 lanes write 32 consecutive bytes
+        uint8_t* blk = a.blocks ? a.blocks + (size_t)p * a.block_stride : nullptr;
+        uint32_t pop = 0, wpop = 0;
         if (B == 1) {
             // sign bits, |rotated|_1 and the signed sum of the rotated parent, coordinate by coordinate
             float l1 = 0.0f, ip = 0.0f;
@@ -140,7 +145,9 @@ neighbor_codes_kernel(NeighborCodesArgs a) {
                             ip = bit ? __fadd_rn(ip, rp[i]) : __fsub_rn(ip, rp[i]);
                         }
                     }
-                    out_code[j] = (uint8_t)byte;
+                    pop += __popc(byte);
+                    if (out_code) out_code[j] = (uint8_t)byte;
+                    if (blk) blk[(size_t)j * kR + my_slot] = (uint8_t)byte;
                 }
                 ip_qo = __fmul_rn(l1, a.inv_sqrt_d);
                 ip_cp = __fmul_rn(ip, a.inv_sqrt_d);
@@ -235,25 +242,42 @@ neighbor_codes_kernel(NeighborCodesArgs a) {
                             const float c = ctab[u];
                             sq = __fmaf_rn(c, xr[i], sq);
                             sc = __fmaf_rn(c, rp[i], sc);
+                            wpop += u;
 #pragma unroll
                             for (int b = 0; b < B; ++b) bytes[b] |= ((u >> (B - 1 - b)) & 1u) << t;
                         }
                     }
+                    pop += __popc(bytes[0]);
 #pragma unroll
-                    for (int b = 0; b < B; ++b) out_code[(size_t)b * (D / 8) + j] = (uint8_t)bytes[b];
+                    for (int b = 0; b < B; ++b) {
+                        if (out_code) out_code[(size_t)b * (D / 8) + j] = (uint8_t)bytes[b];
+                        if (blk) blk[(size_t)b * 4 * D + (size_t)j * kR + my_slot] = (uint8_t)bytes[b];
+                    }
                 }
                 ip_qo = __fmul_rn(sq, a.inv_sqrt_d);
                 ip_cp = __fmul_rn(sc, a.inv_sqrt_d);
             }
         }
         if (lane < rows) {
-            float* o = a.aux + ((size_t)p * kR + my_slot) * 3;
-            o[0] = nop;
-            o[1] = live ? ip_qo : 0.0f;
-            o[2] = live ? ip_cp : 0.0f;
+            if (!live) { ip_qo = 0.0f; ip_cp = 0.0f; }
+            if (a.aux) {
+                float* o = a.aux + ((size_t)p * kR + my_slot) * 3;
+                o[0] = nop; o[1] = ip_qo; o[2] = ip_cp;
+            }
+            if (blk) {   // set_neighbor (fastscan_layout.hpp:73-87, 134-150)
+                reinterpret_cast<float*>(blk + a.nop_off)[my_slot] = nop;
+                reinterpret_cast<float*>(blk + a.nop_off + 128)[my_slot] = ip_qo;
+                reinterpret_cast<float*>(blk + a.nop_off + 256)[my_slot] = ip_cp;
+                reinterpret_cast<uint16_t*>(blk + a.nop_off + 384)[my_slot] = (uint16_t)pop;
+                if (B > 1) reinterpret_cast<uint16_t*>(blk + a.nop_off + 448)[my_slot] = (uint16_t)wpop;
+                reinterpret_cast<uint32_t*>(blk + a.ids_off)[my_slot] = valid ? my_nid : kInvalid;
+            }
         }
+        const unsigned vm = __ballot_sync(kFull, valid);
+        if (vm) count = v0 + 32 - __clz(vm);
         __syncwarp();
     }
+    if (lane == 0 && a.blocks) *reinterpret_cast<uint32_t*>(a.blocks + (size_t)p * a.block_stride + a.ids_off + 128) = count;
 }
 
 }  // namespace
@@ -280,6 +304,9 @@ cudaError_t neighbor_codes_plan(NeighborCodesArgs& a, uint32_t B, uint32_t* warp
     a.norm_factor = 1.0f / (Df * sqrtf(Df));
     a.inv_sqrt_d = 1.0f / sqrtf(Df);
     a.norm_eps = 1e-8f / Df;
+    // FastScanNeighborBlock / NbitFastScanNeighborBlock (fastscan_layout.hpp:51-92, 114-155)
+    a.nop_off = 4 * a.D * B;
+    a.ids_off = a.nop_off + 384 + 64 * (B > 1 ? 2 : 1);
     a.coord_eps = 1e-10f / Df;
     *warps_out = warps;
     *smem_out = 64 + (size_t)warps * per_warp;

@@ -240,3 +240,26 @@ def expected_neighbor_codes(oracle, dim, bits, vec, pids, nbr, ref=False):
         codes[p][ok] = c[ok]
         aux[p][ok] = a[ok]
     return codes, aux
+
+
+def blocks_from_codes(dim, bits, codes, aux, nbr, n_vectors):
+    """The reference's neighbour blocks (fastscan_layout.hpp:51-92, 114-155) holding `codes`/`aux` of one call: packed
+    planes (byte sp of slot v at [plane][sp][v]), nop, ip_qo, ip_cp, popcounts, weighted popcounts, ids, count."""
+    D = max(16, 1 << (dim - 1).bit_length())
+    lay = co.nb_layout(D, bits)
+    out = np.zeros((len(nbr), lay["size"]), np.uint8)
+    pc = np.unpackbits(codes, axis=3).sum(3).astype(np.uint32)          # [np, 32, bits]
+    for p in range(len(nbr)):
+        out[p, :4 * D * bits] = np.transpose(codes[p], (1, 2, 0)).reshape(-1)
+        for k, name in enumerate(("nop", "ip_qo", "ip_cp")):
+            out[p, lay[name]:lay[name] + 128] = np.ascontiguousarray(aux[p, :, k]).view(np.uint8)
+        out[p, lay["pop"]:lay["pop"] + 64] = pc[p, :, 0].astype(np.uint16).view(np.uint8)
+        if bits > 1:
+            w = sum(pc[p, :, b] << (bits - 1 - b) for b in range(bits))
+            out[p, lay["wpop"]:lay["wpop"] + 64] = w.astype(np.uint16).view(np.uint8)
+        ok = nbr[p] < n_vectors
+        ids = np.where(ok, nbr[p], 0xFFFFFFFF).astype(np.uint32)
+        out[p, lay["ids"]:lay["ids"] + 128] = ids.view(np.uint8)
+        cnt = int(np.nonzero(ok)[0].max()) + 1 if ok.any() else 0
+        out[p, lay["count"]:lay["count"] + 4] = np.array([cnt], np.uint32).view(np.uint8)
+    return out

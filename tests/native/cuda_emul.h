@@ -44,6 +44,8 @@ inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 inline float __fsqrt_rn(float a) { return std::sqrt(a); }
 inline int __float2int_rz(float a) { return (int)a; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 
 inline void __syncwarp(unsigned = 0xFFFFFFFFu) { cuda_emul::t_warp->bar.arrive_and_wait(); }
 inline void __syncthreads() { cuda_emul::t_block->bar->arrive_and_wait(); }

@@ -10,12 +10,14 @@ namespace cpb { namespace { alignas(16) float smem[64 * 1024]; } }   // 256 KB: 
 
 extern "C" int emul_neighbor_codes(uint32_t dim, uint32_t bits, const float* signs, const float* vectors, uint64_t row_stride,
                                    uint64_t n_vectors, const uint32_t* parent_ids, const uint32_t* nbr_ids, uint64_t n_parents,
-                                   uint8_t* codes, float* aux, uint32_t max_warps, uint32_t* rows_used) {
+                                   uint8_t* codes, float* aux, uint8_t* blocks, uint64_t block_stride, uint32_t max_warps,
+                                   uint32_t* rows_used) {
     cpb::NeighborCodesArgs a{};
     uint32_t D = 16;
     while (D < dim) D <<= 1;
     a.D = D; a.dim = dim; a.signs = signs; a.vectors = vectors; a.row_stride = row_stride; a.n_vectors = n_vectors;
     a.parent_ids = parent_ids; a.nbr_ids = nbr_ids; a.n_parents = n_parents; a.codes = codes; a.aux = aux;
+    a.blocks = blocks; a.block_stride = block_stride;
     uint32_t warps = 0;
     size_t smem_bytes = 0;
     if (cpb::neighbor_codes_plan(a, bits, &warps, &smem_bytes) != cudaSuccess) return 1;

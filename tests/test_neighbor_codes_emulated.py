@@ -28,7 +28,7 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
-def _run(emul, oracle, dim, bits, vec, pids, nbr, max_warps=0, stride=None):
+def _run(emul, oracle, dim, bits, vec, pids, nbr, max_warps=0, stride=None, want_blocks=False):
     D = max(16, 1 << (dim - 1).bit_length())
     stride = stride or dim
     rows = np.zeros((len(vec), stride), np.float32)
@@ -37,12 +37,16 @@ def _run(emul, oracle, dim, bits, vec, pids, nbr, max_warps=0, stride=None):
     signs = oracle.rotation_signs(D)
     codes = np.full((len(nbr), 32, bits, D // 8), 0xAA, np.uint8)
     aux = np.full((len(nbr), 32, 3), np.nan, np.float32)
+    bsize = co.nb_layout(D, bits)["size"]
+    blocks = np.full((len(nbr), bsize), 0xCC, np.uint8) if want_blocks else None
     used = C.c_uint32(0)
     rc = emul.emul_neighbor_codes(C.c_uint32(dim), C.c_uint32(bits), _p(signs, C.c_float), _p(rows, C.c_float), C.c_uint64(stride),
                                   C.c_uint64(len(vec)), None if pids is None else _p(pids, C.c_uint32), _p(nbr, C.c_uint32),
-                                  C.c_uint64(len(nbr)), _p(codes, C.c_uint8), _p(aux, C.c_float), C.c_uint32(max_warps), C.byref(used))
+                                  C.c_uint64(len(nbr)), _p(codes, C.c_uint8), _p(aux, C.c_float),
+                                  None if blocks is None else _p(blocks, C.c_uint8), C.c_uint64(bsize), C.c_uint32(max_warps),
+                                  C.byref(used))
     assert rc == 0
-    return codes, aux, used.value
+    return (codes, aux, used.value, blocks) if want_blocks else (codes, aux, used.value)
 
 
 @pytest.mark.parametrize("bits", [1, 2, 4])
@@ -84,3 +88,42 @@ def test_emulated_kernel_equals_the_compiled_reference(emul, oracle, bits):
     want_c, want_a = common.expected_neighbor_codes(oracle, 128, bits, vec, pids, nbr, ref=True)
     codes, aux, _ = _run(emul, oracle, 128, bits, vec, pids, nbr)
     assert np.array_equal(codes, want_c) and np.array_equal(aux.view(np.uint32), want_a.view(np.uint32))
+
+
+@pytest.mark.parametrize("bits", [1, 2, 4])
+@pytest.mark.parametrize("dim", [20, 128, 1500])
+def test_emulated_block_output_is_the_codes_in_the_reference_layout(emul, oracle, dim, bits):
+    vec, pids, nbr = common.neighbor_code_case(dim, 3, 9 * dim + bits)
+    nbr[1, 20:] = 0xFFFFFFFF                            # a short list: count = one past the last occupied slot
+    nbr[1, 19] = 5
+    codes, aux, _, blocks = _run(emul, oracle, dim, bits, vec, pids, nbr, want_blocks=True)
+    want = common.blocks_from_codes(dim, bits, codes, aux, nbr, len(vec))
+    lay = co.nb_layout(max(16, 1 << (dim - 1).bit_length()), bits)
+    assert np.array_equal(blocks[:, :lay["count"] + 4], want[:, :lay["count"] + 4])
+    assert (blocks[:, lay["count"] + 4:] == 0xCC).all()   # the struct's tail padding is left alone
+    assert blocks[1, lay["count"]:lay["count"] + 4].view(np.uint32)[0] == 20
+
+
+@pytest.mark.parametrize("bits", [1, 2, 4])
+def test_emulated_kernel_regenerates_the_blocks_of_a_reference_built_index(emul, oracle, bits):
+    """Every neighbour block of a real index (built and saved by the unmodified reference), from nothing but its raw
+    vectors and neighbour ids: what prune_and_write stored, bit for bit, up to each block's count."""
+    sf = co.SaveFile(common.GOLDEN / f"ref_n300_d24_b{bits}.bin")
+    ids, cnt = sf.field("ids").copy(), sf.field("count")
+    for p in range(sf.n):
+        ids[p, cnt[p]:] = 0xFFFFFFFF                    # slots past count hold leftovers of earlier refinement rounds
+    vec = np.ascontiguousarray(sf.raw[:, :sf.dim])
+    _, _, _, blocks = _run(emul, oracle, sf.dim, bits, vec, None, ids, want_blocks=True)
+    lay, nb = sf.lay, sf.nb_off
+    ref = sf.search_data[:, nb:]
+    for p in range(sf.n):
+        c = int(cnt[p])
+        got_pl = blocks[p, :4 * sf.D * bits].reshape(bits, sf.D // 8, 32)
+        ref_pl = ref[p, :4 * sf.D * bits].reshape(bits, sf.D // 8, 32)
+        assert np.array_equal(got_pl[:, :, :c], ref_pl[:, :, :c]), p
+        for name, width in (("nop", 4), ("ip_qo", 4), ("ip_cp", 4), ("pop", 2), ("wpop", 2), ("ids", 4)):
+            if lay[name] is None:
+                continue
+            o = lay[name]
+            assert np.array_equal(blocks[p, o:o + width * c], ref[p, o:o + width * c]), (p, name)
+        assert blocks[p, lay["count"]:lay["count"] + 4].view(np.uint32)[0] == c
