@@ -177,6 +177,7 @@ void cphnsw_b200_destroy(cphnsw_b200_index* ix) {
     if (ix->d_stats) cudaFree(ix->d_stats);
     if (ix->d_counters) cudaFree(ix->d_counters);
     if (ix->enc_signs) cudaFree(ix->enc_signs);
+    if (ix->enc_scratch) cudaFree(ix->enc_scratch);
     if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
     for (auto& e : ix->ev) if (e) cudaEventDestroy(e);
     delete ix;
@@ -191,6 +192,7 @@ int cphnsw_b200_set_option(cphnsw_b200_index* ix, const char* name, int64_t valu
     else if (n == "ctas_per_sm") { if (value < 1 || value > 32) return fail(ix, CPHNSW_B200_EINVAL, "ctas_per_sm must be 1..32"); ix->ctas_per_sm = value; }
     else if (n == "collect_stats") ix->collect_stats = value ? 1 : 0;
     else if (n == "exhaustive_tensor_cores") ix->exhaustive_tensor_cores = value < 0 ? 0 : (value > 2 ? 2 : value);
+    else if (n == "neighbor_codes_tile") ix->neighbor_codes_tile = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (n == "beam_capacity") { if (value < 64) return fail(ix, CPHNSW_B200_EINVAL, "beam_capacity must be >= 64"); ix->beam_capacity = value; }
     else return fail(ix, CPHNSW_B200_EINVAL, "unknown option " + n);
     return 0;
@@ -762,7 +764,19 @@ int cphnsw_b200_neighbor_codes(cphnsw_b200_index* ix, uint32_t dim, uint32_t bit
     a.vectors = d_vectors; a.row_stride = row_stride; a.n_vectors = n_vectors;
     a.parent_ids = d_parent_ids; a.nbr_ids = d_nbr_ids; a.n_parents = n_parents;
     a.codes = d_codes; a.aux = d_aux; a.blocks = d_blocks; a.block_stride = block_stride;
-    CUDA_TRY(ix, launch_neighbor_codes(a, bits, static_cast<cudaStream_t>(stream)));
+    // per-warp tiles in a scratch buffer (L2) unless the option asks for shared memory: measured faster at every D
+    // (profiles/n3_gpu_check_r01.log), shared memory caps the warps per SM
+    const bool global_tile = ix->neighbor_codes_tile != 1;
+    NeighborCodesPlan plan{};
+    if (neighbor_codes_plan(a, bits, ix->num_sms, global_tile, &plan) != cudaSuccess)
+        return fail(ix, CPHNSW_B200_EINVAL, "no launch shape for this dimension");
+    if (plan.scratch_bytes) {
+        int rc = ensure_buffer(ix, &ix->enc_scratch, &ix->enc_scratch_bytes, plan.scratch_bytes, false);
+        if (rc) return rc;
+        a.tile_x = static_cast<float*>(ix->enc_scratch);
+        a.tile_u = reinterpret_cast<uint8_t*>(a.tile_x + (size_t)a.total_warps * D * 32);
+    }
+    CUDA_TRY(ix, launch_neighbor_codes(a, bits, plan, static_cast<cudaStream_t>(stream)));
     return 0;
 }
 

@@ -120,6 +120,9 @@ struct cphnsw_b200_index {
     float* enc_signs = nullptr;      // rotation sign diagonals of the build-side encoder (neighbor_codes), [3][enc_signs_D]
     uint32_t enc_signs_D = 0;
     uint64_t enc_signs_seed = 0;
+    void* enc_scratch = nullptr;     // global-tile mode of neighbor_codes
+    size_t enc_scratch_bytes = 0;
+    int64_t neighbor_codes_tile = 0; // option: where the per-warp tiles live: 1 = shared memory, else global memory / L2 (results identical)
     cphnsw_b200_stats last_stats{};
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[6] = {};  // prep begin/end, search begin/end, re-run begin/end

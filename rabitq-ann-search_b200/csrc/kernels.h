@@ -115,12 +115,16 @@ struct NeighborCodesArgs {
     float* aux;                  // [n_parents][32][3] nop, ip_qo, ip_cp; may be NULL
     uint8_t* blocks;             // [n_parents] neighbour blocks in the reference's layout, block_stride apart; may be NULL
     uint64_t block_stride;
-    // filled in by the launcher
-    uint32_t rows, warp_floats;
+    // filled in by neighbor_codes_plan
+    uint32_t rows, warp_floats, total_warps;
     uint32_t nop_off, ids_off;   // field offsets inside a block
     float norm_factor, inv_sqrt_d, norm_eps, coord_eps;
+    // global-tile mode (large D): per-warp tiles [D][32] f32 and [D][32] u8; NULL = tiles in shared memory
+    float* tile_x;
+    uint8_t* tile_u;
 };
-cudaError_t neighbor_codes_plan(NeighborCodesArgs& a, uint32_t B, uint32_t* warps, size_t* smem_bytes);
-cudaError_t launch_neighbor_codes(NeighborCodesArgs a, uint32_t B, cudaStream_t stream);
+struct NeighborCodesPlan { unsigned grid; uint32_t warps; size_t smem_bytes, scratch_bytes; };
+cudaError_t neighbor_codes_plan(NeighborCodesArgs& a, uint32_t B, int num_sms, bool global_tile, NeighborCodesPlan* plan);
+cudaError_t launch_neighbor_codes(const NeighborCodesArgs& a, uint32_t B, const NeighborCodesPlan& plan, cudaStream_t stream);
 
 }  // namespace cpb

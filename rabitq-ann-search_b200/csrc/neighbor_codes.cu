@@ -23,20 +23,58 @@ namespace {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
-// unnormalised Walsh-Hadamard transform of one row by one thread; butterfly convention of K1
-__device__ __forceinline__ void fht_row(float* x, uint32_t D) {
-    for (uint32_t h = 1; h < D; h <<= 1) {
-        for (uint32_t p = 0; p < D / 2; ++p) {
-            const uint32_t i = ((p & ~(h - 1)) << 1) | (p & (h - 1));
-            const float a = x[i], b = x[i + h];
-            x[i] = __fadd_rn(a, b);
-            x[i + h] = (h < 8) ? __fsub_rn(b, a) : __fsub_rn(a, b);
+// S butterfly stages (h = H, 2H, ..) of the unnormalised Walsh-Hadamard transform of one row, by one thread, on 2^S
+// elements H apart held in registers: one read and one write of the row per S stages.  Butterfly convention of the
+// reference's FHT as in K1: (a, b) -> (a + b, h < 8 ? b - a : a - b).  pre != NULL: the row is multiplied
+// by `scale` and then by the sign diagonal `pre` on the way in (the layer's diagonal; scale = 1/nop on the first layer).
+template <int S>
+__device__ __forceinline__ void fht_stages(float* x, uint32_t D, uint32_t cs, uint32_t H, const float* pre, bool scaled, float scale) {
+    constexpr uint32_t N = 1u << S;
+    for (uint32_t g = 0; g < D / N; ++g) {
+        const uint32_t base = ((g & ~(H - 1)) << S) | (g & (H - 1));   // bits log2(H) .. log2(H)+S-1 are zero
+        float v[N];
+#pragma unroll
+        for (uint32_t k = 0; k < N; ++k) {
+            const uint32_t i = base + k * H;
+            float t = x[i * cs];
+            if (pre) {
+                if (scaled) t = __fmul_rn(t, scale);
+                t = __fmul_rn(t, pre[i]);
+            }
+            v[k] = t;
         }
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const bool low = (H << s) < 8;
+#pragma unroll
+            for (uint32_t k = 0; k < N; ++k) {
+                if (k & (1u << s)) continue;
+                const float a = v[k], b = v[k | (1u << s)];
+                v[k] = __fadd_rn(a, b);
+                v[k | (1u << s)] = low ? __fsub_rn(b, a) : __fsub_rn(a, b);
+            }
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < N; ++k) x[(base + k * H) * cs] = v[k];
+    }
+}
+
+// one layer of the rotation on one row: (scale,) sign diagonal, transform
+__device__ __forceinline__ void rotate_row(float* x, uint32_t D, uint32_t cs, const float* sg, bool scaled, float scale) {
+    uint32_t H = 1;
+    const float* pre = sg;
+    while (H < D) {
+        const uint32_t left = D / H;     // 2^(stages left)
+        if (left >= 16) { fht_stages<4>(x, D, cs, H, pre, scaled, scale); H <<= 4; }
+        else if (left == 8) { fht_stages<3>(x, D, cs, H, pre, scaled, scale); H <<= 3; }
+        else if (left == 4) { fht_stages<2>(x, D, cs, H, pre, scaled, scale); H <<= 2; }
+        else { fht_stages<1>(x, D, cs, H, pre, scaled, scale); H <<= 1; }
+        pre = nullptr;
     }
 }
 
 template <int B>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 neighbor_codes_kernel(NeighborCodesArgs a) {
     extern __shared__ float smem[];
     constexpr int K_INT = (1 << B) - 1;
@@ -50,13 +88,19 @@ neighbor_codes_kernel(NeighborCodesArgs a) {
     float* rp = wbase + D;                           // rotated and scaled parent
     float* x = wbase + 2 * D;                        // [rows][D+1]
     uint8_t* u8 = reinterpret_cast<uint8_t*>(x + (size_t)rows * xs);   // [rows][D+4]  (B > 1)
+    // large D: the two tiles live in global memory instead (L2), as [coordinate][lane] -- one 128-byte line per
+    // coordinate and warp access -- so that shared memory no longer caps the pairs in flight per SM
+    const bool gtile = a.tile_x != nullptr;
+    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (gtile) { x = a.tile_x + (size_t)gw * D * 32; u8 = a.tile_u + (size_t)gw * D * 32; }
+    const uint32_t cs = gtile ? 32u : 1u;                              // between coordinates of one row (both tiles)
+    const uint32_t xrow = gtile ? 1u : xs, urow = gtile ? 1u : us;     // between rows
 
     if (threadIdx.x <= (unsigned)K_INT)
         ctab[threadIdx.x] = __fdiv_rn(__fsub_rn(__fmul_rn(2.0f, (float)threadIdx.x), (float)K_INT), (float)K_INT);
     __syncthreads();
 
-    const uint64_t p = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-    if (p >= a.n_parents) return;
+    for (uint64_t p = gw; p < a.n_parents; p += a.total_warps) {
     const uint32_t pid = a.parent_ids ? a.parent_ids[p] : (uint32_t)p;
     const bool parent_ok = pid < a.n_vectors;
 
@@ -98,29 +142,24 @@ neighbor_codes_kernel(NeighborCodesArgs a) {
             const uint32_t nid = __shfl_sync(kFull, my_nid, r);
             if (nid >= a.n_vectors) continue;
             const float* src = a.vectors + (size_t)nid * a.row_stride;
-            float* xr = x + (size_t)r * xs;
-            for (uint32_t i = lane; i < D; i += 32) xr[i] = i < dim ? __fsub_rn(src[i], praw[i]) : 0.0f;
+            float* xr = x + (size_t)r * xrow;
+            for (uint32_t i = lane; i < D; i += 32) xr[i * cs] = i < dim ? __fsub_rn(src[i], praw[i]) : 0.0f;
         }
         __syncwarp();
 
-        float* xr = x + (size_t)lane * xs;
-        uint8_t* ur = u8 + (size_t)lane * us;
+        float* xr = x + (size_t)lane * xrow;
+        uint8_t* ur = u8 + (size_t)lane * urow;
         float nop = 0.0f, ip_qo = 0.0f, ip_cp = 0.0f;
         bool live = false;
         if (valid) {
             float nop_sq = 0.0f;                     // nop_sq += d * d: multiply, then add (not fused)
-            for (uint32_t i = 0; i < dim; ++i) { const float d = xr[i]; nop_sq = __fadd_rn(nop_sq, __fmul_rn(d, d)); }
+            for (uint32_t i = 0; i < dim; ++i) { const float d = xr[i * cs]; nop_sq = __fadd_rn(nop_sq, __fmul_rn(d, d)); }
             nop = __fsqrt_rn(nop_sq);
             live = !(nop < a.norm_eps);
         }
         if (live) {
-            const float inv_nop = __fdiv_rn(1.0f, nop);
-            for (uint32_t i = 0; i < D; ++i) xr[i] = __fmul_rn(xr[i], inv_nop);
-            for (int layer = 0; layer < 3; ++layer) {
-                const float* sg = a.signs + (size_t)layer * D;
-                for (uint32_t i = 0; i < D; ++i) xr[i] = __fmul_rn(xr[i], sg[i]);
-                fht_row(xr, D);
-            }
+            const float inv_nop = __fdiv_rn(1.0f, nop);   // the unit offset (x * inv_nop), then three (diagonal, transform) layers
+            for (int layer = 0; layer < 3; ++layer) rotate_row(xr, D, cs, a.signs + (size_t)layer * D, layer == 0, inv_nop);
         }
 
         uint8_t* out_code = a.codes ? a.codes + ((size_t)p * kR + my_slot) * code_bytes : nullptr;
@@ -138,7 +177,7 @@ neighbor_codes_kernel(NeighborCodesArgs a) {
 #pragma unroll
                         for (uint32_t t = 0; t < 8; ++t) {
                             const uint32_t i = 8 * j + t;
-                            const float r = __fmul_rn(xr[i], a.norm_factor);
+                            const float r = __fmul_rn(xr[i * cs], a.norm_factor);
                             const bool bit = r >= 0.0f;
                             byte |= (bit ? 1u : 0u) << t;
                             l1 = __fadd_rn(l1, fabsf(r));
@@ -161,8 +200,8 @@ neighbor_codes_kernel(NeighborCodesArgs a) {
                     xr[0] = v; mn = v; mx = v;
                 }
                 for (uint32_t i = 1; i < D; ++i) {
-                    const float v = __fmul_rn(xr[i], a.norm_factor);
-                    xr[i] = v;
+                    const float v = __fmul_rn(xr[i * cs], a.norm_factor);
+                    xr[i * cs] = v;
                     if (v < mn) mn = v;
                     if (v > mx) mx = v;
                 }
@@ -172,10 +211,10 @@ neighbor_codes_kernel(NeighborCodesArgs a) {
                 // initial rounding; dot_co and norm_c_sq start as plain multiply-then-add sums
                 float dot_co = 0.0f, norm_c_sq = 0.0f;
                 for (uint32_t i = 0; i < D; ++i) {
-                    const float xi = xr[i];
+                    const float xi = xr[i * cs];
                     int u = __float2int_rz(__fmaf_rn(__fsub_rn(xi, mn), inv_delta, 0.5f));
                     u = u < 0 ? 0 : (u > K_INT ? K_INT : u);
-                    ur[i] = (uint8_t)u;
+                    ur[i * cs] = (uint8_t)u;
                     const float c = ctab[u];
                     dot_co = __fadd_rn(__fmul_rn(c, xi), dot_co);
                     norm_c_sq = __fadd_rn(__fmul_rn(c, c), norm_c_sq);
@@ -185,8 +224,8 @@ neighbor_codes_kernel(NeighborCodesArgs a) {
                 for (int iter = 0; iter < 10; ++iter) {
                     bool changed = false;
                     for (uint32_t i = 0; i < D; ++i) {
-                        const int old_u = ur[i];
-                        const float xi = xr[i];
+                        const int old_u = ur[i * cs];
+                        const float xi = xr[i * cs];
                         const float old_c = ctab[old_u];
                         const float dot_without = __fmaf_rn(-old_c, xi, dot_co);
                         const float norm_without = __fmaf_rn(-old_c, old_c, norm_c_sq);
@@ -217,7 +256,7 @@ neighbor_codes_kernel(NeighborCodesArgs a) {
                         if (best_u != old_u) {       // the accepted trial's sums are the new running sums
                             dot_co = best_dot;
                             norm_c_sq = best_norm;
-                            ur[i] = (uint8_t)best_u;
+                            ur[i * cs] = (uint8_t)best_u;
                             changed = true;
                         }
                     }
@@ -238,9 +277,9 @@ neighbor_codes_kernel(NeighborCodesArgs a) {
 #pragma unroll
                         for (uint32_t t = 0; t < 8; ++t) {
                             const uint32_t i = 8 * j + t;
-                            const uint32_t u = ur[i];
+                            const uint32_t u = ur[i * cs];
                             const float c = ctab[u];
-                            sq = __fmaf_rn(c, xr[i], sq);
+                            sq = __fmaf_rn(c, xr[i * cs], sq);
                             sc = __fmaf_rn(c, rp[i], sc);
                             wpop += u;
 #pragma unroll
@@ -278,6 +317,7 @@ neighbor_codes_kernel(NeighborCodesArgs a) {
         __syncwarp();
     }
     if (lane == 0 && a.blocks) *reinterpret_cast<uint32_t*>(a.blocks + (size_t)p * a.block_stride + a.ids_off + 128) = count;
+    }   // parents of this warp
 }
 
 }  // namespace
@@ -286,19 +326,40 @@ size_t neighbor_codes_warp_bytes(uint32_t D, uint32_t B, uint32_t rows) {
     return sizeof(float) * (2 * (size_t)D + (size_t)rows * (D + 1)) + (B > 1 ? (size_t)rows * (D + 4) : 0);
 }
 
-// rows per pass, warps per CTA, dynamic shared memory and the encoder's constants for (a.D, B)
-cudaError_t neighbor_codes_plan(NeighborCodesArgs& a, uint32_t B, uint32_t* warps_out, size_t* smem_out) {
+// Launch shape and the encoder's constants for (a.D, B).  global_tile: the per-warp tiles go to a scratch buffer of
+// plan->scratch_bytes (the caller allocates it and sets a.tile_x / a.tile_u = tile_x + total_warps * D * 32 floats)
+// and a bounded grid of warps loops over the parents; else they live in shared memory, one parent per warp.
+cudaError_t neighbor_codes_plan(NeighborCodesArgs& a, uint32_t B, int num_sms, bool global_tile, NeighborCodesPlan* plan) {
     if (B != 1 && B != 2 && B != 4) return cudaErrorInvalidValue;
     constexpr size_t kBudget = 200 * 1024;
-    uint32_t rows = kR;
-    while (rows > 1 && neighbor_codes_warp_bytes(a.D, B, rows) + 64 > kBudget) rows >>= 1;
-    size_t per_warp = (neighbor_codes_warp_bytes(a.D, B, rows) + 15) & ~(size_t)15;
-    if (per_warp + 64 > kBudget) return cudaErrorInvalidValue;
-    uint32_t warps = (uint32_t)((kBudget - 64) / per_warp);
-    warps = warps > 8 ? 8 : warps;
-    if ((uint64_t)warps > a.n_parents) warps = (uint32_t)a.n_parents;
+    uint32_t rows = kR, warps;
+    size_t per_warp;
+    if (global_tile) {
+        per_warp = sizeof(float) * 2 * (size_t)a.D;
+        warps = 8;
+        const size_t cta = 64 + warps * per_warp;
+        size_t per_sm = kBudget / cta;
+        per_sm = per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm);   // 80 registers x 256 threads: three CTAs per SM
+        const uint64_t want = (a.n_parents + warps - 1) / warps, cap = (uint64_t)num_sms * per_sm;
+        plan->grid = (unsigned)(want < cap ? want : cap);
+        plan->scratch_bytes = (size_t)plan->grid * warps * a.D * 32 * (sizeof(float) + 1);
+    } else {
+        while (rows > 1 && neighbor_codes_warp_bytes(a.D, B, rows) + 64 > kBudget) rows >>= 1;
+        per_warp = (neighbor_codes_warp_bytes(a.D, B, rows) + 15) & ~(size_t)15;
+        if (per_warp + 64 > kBudget) return cudaErrorInvalidValue;
+        warps = (uint32_t)((kBudget - 64) / per_warp);
+        warps = warps > 8 ? 8 : warps;
+        if ((uint64_t)warps > a.n_parents) warps = (uint32_t)a.n_parents;
+        plan->grid = (unsigned)((a.n_parents + warps - 1) / warps);
+        plan->scratch_bytes = 0;
+    }
+    plan->warps = warps;
+    plan->smem_bytes = 64 + (size_t)warps * per_warp;
     a.rows = rows;
     a.warp_floats = (uint32_t)(per_warp / sizeof(float));
+    a.total_warps = plan->grid * warps;
+    a.tile_x = nullptr;
+    a.tile_u = nullptr;
     const float Df = (float)a.D;
     // constants of RaBitQEncoderBase's constructor (encoder/rabitq_encoder.hpp:37-39) and core/constants.hpp, host floats
     a.norm_factor = 1.0f / (Df * sqrtf(Df));
@@ -308,23 +369,16 @@ cudaError_t neighbor_codes_plan(NeighborCodesArgs& a, uint32_t B, uint32_t* warp
     a.nop_off = 4 * a.D * B;
     a.ids_off = a.nop_off + 384 + 64 * (B > 1 ? 2 : 1);
     a.coord_eps = 1e-10f / Df;
-    *warps_out = warps;
-    *smem_out = 64 + (size_t)warps * per_warp;
     return cudaSuccess;
 }
 
 #ifndef CPB_HOST_EMULATION
-cudaError_t launch_neighbor_codes(NeighborCodesArgs a, uint32_t B, cudaStream_t stream) {
+cudaError_t launch_neighbor_codes(const NeighborCodesArgs& a, uint32_t B, const NeighborCodesPlan& plan, cudaStream_t stream) {
     if (a.n_parents == 0) return cudaSuccess;
-    uint32_t warps = 0;
-    size_t smem = 0;
-    cudaError_t pe = neighbor_codes_plan(a, B, &warps, &smem);
-    if (pe != cudaSuccess) return pe;
-    const unsigned grid = (unsigned)((a.n_parents + warps - 1) / warps);
     auto go = [&](auto kernel) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);
         if (e != cudaSuccess) return e;
-        kernel<<<grid, warps * 32, smem, stream>>>(a);
+        kernel<<<plan.grid, plan.warps * 32, plan.smem_bytes, stream>>>(a);
         return cudaGetLastError();
     };
     switch (B) {

@@ -18,17 +18,26 @@ extern "C" int emul_neighbor_codes(uint32_t dim, uint32_t bits, const float* sig
     a.D = D; a.dim = dim; a.signs = signs; a.vectors = vectors; a.row_stride = row_stride; a.n_vectors = n_vectors;
     a.parent_ids = parent_ids; a.nbr_ids = nbr_ids; a.n_parents = n_parents; a.codes = codes; a.aux = aux;
     a.blocks = blocks; a.block_stride = block_stride;
-    uint32_t warps = 0;
-    size_t smem_bytes = 0;
-    if (cpb::neighbor_codes_plan(a, bits, &warps, &smem_bytes) != cudaSuccess) return 1;
-    if (smem_bytes > sizeof(cpb::smem)) return 2;
-    if (max_warps && warps > max_warps) warps = max_warps;
+    cpb::NeighborCodesPlan plan{};
+    const bool global_tile = (max_warps >> 16) != 0;       // high half of max_warps: tiles in "global" memory
+    max_warps &= 0xFFFF;
+    if (cpb::neighbor_codes_plan(a, bits, /*num_sms=*/2, global_tile, &plan) != cudaSuccess) return 1;
+    if (plan.smem_bytes > sizeof(cpb::smem)) return 2;
+    if (max_warps && plan.warps > max_warps && !global_tile) {
+        plan.warps = max_warps;
+        plan.grid = (unsigned)((n_parents + max_warps - 1) / max_warps);
+        a.total_warps = plan.grid * plan.warps;
+    }
+    std::vector<uint8_t> scratch(plan.scratch_bytes + 16, 0xFF);
+    if (plan.scratch_bytes) {
+        a.tile_x = reinterpret_cast<float*>(scratch.data());
+        a.tile_u = reinterpret_cast<uint8_t*>(a.tile_x + (size_t)a.total_warps * D * 32);
+    }
     if (rows_used) *rows_used = a.rows;
-    const unsigned grid = (unsigned)((n_parents + warps - 1) / warps);
     switch (bits) {
-        case 1: cuda_emul::launch(cpb::neighbor_codes_kernel<1>, grid, warps * 32, cpb::smem, smem_bytes / 4, a); break;
-        case 2: cuda_emul::launch(cpb::neighbor_codes_kernel<2>, grid, warps * 32, cpb::smem, smem_bytes / 4, a); break;
-        default: cuda_emul::launch(cpb::neighbor_codes_kernel<4>, grid, warps * 32, cpb::smem, smem_bytes / 4, a); break;
+        case 1: cuda_emul::launch(cpb::neighbor_codes_kernel<1>, plan.grid, plan.warps * 32, cpb::smem, plan.smem_bytes / 4, a); break;
+        case 2: cuda_emul::launch(cpb::neighbor_codes_kernel<2>, plan.grid, plan.warps * 32, cpb::smem, plan.smem_bytes / 4, a); break;
+        default: cuda_emul::launch(cpb::neighbor_codes_kernel<4>, plan.grid, plan.warps * 32, cpb::smem, plan.smem_bytes / 4, a); break;
     }
     return 0;
 }

@@ -28,7 +28,7 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
-def _run(emul, oracle, dim, bits, vec, pids, nbr, max_warps=0, stride=None, want_blocks=False):
+def _run(emul, oracle, dim, bits, vec, pids, nbr, max_warps=0, stride=None, want_blocks=False, global_tile=False):
     D = max(16, 1 << (dim - 1).bit_length())
     stride = stride or dim
     rows = np.zeros((len(vec), stride), np.float32)
@@ -43,7 +43,7 @@ def _run(emul, oracle, dim, bits, vec, pids, nbr, max_warps=0, stride=None, want
     rc = emul.emul_neighbor_codes(C.c_uint32(dim), C.c_uint32(bits), _p(signs, C.c_float), _p(rows, C.c_float), C.c_uint64(stride),
                                   C.c_uint64(len(vec)), None if pids is None else _p(pids, C.c_uint32), _p(nbr, C.c_uint32),
                                   C.c_uint64(len(nbr)), _p(codes, C.c_uint8), _p(aux, C.c_float),
-                                  None if blocks is None else _p(blocks, C.c_uint8), C.c_uint64(bsize), C.c_uint32(max_warps),
+                                  None if blocks is None else _p(blocks, C.c_uint8), C.c_uint64(bsize), C.c_uint32(max_warps | (0x10000 if global_tile else 0)),
                                   C.byref(used))
     assert rc == 0
     return (codes, aux, used.value, blocks) if want_blocks else (codes, aux, used.value)
@@ -58,6 +58,20 @@ def test_emulated_kernel_equals_the_oracle(emul, oracle, dim, bits):
     assert rows == 32
     assert np.array_equal(codes, want_c)
     assert np.array_equal(aux.view(np.uint32), want_a.view(np.uint32))
+
+
+@pytest.mark.parametrize("bits", [1, 2, 4])
+@pytest.mark.parametrize("dim,npar", [(20, 40), (128, 37), (300, 18), (960, 3)])
+def test_emulated_kernel_with_tiles_in_global_memory(emul, oracle, dim, bits, npar):
+    """The large-D mode: [coordinate][lane] tiles in a scratch buffer, a bounded grid of warps looping over the parents
+    (the emulated device has 2 SMs, so every warp takes several parents here)."""
+    vec, pids, nbr = common.neighbor_code_case(dim, npar, 7 * dim + bits)
+    want_c, want_a = common.expected_neighbor_codes(oracle, dim, bits, vec, pids, nbr)
+    codes, aux, _, blocks = _run(emul, oracle, dim, bits, vec, pids, nbr, want_blocks=True, global_tile=True)
+    assert np.array_equal(codes, want_c) and np.array_equal(aux.view(np.uint32), want_a.view(np.uint32))
+    lay = co.nb_layout(max(16, 1 << (dim - 1).bit_length()), bits)
+    want_b = common.blocks_from_codes(dim, bits, want_c, want_a, nbr, len(vec))
+    assert np.array_equal(blocks[:, :lay["count"] + 4], want_b[:, :lay["count"] + 4])
 
 
 @pytest.mark.parametrize("dim,bits,rows", [(960, 2, 32), (960, 4, 32), (1500, 1, 16), (1500, 4, 16)])
