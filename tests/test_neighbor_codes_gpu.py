@@ -27,9 +27,10 @@ def _bits(t):
     return t.cpu().numpy().view(np.uint32)
 
 
+@pytest.mark.parametrize("tile", [0, 1])
 @pytest.mark.parametrize("bits", [1, 2, 4])
 @pytest.mark.parametrize("dim", [10, 20, 64, 96, 128, 300, 960, 1500])
-def test_neighbor_codes_match_the_oracle(oracle, dim, bits):
+def test_neighbor_codes_match_the_oracle(oracle, dim, bits, tile):
     import cphnsw_b200
     from cphnsw_b200 import hooks
 
@@ -38,6 +39,7 @@ def test_neighbor_codes_match_the_oracle(oracle, dim, bits):
     vec, pids, nbr = common.neighbor_code_case(dim, npar, 100 * dim + bits)
     want_c, want_a = common.expected_neighbor_codes(oracle, dim, bits, vec, pids, nbr)
     ix = cphnsw_b200.CPIndex(dim, bits)                  # no index data: the build side runs before one exists
+    ix.set_option("neighbor_codes_tile", tile)           # 0: per-warp tiles in global memory / L2 (default), 1: in shared memory
     codes, aux, blocks = hooks.neighbor_codes(ix, torch.from_numpy(vec), _ids(nbr), _ids(pids), blocks=True)
     assert np.array_equal(codes.cpu().numpy(), want_c)
     assert np.array_equal(_bits(aux), want_a.view(np.uint32))

@@ -77,3 +77,35 @@ def test_fixture_is_what_the_reference_writes(oracle):
         for B in (1, 2, 4):
             rc, ra = oracle.neighbor_aux(dim, B, g[f"parent_{dim}"], g[f"nbrs_{dim}"], ref=True)
             assert np.array_equal(rc, g[f"codes_{dim}_b{B}"]) and np.array_equal(ra.view(np.uint32), g[f"aux_{dim}_b{B}"].view(np.uint32))
+
+
+def _check_against_index_file(oracle, path):
+    sf = co.SaveFile(path)
+    planes, ids, cnt = sf.field("planes"), sf.field("ids"), sf.field("count")
+    nop, ip_qo, ip_cp = sf.field("nop"), sf.field("ip_qo"), sf.field("ip_cp")
+    pairs = 0
+    for p in range(sf.n):
+        c = int(cnt[p])
+        if c == 0:
+            continue
+        oc, oa = oracle.neighbor_aux(sf.dim, sf.B, sf.raw[p][:sf.dim], sf.raw[ids[p][:c]][:, :sf.dim])
+        stored = np.transpose(planes[p].reshape(sf.B, sf.D // 8, 32), (2, 0, 1))[:c]     # packed[sp][v] = byte sp of slot v
+        assert np.array_equal(stored, oc), p
+        aux = np.stack([nop[p][:c], ip_qo[p][:c], ip_cp[p][:c]], 1)
+        assert np.array_equal(aux.view(np.uint32), oa.view(np.uint32)), p
+        pairs += c
+    return pairs
+
+
+@pytest.mark.parametrize("bits", [1, 2, 4])
+def test_restatement_reproduces_the_blocks_of_the_golden_index_files(oracle, bits):
+    """What prune_and_write stored in indexes built and saved by the unmodified reference (D = 32; committed files)."""
+    assert _check_against_index_file(oracle, common.GOLDEN / f"ref_n300_d24_b{bits}.bin") == 9600
+
+
+@needs_ref
+@pytest.mark.parametrize("n,dim,bits", [(2000, 128, 4), (1500, 96, 2), (1000, 64, 1), (600, 960, 2)])
+def test_restatement_reproduces_the_blocks_of_indexes_built_by_the_reference_module(oracle, n, dim, bits):
+    """The same against the compiled pybind module (oracle/_ref), whose own instantiation and inlining of the encoder --
+    not the shim's -- wrote these blocks: the contraction pattern pinned through the shim holds there too."""
+    assert _check_against_index_file(oracle, common.reference_index_file(n, dim, bits)) > 10000
