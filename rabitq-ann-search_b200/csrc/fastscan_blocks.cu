@@ -22,9 +22,14 @@ namespace cpb {
 
 constexpr int kFsMaxWarps = 8;
 
+#ifndef CPB_HOST_EMULATION
 __device__ __forceinline__ uint32_t fs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void fs_mbar_init(uint64_t* bar) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fs_smem_u32(bar)));
+}
+__device__ __forceinline__ void fs_mbar_init_fence() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void fs_issue(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fs_smem_u32(bar)), "r"(bytes) : "memory");
@@ -38,6 +43,19 @@ __device__ __forceinline__ void fs_wait(uint64_t* bar, uint32_t phase) {
                      : "=r"(done) : "r"(fs_smem_u32(bar)), "r"(phase) : "memory");
     } while (!done);
 }
+#else
+// host emulation (tests/native/): the bulk copy is a memcpy by the issuing thread; the barrier word counts completed
+// phases, and a parity wait returns once the phase of that parity is over -- the same protocol, minus the hardware
+inline void fs_mbar_init(uint64_t* bar) { __atomic_store_n(bar, 0, __ATOMIC_RELEASE); }
+inline void fs_mbar_init_fence() {}
+inline void fs_issue(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    memcpy(dst, src, bytes);
+    __atomic_fetch_add(bar, 1, __ATOMIC_RELEASE);
+}
+inline void fs_wait(uint64_t* bar, uint32_t phase) {
+    while ((__atomic_load_n(bar, __ATOMIC_ACQUIRE) & 1u) == phase) {}
+}
+#endif
 
 // LEAN = the streaming case (a contiguous range of blocks, one query, slack level 0, only est and lower written): no
 // per-block look-ups of which query / which vertex / which outputs.
@@ -62,8 +80,7 @@ __global__ void __launch_bounds__(kFsMaxWarps * 32) fastscan_blocks_kernel(const
 
     if (lane == 0) {
         for (uint32_t s = 0; s < ns; ++s) fs_mbar_init(mbar + s);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        fs_mbar_init_fence();
     }
     __syncwarp();
 
@@ -144,6 +161,7 @@ __global__ void __launch_bounds__(kFsMaxWarps * 32) fastscan_blocks_kernel(const
     }
 }
 
+#ifndef CPB_HOST_EMULATION
 cudaError_t launch_fastscan_blocks(const DevIndex& ix, const FastScanArgs& a, int num_sms, cudaStream_t stream) {
     if (a.nblocks == 0) return cudaSuccess;
     const uint32_t copy_bytes = (ix.aux_off + 644u + 15u) & ~15u;
@@ -169,5 +187,7 @@ cudaError_t launch_fastscan_blocks(const DevIndex& ix, const FastScanArgs& a, in
     kern<<<grid, warps * 32, smem, stream>>>(ix, a, ns, stage_bytes);
     return cudaGetLastError();
 }
+
+#endif
 
 }  // namespace cpb

@@ -132,6 +132,7 @@ query_prep_kernel(DevIndex ix, const float* __restrict__ queries, uint32_t nq, i
     }
 }
 
+#ifndef CPB_HOST_EMULATION   // tests/native/ compiles the kernel above for the host (it has no PTX)
 cudaError_t launch_query_prep(const DevIndex& ix, const float* d_queries, uint32_t nq, int center,
                               const PrepOut& out, cudaStream_t stream) {
     if (nq == 0) return cudaSuccess;
@@ -149,5 +150,7 @@ cudaError_t launch_query_prep(const DevIndex& ix, const float* d_queries, uint32
     query_prep_kernel<<<grid, kPrepWarps * 32, smem, stream>>>(ix, d_queries, nq, center, norm_factor, inv_sqrt_d, out);
     return cudaGetLastError();
 }
+
+#endif
 
 }  // namespace cpb

@@ -93,6 +93,7 @@ __global__ void relayout_raw_kernel(const DevIndex ix, const float* __restrict__
     }
 }
 
+#ifndef CPB_HOST_EMULATION   // tests/native/ compiles the kernels above for the host (no PTX)
 cudaError_t launch_relayout_blocks(const DevIndex& ix, const uint8_t* d_records, uint64_t rec_size, uint32_t nb_off,
                                    uint64_t first, uint32_t count, uint32_t* d_problems, cudaStream_t stream) {
     if (count == 0) return cudaSuccess;
@@ -108,5 +109,7 @@ cudaError_t launch_relayout_raw(const DevIndex& ix, const float* d_raw, uint64_t
     relayout_raw_kernel<<<grid, 256, 0, stream>>>(ix, d_raw, first, count);
     return cudaGetLastError();
 }
+
+#endif
 
 }  // namespace cpb

@@ -62,6 +62,11 @@ inline T __shfl_sync(unsigned, T v, int src) {
     return r;
 }
 
+template <typename T>
+inline T __shfl_xor_sync(unsigned m, T v, int lane_mask) { return __shfl_sync(m, v, (int)(threadIdx.x & 31) ^ lane_mask); }
+template <typename T>
+inline T __ldg(const T* p) { return *p; }
+
 inline unsigned __ballot_sync(unsigned, int pred) {
     cuda_emul::Warp* w = cuda_emul::t_warp;
     w->slot[threadIdx.x & 31] = pred ? 1u : 0u;
@@ -72,14 +77,28 @@ inline unsigned __ballot_sync(unsigned, int pred) {
     return m;
 }
 
+inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+
+inline unsigned __match_any_sync(unsigned, unsigned value) {
+    cuda_emul::Warp* w = cuda_emul::t_warp;
+    w->slot[threadIdx.x & 31] = value;
+    w->bar.arrive_and_wait();
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l) m |= (w->slot[l] == value ? 1u : 0u) << l;
+    w->bar.arrive_and_wait();
+    return m;
+}
+
+inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+
 namespace cuda_emul {
 
-// Runs kernel(args) for every block of the grid, one block after the other.  `smem`/`smem_floats`: the shared-memory
-// array, re-filled with signalling garbage (NaNs) before each block so that a read of unwritten memory shows.
+// Runs kernel(args) for every block of the grid, one block after the other.  `smem`/`smem_bytes`: the shared-memory
+// array, re-filled with garbage (0xFF: NaNs as floats) before each block so that a read of unwritten memory shows.
 template <typename Kernel, typename Args>
-void launch(Kernel kernel, unsigned grid, unsigned block, float* smem, size_t smem_floats, const Args& args) {
+void launch(Kernel kernel, unsigned grid, unsigned block, void* smem, size_t smem_bytes, const Args& args) {
     for (unsigned b = 0; b < grid; ++b) {
-        std::memset(smem, 0xFF, smem_floats * sizeof(float));
+        std::memset(smem, 0xFF, smem_bytes);
         Block blk;
         blk.bar = std::make_unique<std::barrier<>>(block);
         for (unsigned w = 0; w < (block + 31) / 32; ++w) blk.warps.push_back(std::make_unique<Warp>());

@@ -35,9 +35,9 @@ extern "C" int emul_neighbor_codes(uint32_t dim, uint32_t bits, const float* sig
     }
     if (rows_used) *rows_used = a.rows;
     switch (bits) {
-        case 1: cuda_emul::launch(cpb::neighbor_codes_kernel<1>, plan.grid, plan.warps * 32, cpb::smem, plan.smem_bytes / 4, a); break;
-        case 2: cuda_emul::launch(cpb::neighbor_codes_kernel<2>, plan.grid, plan.warps * 32, cpb::smem, plan.smem_bytes / 4, a); break;
-        default: cuda_emul::launch(cpb::neighbor_codes_kernel<4>, plan.grid, plan.warps * 32, cpb::smem, plan.smem_bytes / 4, a); break;
+        case 1: cuda_emul::launch(cpb::neighbor_codes_kernel<1>, plan.grid, plan.warps * 32, cpb::smem, plan.smem_bytes, a); break;
+        case 2: cuda_emul::launch(cpb::neighbor_codes_kernel<2>, plan.grid, plan.warps * 32, cpb::smem, plan.smem_bytes, a); break;
+        default: cuda_emul::launch(cpb::neighbor_codes_kernel<4>, plan.grid, plan.warps * 32, cpb::smem, plan.smem_bytes, a); break;
     }
     return 0;
 }

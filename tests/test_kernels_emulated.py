@@ -1,0 +1,176 @@
+"""Kernel source on the CPU: the PTX-free kernels of rabitq-ann-search_b200/csrc compiled for the host over
+tests/native/cuda_emul.h (a thread per lane, barriers for the warp primitives, IEEE operations for the _rn intrinsics)
+and held to the reference's committed golden vectors.  The GPU runs of the same comparisons are in tests/test_parity_gpu.py;
+the build-side encoder has its own file (tests/test_neighbor_codes_emulated.py)."""
+import ctypes as C
+import subprocess
+
+import numpy as np
+import pytest
+
+import common
+
+NATIVE = common.ROOT / "tests" / "native"
+
+
+def _build(tmp_path_factory, name):
+    out = tmp_path_factory.mktemp("emul") / f"lib{name}.so"
+    cmd = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I/usr/local/cuda/include",
+           str(NATIVE / f"{name}.cpp"), "-o", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return C.CDLL(str(out))
+
+
+@pytest.fixture(scope="module")
+def k1(tmp_path_factory):
+    return _build(tmp_path_factory, "query_prep_emul")
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _prepare(k1, oracle, q, center=False, centroid=None):
+    nq, dim = q.shape
+    D = max(16, 1 << (dim - 1).bit_length())
+    W = max(D, 128) // 32
+    signs = oracle.rotation_signs(D)
+    cen = np.zeros(dim, np.float32) if centroid is None else np.ascontiguousarray(centroid, np.float32)
+    lut = np.full((nq, D // 4, 16), 0xEE, np.uint8)
+    coeffs = np.full((nq, 8), np.nan, np.float32)
+    rot = np.full((nq, D), np.nan, np.float32)
+    upl = np.full((nq, 4, W), 0xDDDDDDDD, np.uint32)
+    qT = np.full((nq, D), np.nan, np.float32)
+    q = np.ascontiguousarray(q, np.float32)
+    rc = k1.emul_prepare_queries(C.c_uint32(dim), _p(signs, C.c_float), _p(cen, C.c_float), _p(q, C.c_float), C.c_uint32(nq),
+                                 C.c_int(int(center)), _p(lut, C.c_uint8), _p(coeffs, C.c_float), _p(rot, C.c_float),
+                                 _p(upl, C.c_uint32), _p(qT, C.c_float))
+    assert rc == 0
+    return lut, coeffs, rot, upl, qT
+
+
+@pytest.mark.parametrize("dim", [16, 20, 96, 128, 960])
+def test_k1_source_reproduces_the_reference_golden_vectors(k1, oracle, dim):
+    g = np.load(common.GOLDEN / "k1_golden.npz")
+    q = g[f"q_{dim}"]
+    lut, coeffs, rot, upl, qT = _prepare(k1, oracle, q)
+    assert np.array_equal(lut, g[f"lut_{dim}"])
+    assert np.array_equal(_bits(coeffs[:, :3]), _bits(g[f"coeffs_{dim}"]))
+    assert np.array_equal(_bits(rot), _bits(g[f"rot_{dim}"]))
+    # the bit-plane form of the same 4-bit values (what K2/K3/K5 consume): u_i = lut[i/4][1 << i%4]
+    D = rot.shape[1]
+    u = np.stack([g[f"lut_{dim}"][:, :, 1 << b] for b in range(4)], 2).reshape(len(q), D).astype(np.uint32)
+    W = upl.shape[2]
+    for t in range(4):
+        bits = np.zeros((len(q), W * 32), np.uint32)
+        bits[:, :D] = (u >> t) & 1
+        words = (bits.reshape(len(q), W, 32) << np.arange(32, dtype=np.uint32)).sum(2).astype(np.uint32)
+        assert np.array_equal(upl[:, t], words), t
+    # |q|^2 by dot_product_simd's eight chains, and the accumulator-major copy of the padded query
+    for i in range(len(q)):
+        pad = np.zeros(D, np.float32); pad[:dim] = q[i]
+        assert _bits(coeffs[i, 3:4])[0] == _bits(np.float32(oracle.dot(pad, pad)))[0]
+        assert np.array_equal(qT[i].reshape(8, D // 8), pad.reshape(D // 8, 8).T)
+
+
+@pytest.mark.parametrize("dim", [20, 96, 300])
+def test_k1_source_centred_queries_equal_the_oracle(k1, oracle, dim):
+    """center=True (the exhaustive scan's query form): q - centroid before the rotation."""
+    rng = np.random.default_rng(dim)
+    q = rng.standard_normal((9, dim)).astype(np.float32)
+    cen = rng.standard_normal(dim).astype(np.float32) * 0.3
+    q[2] = cen
+    lut, coeffs, rot, _, _ = _prepare(k1, oracle, q, center=True, centroid=cen)
+    olut, oco, orot = oracle.encode_queries((q - cen).astype(np.float32), want_rotated=True)
+    assert np.array_equal(lut, olut)
+    assert np.array_equal(_bits(coeffs[:, :3]), _bits(oco))
+    assert np.array_equal(_bits(rot), _bits(orot))
+
+
+# ---- index hand-off (relayout.cu) + K2 (fastscan_blocks.cu) ------------------------------------------------------------
+@pytest.fixture(scope="module")
+def k2(tmp_path_factory):
+    return _build(tmp_path_factory, "fastscan_emul")
+
+
+def _uplanes_from_lut(lut, D):
+    nq = lut.shape[0]
+    u = np.stack([lut[:, :, 1 << b] for b in range(4)], axis=2).reshape(nq, D)
+    W = max(D, 128) // 32
+    up = np.zeros((nq, 4, W), np.uint32)
+    for t in range(4):
+        pad = np.zeros((nq, W * 32), np.uint8)
+        pad[:, :D] = (u >> t) & 1
+        up[:, t, :] = np.packbits(pad.reshape(nq, W, 32), axis=2, bitorder="little").view(np.uint32)[:, :, 0]
+    return up
+
+
+def _fastscan(k2, dim, bits, blocks, calib, up, coeffs, dqp, qi=None, levels=None, vertex_ids=None, lean=False):
+    n = blocks.shape[0]
+    nblocks = n if vertex_ids is None else len(vertex_ids)
+    blocks = np.ascontiguousarray(blocks)
+    co8 = np.zeros((up.shape[0], 8), np.float32)
+    co8[:, :3] = coeffs
+    outs = {name: np.full((nblocks, 32), 0xABABABAB, np.uint32) for name in ("nbit", "msb", "msb2")}
+    outs.update({name: np.full((nblocks, 32), np.nan, np.float32) for name in ("est", "lower", "msb_lower")})
+    problems = np.zeros(2, np.uint32)
+    calib = np.ascontiguousarray(calib, np.float32)
+    opt = lambda a, t: None if a is None else _p(np.ascontiguousarray(a), t)  # noqa: E731
+    keep = [np.ascontiguousarray(a) if a is not None else None for a in (qi, vertex_ids, levels)]
+    want = (lambda name: None) if lean else (lambda name: _p(outs[name], C.c_uint32 if outs[name].dtype == np.uint32 else C.c_float))
+    rc = k2.emul_fastscan_blocks(
+        C.c_uint32(dim), C.c_uint32(bits), _p(blocks, C.c_uint8), C.c_uint64(blocks.shape[1]), C.c_uint64(n), _p(calib, C.c_float),
+        C.c_int(len(calib) - 3), _p(up, C.c_uint32), _p(co8, C.c_float), C.c_uint32(up.shape[0]),
+        None if keep[0] is None else _p(keep[0], C.c_uint32), None if keep[1] is None else _p(keep[1], C.c_uint32), C.c_uint64(nblocks),
+        _p(dqp, C.c_float), None if keep[2] is None else _p(keep[2], C.c_int32),
+        want("nbit"), want("msb"), want("msb2"), _p(outs["est"], C.c_float), _p(outs["lower"], C.c_float), want("msb_lower"),
+        C.c_int(int(lean)), _p(problems, C.c_uint32))
+    assert rc == 0, rc
+    del opt
+    return outs, problems
+
+
+@pytest.mark.parametrize("tag", ["128_1", "128_2", "128_4", "960_2", "16_4"])
+def test_relayout_and_k2_sources_reproduce_the_reference_golden_vectors(k2, tag):
+    """Reference neighbour blocks -> the product's re-layout kernel -> the product's FastScan kernel (general form: block
+    list, per-block query and slack level) = the reference's integer sums and float estimates / bounds, bit for bit."""
+    g = np.load(common.GOLDEN / "k2_golden.npz")
+    dim, bits = map(int, tag.split("_"))
+    D = max(16, 1 << (dim - 1).bit_length())
+    blocks = g[f"blocks_{tag}"]
+    n = blocks.shape[0]
+    up = _uplanes_from_lut(g[f"lut_{tag}"], D)
+    outs, problems = _fastscan(k2, dim, bits, blocks, g[f"calib_{tag}"][:6], up, g[f"coeffs_{tag}"], g[f"dqp_{tag}"].astype(np.float32),
+                               qi=g[f"qi_{tag}"].astype(np.uint32), levels=(np.arange(n) % 3).astype(np.int32),
+                               vertex_ids=np.arange(n, dtype=np.uint32))
+    for v in range(n):
+        c = int(g[f"count_{tag}"][v])
+        for name in ("nbit", "msb", "msb2"):
+            assert np.array_equal(outs[name][v], g[f"{name}_{tag}"][v]), (name, v)
+        for name in ("est", "lower", "msb_lower"):
+            assert np.array_equal(_bits(outs[name][v][:c]), _bits(g[f"{name}_{tag}"][v][:c])), (name, v)
+            assert (outs[name][v][c:] == np.finfo(np.float32).max).all()
+
+
+@pytest.mark.parametrize("dim,bits", [(128, 4), (96, 1), (300, 2)])
+def test_k2_streaming_specialisation_equals_the_general_form(k2, dim, bits):
+    """LEAN (contiguous range, one query, slack level 0, est + lower only: the kernel behind the HBM figure)."""
+    fab = common.fabricate(37, dim, bits, seed=dim, counts=(32, 31, 9, 1), degenerate=True, a=1.01, b=0.002)
+    blocks = fab.search_data[:, fab.nb_off:]
+    rng = np.random.default_rng(3)
+    up = rng.integers(0, 2 ** 32, (1, 4, max(fab.D, 128) // 32), dtype=np.uint64).astype(np.uint32)
+    if fab.D < 128:
+        up[:, :, fab.D // 32:] = 0
+    coeffs = np.array([[0.013, -0.4, 0.07]], np.float32)
+    dqp = rng.uniform(0.5, 40.0, fab.n).astype(np.float32)
+    import struct
+    cal = np.array(struct.unpack_from("<3f", fab.calibration, 0) + struct.unpack_from("<3f", fab.calibration, 108), np.float32)
+    general, _ = _fastscan(k2, dim, bits, blocks, cal, up, coeffs, dqp)
+    lean, _ = _fastscan(k2, dim, bits, blocks, cal, up, coeffs, dqp, lean=True)
+    assert np.array_equal(_bits(lean["est"]), _bits(general["est"]))
+    assert np.array_equal(_bits(lean["lower"]), _bits(general["lower"]))
