@@ -198,6 +198,8 @@ __device__ __forceinline__ void heap_pop(const WarpCtx& w, uint32_t n) {
 }
 
 // ---- bulk asynchronous copies (TMA engine) completing on an mbarrier ----------------------------------
+#ifndef CPB_HOST_EMULATION
+#define CPB_BLOCK_SHARED __shared__
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -218,6 +220,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
     } while (!done);
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#else
+// host emulation (tests/native/): bar[0] counts completed phases, bar[1] the bytes the issuing thread still owes the
+// current one (the kernel reserves 16 bytes per barrier); a bulk copy is a memcpy by the issuing thread
+#define CPB_BLOCK_SHARED static
+inline void mbar_init(uint64_t* bar, uint32_t) { bar[1] = 0; __atomic_store_n(&bar[0], 0, __ATOMIC_RELEASE); }
+inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { bar[1] = bytes; }
+inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    memcpy(dst, src, bytes);
+    bar[1] -= bytes;
+    if (bar[1] == 0) __atomic_fetch_add(&bar[0], 1, __ATOMIC_RELEASE);
+}
+inline void mbar_wait(uint64_t* bar, uint32_t phase) {
+    while ((__atomic_load_n(&bar[0], __ATOMIC_ACQUIRE) & 1u) == phase) {}
+}
+inline void prefetch_l2(const void*) {}
+#endif
 
 // BoundedMaxHeap::push (search/rabitq_search.hpp:26-35) on an ascending list: accept while not
 // full, else replace the worst iff strictly closer.  No de-duplication.  Equal
@@ -317,8 +336,6 @@ __device__ __forceinline__ uint32_t greedy_descent(const DevIndex& ix, const War
     return node;
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 // DT = 128: the padded dimension is the compile-time constant 128 (SIFT/Deep shapes: one 128-dim chunk per
 // code plane, 16-step distance chains, constant shared-memory offsets); DT = 0: any supported dimension.
 template <int B, bool STATS, int DT>
@@ -336,7 +353,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
     WarpCtx w;
     w.lane = lane;
     w.D = D; w.T = T;
-    __shared__ uint2 walk_tab[32];
+    CPB_BLOCK_SHARED uint2 walk_tab[32];
     if (warp == 0) init_walk_table(walk_tab, lane);
     w.walk = walk_tab;
     __syncthreads();
@@ -654,6 +671,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
 
 size_t search_smem_per_warp(const DevIndex& ix, uint32_t k) { return smem_per_warp(ix.D, ix.B, k); }
 
+#ifndef CPB_HOST_EMULATION   // tests/native/ compiles the kernels of this file for the host
 typedef void (*SearchKernel)(const DevIndex, const SearchArgs);
 
 template <int DT>
@@ -690,6 +708,8 @@ cudaError_t launch_search(const DevIndex& ix, const SearchArgs& a, int ctas, int
     return cudaGetLastError();
 }
 
+#endif
+
 // ---- K4 primitive ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) exact_l2_kernel(const DevIndex ix, const float* __restrict__ qT,
                                                        const float* __restrict__ coeffs, uint32_t nq,
@@ -713,6 +733,7 @@ __global__ void __launch_bounds__(128) exact_l2_kernel(const DevIndex ix, const 
     }
 }
 
+#ifndef CPB_HOST_EMULATION
 cudaError_t launch_exact_l2(const DevIndex& ix, const float* qT, const float* coeffs, uint32_t nq,
                             const uint32_t* ids, uint32_t m, float* out, cudaStream_t stream) {
     if (nq == 0 || m == 0) return cudaSuccess;
@@ -721,5 +742,7 @@ cudaError_t launch_exact_l2(const DevIndex& ix, const float* qT, const float* co
     exact_l2_kernel<<<(nq + warps - 1) / warps, warps * 32, smem, stream>>>(ix, qT, coeffs, nq, ids, m, out);
     return cudaGetLastError();
 }
+
+#endif
 
 }  // namespace cpb

@@ -174,3 +174,113 @@ def test_k2_streaming_specialisation_equals_the_general_form(k2, dim, bits):
     lean, _ = _fastscan(k2, dim, bits, blocks, cal, up, coeffs, dqp, lean=True)
     assert np.array_equal(_bits(lean["est"]), _bits(general["est"]))
     assert np.array_equal(_bits(lean["lower"]), _bits(general["lower"]))
+
+
+# ---- K3 (+ fused K4): search.cu, over the re-laid-out index and K1's prepared queries --------------------------------
+@pytest.fixture(scope="module")
+def k3(tmp_path_factory):
+    return _build(tmp_path_factory, "search_emul")
+
+
+def _level_csr(layers, max_level, entry_point):
+    """The slot-addressed CSR cphnsw_b200_upload derives from the save file's sorted edge lists (find_edge becomes a
+    table: neighbour -> its slot in the same level, node -> its slot one level down)."""
+    out, sizes, entry_slot = [], [], 0xFFFFFFFF
+    n_levels = len(layers) if max_level > 0 else 0
+    for L in range(n_levels):
+        nodes, offs, nbrs = (np.ascontiguousarray(a, np.uint32) for a in layers[L])
+
+        def slot_of(arr, ids):
+            pos = np.searchsorted(arr, ids)
+            ok = (pos < len(arr)) & (arr[np.minimum(pos, len(arr) - 1)] == ids)
+            return np.where(ok, pos, 0xFFFFFFFF).astype(np.uint32)
+
+        nbr_slot = slot_of(nodes, nbrs)
+        down = nodes.copy() if L == 0 else slot_of(np.ascontiguousarray(layers[L - 1][0], np.uint32), nodes)
+        out += [nodes, offs, nbrs, nbr_slot, down]
+        sizes.append(len(nodes))
+        if L + 1 == max_level:
+            entry_slot = int(slot_of(nodes, np.array([entry_point], np.uint32))[0])
+    return out, np.array(sizes + [0], np.uint32), entry_slot, n_levels
+
+
+def _search(k1, k3, oracle, dim, bits, records, rec_size, nb_off, raw, norm_sq, calib, max_level, entry_point, layers, queries, k,
+            warps=4, ctas=2, beam_capacity=0, want_stats=False):
+    n = raw.shape[0]
+    _, coeffs, _, upl, qT = _prepare(k1, oracle, queries)
+    arrays, sizes, entry_slot, n_levels = _level_csr(layers, max_level, entry_point)
+    ptrs = (C.POINTER(C.c_uint32) * max(1, len(arrays)))(*[_p(a, C.c_uint32) for a in arrays])
+    nq = len(queries)
+    ids = np.full((nq, k), -77, np.int64)
+    dists = np.full((nq, k), np.nan, np.float32)
+    stats = np.zeros(11, np.uint64)
+    over = C.c_uint32(0)
+    records = np.ascontiguousarray(records)
+    raw = np.ascontiguousarray(raw, np.float32)
+    norm_sq = np.ascontiguousarray(norm_sq, np.float32)
+    cal = np.frombuffer(bytes(calib), np.uint8).copy()
+    rc = k3.emul_search(C.c_uint32(dim), C.c_uint32(bits), _p(records, C.c_uint8), C.c_uint64(rec_size), C.c_uint32(nb_off), C.c_uint64(n),
+                        _p(raw, C.c_float), _p(norm_sq, C.c_float), _p(cal, C.c_uint8), C.c_int32(max_level), C.c_uint32(entry_point),
+                        C.c_uint32(entry_slot), C.c_uint32(entry_point), C.c_uint32(n_levels), ptrs, _p(sizes, C.c_uint32),
+                        _p(qT, C.c_float), _p(upl, C.c_uint32), _p(coeffs, C.c_float), C.c_uint32(nq), C.c_uint32(k),
+                        _p(ids, C.c_int64), _p(dists, C.c_float), C.c_int(warps), C.c_int(ctas), C.c_uint32(beam_capacity),
+                        _p(stats, C.c_uint64) if want_stats else None, C.byref(over))
+    assert rc == 0, rc
+    return ids, dists, over.value, stats
+
+
+@pytest.mark.parametrize("bits", [1, 2, 4])
+@pytest.mark.parametrize("k", [1, 10, 50])
+def test_search_kernel_source_reproduces_the_reference_results(k1, k3, oracle, bits, k):
+    """Index files built and saved by the unmodified reference, and its own search_batch results on them (e2e_golden):
+    re-layout kernels + K1 + the search kernel, all from the product's source, on host threads -- ids and distance bits."""
+    g = np.load(common.GOLDEN / "e2e_golden.npz")
+    sf = co_SaveFile(common.GOLDEN / f"ref_n300_d24_b{bits}.bin")
+    ids, dists, over, _ = _search(k1, k3, oracle, sf.dim, bits, sf.search_data, sf.rec_size, sf.nb_off, sf.raw, sf.norm_sq, sf.calib_bytes,
+                                  sf.max_level, sf.entry_point, sf.layers, g["queries"], k)
+    assert over == 0
+    gi, gd = common.sorted_rows(ids, dists)
+    wi, wd = common.sorted_rows(g[f"ids_b{bits}_k{k}"], g[f"dists_b{bits}_k{k}"])
+    assert np.array_equal(gi, wi) and np.array_equal(_bits(gd), _bits(wd))
+
+
+def co_SaveFile(path):
+    from common import co
+
+    return co.SaveFile(path)
+
+
+_STAT_FIELDS = ("pops", "expansions", "exact_calls", "beam_pushes", "max_beam", "nn_pushes", "lb_skips", "gamma_terms", "msb_skipped",
+                "estimated", "descent_dists")
+
+
+@pytest.mark.parametrize("dim,bits,k", [(128, 4, 10), (128, 1, 3), (96, 2, 33), (20, 4, 130)])
+def test_search_kernel_source_equals_the_oracle_on_fabricated_indexes(k1, k3, oracle, dim, bits, k):
+    """Random 'finalized indexes' (partial and empty blocks, degenerate aux values, two upper layers; small gamma and wide
+    slack so that gamma termination, lower-bound skips and MSB-only skips fire): results and the kernel's counters against
+    the C restatement of rabitq_search::search.  D = 128 takes the compile-time-dimension kernel."""
+    fab = common.fabricate(400, dim, bits, seed=dim + bits, counts=(32, 32, 31, 24, 9, 0), degenerate=True, layers=2,
+                           gamma=1.02, gamma_max=1.6, gamma_beta=0.8, gamma_warmup=4, floor=0.35, slacks=(0.05, 0.08, 0.1, 0.12))
+    q = np.random.default_rng(11).standard_normal((12, dim)).astype(np.float32)
+    q[0] = fab.raw[3, :dim]
+    ids, dists, over, st = _search(k1, k3, oracle, dim, bits, fab.search_data, fab.search_data.shape[1], fab.nb_off, fab.raw, fab.norm_sq,
+                                   fab.calibration, fab.max_level, fab.entry_point, fab.layers, q, k, want_stats=True)
+    assert over == 0
+    oid, od, ost = oracle.search_batch(oracle.index_view(fab), q, k)
+    gi, gd = common.sorted_rows(ids, dists)
+    wi, wd = common.sorted_rows(oid, od)
+    assert np.array_equal(gi, wi) and np.array_equal(_bits(gd), _bits(wd))
+    got = dict(zip(_STAT_FIELDS, (int(v) for v in st)))
+    for key in ("pops", "expansions", "beam_pushes", "nn_pushes", "lb_skips", "gamma_terms", "msb_skipped", "estimated", "descent_dists",
+                "max_beam"):
+        assert got[key] == ost[key], (key, got[key], ost[key])
+    assert got["exact_calls"] >= ost["exact_calls"]
+
+
+def test_search_kernel_source_reports_frontier_overflow(k1, k3, oracle):
+    """A frontier arena too small for the query: the kernel must list the query for the re-run instead of writing past it."""
+    fab = common.fabricate(400, 64, 1, seed=5, layers=1, gamma=1e6, gamma_max=1e7)
+    q = np.random.default_rng(2).standard_normal((4, 64)).astype(np.float32)
+    _, _, over, _ = _search(k1, k3, oracle, 64, 1, fab.search_data, fab.search_data.shape[1], fab.nb_off, fab.raw, fab.norm_sq,
+                            fab.calibration, fab.max_level, fab.entry_point, fab.layers, q, 5, beam_capacity=64)
+    assert over > 0
