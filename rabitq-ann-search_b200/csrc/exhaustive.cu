@@ -34,9 +34,9 @@ __global__ void __launch_bounds__(kExThreads) exhaustive_scan_kernel(const DevIn
     unsigned long long* cand = reinterpret_cast<unsigned long long*>(smem_raw);              // [kQT][kCap]
     uint4* uq = reinterpret_cast<uint4*>(smem_raw + (size_t)kQT * kCap * 8);                 // [kQT][4][nch]
     float* par = reinterpret_cast<float*>(smem_raw + (size_t)kQT * kCap * 8 + (size_t)kQT * nch * 64);   // [kQT][4]
-    __shared__ uint32_t cnt[kQT];
-    __shared__ float tau[kQT];
-    __shared__ uint32_t need_compact;
+    CPB_BLOCK_SHARED uint32_t cnt[kQT];
+    CPB_BLOCK_SHARED float tau[kQT];
+    CPB_BLOCK_SHARED uint32_t need_compact;
 
     const uint32_t slice = blockIdx.x, q0 = blockIdx.y * kQT;
     const uint32_t nqt = min((uint32_t)kQT, a.nq - q0);
@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(kExThreads) exhaustive_select_rerank_kernel(co
     }
 }
 
+#ifndef CPB_HOST_EMULATION   // tests/native/ compiles the kernels above for the host (no PTX)
 // Vertex slices per query tile.  Every (slice, query tile) CTA pays a fixed price in list compactions and a
 // final sort, so slices should be long (>= 64 K vertices) -- but the grid still has to fill the GPU when there
 // are few queries, and one CTA must be able to merge slices x k' keys in shared memory (16 K keys).
@@ -233,5 +234,7 @@ cudaError_t launch_exhaustive(const DevIndex& ix, const ExhaustiveArgs& a, int n
     }
     return e;
 }
+
+#endif
 
 }  // namespace cpb

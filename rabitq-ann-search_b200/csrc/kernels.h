@@ -5,6 +5,13 @@
 
 #include "device_index.h"
 
+// Block-scope shared variables: `static` when tests/native/ compiles a kernel for the host (blocks run one at a time)
+#ifdef CPB_HOST_EMULATION
+#define CPB_BLOCK_SHARED static
+#else
+#define CPB_BLOCK_SHARED __shared__
+#endif
+
 namespace cpb {
 
 constexpr uint32_t kCoeffStride = 8;  // A, Bc, C, |q|^2, |q-c|^2, pad

@@ -199,7 +199,6 @@ __device__ __forceinline__ void heap_pop(const WarpCtx& w, uint32_t n) {
 
 // ---- bulk asynchronous copies (TMA engine) completing on an mbarrier ----------------------------------
 #ifndef CPB_HOST_EMULATION
-#define CPB_BLOCK_SHARED __shared__
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -224,7 +223,6 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 #else
 // host emulation (tests/native/): bar[0] counts completed phases, bar[1] the bytes the issuing thread still owes the
 // current one (the kernel reserves 16 bytes per barrier); a bulk copy is a memcpy by the issuing thread
-#define CPB_BLOCK_SHARED static
 inline void mbar_init(uint64_t* bar, uint32_t) { bar[1] = 0; __atomic_store_n(&bar[0], 0, __ATOMIC_RELEASE); }
 inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { bar[1] = bytes; }
 inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {

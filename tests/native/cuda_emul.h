@@ -17,6 +17,10 @@
 #include <thread>
 #include <vector>
 
+#include <algorithm>
+using std::max;
+using std::min;
+
 #ifndef __launch_bounds__
 #define __launch_bounds__(...)
 #endif
@@ -112,8 +116,9 @@ namespace cuda_emul {
 // Runs kernel(args) for every block of the grid, one block after the other.  `smem`/`smem_bytes`: the shared-memory
 // array, re-filled with garbage (0xFF: NaNs as floats) before each block so that a read of unwritten memory shows.
 template <typename Kernel, typename Args>
-void launch(Kernel kernel, unsigned grid, unsigned block, void* smem, size_t smem_bytes, const Args& args) {
-    for (unsigned b = 0; b < grid; ++b) {
+void launch(Kernel kernel, dim3 grid, unsigned block, void* smem, size_t smem_bytes, const Args& args) {
+    for (unsigned by = 0; by < grid.y; ++by)
+    for (unsigned b = 0; b < grid.x; ++b) {
         std::memset(smem, 0xFF, smem_bytes);
         Block blk;
         blk.bar = std::make_unique<std::barrier<>>(block);
@@ -122,9 +127,9 @@ void launch(Kernel kernel, unsigned grid, unsigned block, void* smem, size_t sme
         for (unsigned t = 0; t < block; ++t)
             threads.emplace_back([&, t] {
                 threadIdx = uint3{t, 0, 0};
-                blockIdx = uint3{b, 0, 0};
+                blockIdx = uint3{b, by, 0};
                 blockDim = dim3(block, 1, 1);
-                gridDim = dim3(grid, 1, 1);
+                gridDim = grid;
                 t_block = &blk;
                 t_warp = blk.warps[t / 32].get();
                 kernel(args);

@@ -284,3 +284,48 @@ def test_search_kernel_source_reports_frontier_overflow(k1, k3, oracle):
     _, _, over, _ = _search(k1, k3, oracle, 64, 1, fab.search_data, fab.search_data.shape[1], fab.nb_off, fab.raw, fab.norm_sq,
                             fab.calibration, fab.max_level, fab.entry_point, fab.layers, q, 5, beam_capacity=64)
     assert over > 0
+
+
+# ---- K5, popcount form (exhaustive.cu): scan + select / exact re-rank -------------------------------------------------
+@pytest.fixture(scope="module")
+def k5(tmp_path_factory):
+    return _build(tmp_path_factory, "exhaustive_emul")
+
+
+def _exhaustive(k1, k5, oracle, sf, queries, k, kprime, nslices=1, dense=False, id_begin=0, id_end=None):
+    id_end = sf.n if id_end is None else id_end
+    _, coeffs, _, upl, qT = _prepare(k1, oracle, queries, center=True, centroid=sf.centroid)
+    nq, m = len(queries), id_end - id_begin
+    sums = np.full((nq, m), 0xABABABAB, np.uint32) if dense else None
+    est = np.full((nq, m), np.nan, np.float32) if dense else None
+    ids = np.full((nq, max(k, 1)), -77, np.int64)
+    dists = np.full((nq, max(k, 1)), np.nan, np.float32)
+    records = np.ascontiguousarray(sf.search_data)
+    raw = np.ascontiguousarray(sf.raw, np.float32)
+    norm_sq = np.ascontiguousarray(sf.norm_sq, np.float32)
+    cal = np.array([sf.affine_a, sf.affine_b, sf.ip_qo_floor], np.float32)
+    rc = k5.emul_exhaustive(C.c_uint32(sf.dim), _p(records, C.c_uint8), C.c_uint64(sf.rec_size), C.c_uint32(sf.nb_off), C.c_uint64(sf.n),
+                            _p(raw, C.c_float), _p(norm_sq, C.c_float), _p(cal, C.c_float), _p(qT, C.c_float), _p(upl, C.c_uint32),
+                            _p(coeffs, C.c_float), C.c_uint32(nq), C.c_uint64(id_begin), C.c_uint64(id_end), C.c_uint32(k),
+                            C.c_uint32(kprime), C.c_uint32(nslices), None if sums is None else _p(sums, C.c_uint32),
+                            None if est is None else _p(est, C.c_float), _p(ids, C.c_int64), _p(dists, C.c_float))
+    assert rc == 0, rc
+    return sums, est, ids, dists
+
+
+def test_exhaustive_kernel_sources_reproduce_the_reference_composition(k1, k5, oracle):
+    """tests/golden/exhaustive_golden.npz was composed from primitives executed by the unmodified reference on its own
+    1-bit index file: integer sums, estimate bits, and (k, k') results -- here from the scan and select/re-rank kernels'
+    source on host threads, with one and with several vertex slices per query tile."""
+    g = np.load(common.GOLDEN / "exhaustive_golden.npz")
+    sf = co_SaveFile(common.GOLDEN / "ref_n300_d24_b1.bin")
+    q = g["queries"]
+    sums, est, _, _ = _exhaustive(k1, k5, oracle, sf, q, 0, 0, dense=True)
+    for i in range(len(q)):
+        assert np.array_equal(sums[i], g[f"sums_{i}"]), i
+        assert np.array_equal(_bits(est[i]), _bits(g[f"est_{i}"])), i
+    for k, kp, nslices in ((10, 100, 1), (10, 100, 3), (1, 1, 1), (5, 32, 3), (10, 300, 1)):
+        _, _, ids, dists = _exhaustive(k1, k5, oracle, sf, q, k, kp, nslices=nslices)
+        for i in range(len(q)):
+            assert np.array_equal(ids[i], g[f"ids_{i}_k{k}_kp{kp}"]), (i, k, kp, nslices)
+            assert np.array_equal(_bits(dists[i]), _bits(g[f"dists_{i}_k{k}_kp{kp}"])), (i, k, kp, nslices)
