@@ -101,3 +101,23 @@ extern "C" int emul_search(uint32_t dim, uint32_t bits, const uint8_t* records, 
     for (uint32_t w : bitmaps) if (w) return 5;   // every slot must leave its bitmap clean for the next query
     return 0;
 }
+
+// K4 primitive (exact_l2_kernel): distances of listed ids, raw vectors re-laid out by relayout_raw_kernel
+extern "C" int emul_exact_l2(uint32_t dim, uint64_t n, const float* raw, const float* norm_sq, const float* qT, const float* coeffs,
+                             uint32_t nq, const uint32_t* ids, uint32_t m, float* out) {
+    using namespace cpb;
+    DevIndex ix{};
+    uint32_t D = 16;
+    while (D < dim) D <<= 1;
+    ix.D = D; ix.B = 1; ix.dim = dim; ix.nch = (D > 128 ? D : 128) / 128; ix.T = D / 8; ix.n = n;
+    std::vector<float> rawT((size_t)n * D + 64, -7.0f);
+    ix.rawT = rawT.data() + (16 - (reinterpret_cast<uintptr_t>(rawT.data()) / 4) % 16) % 16;
+    ix.norm_sq = norm_sq;
+    auto rl_raw = [&](int) { relayout_raw_kernel(ix, raw, 0, (uint32_t)n); };
+    cuda_emul::launch(rl_raw, 2, 256, smem_raw, 0, 0);
+    const int warps = 4;
+    const size_t smem = (size_t)warps * 8 * (ix.T + 4) * 4;
+    auto kern = [&](int) { exact_l2_kernel(ix, qT, coeffs, nq, ids, m, out); };
+    cuda_emul::launch(kern, (nq + warps - 1) / warps, warps * 32, smem_raw, smem, 0);
+    return 0;
+}

@@ -329,3 +329,26 @@ def test_exhaustive_kernel_sources_reproduce_the_reference_composition(k1, k5, o
         for i in range(len(q)):
             assert np.array_equal(ids[i], g[f"ids_{i}_k{k}_kp{kp}"]), (i, k, kp, nslices)
             assert np.array_equal(_bits(dists[i]), _bits(g[f"dists_{i}_k{k}_kp{kp}"])), (i, k, kp, nslices)
+
+
+@pytest.mark.parametrize("D", [16, 128, 1024])
+def test_exact_distance_kernel_source_against_the_reference_dot_products(k1, k3, oracle, D):
+    """K4 primitive: max(|q|^2 + |x|^2 - 2 dot(q, x), 0) (search/rabitq_search.hpp:88-93) with the reference's own
+    dot_product_simd values (l2_golden.npz) -- the eight accumulator chains and their reduction order."""
+    g = np.load(common.GOLDEN / "l2_golden.npz")
+    a, b = g[f"a_{D}"], g[f"b_{D}"]
+    _, coeffs, _, _, qT = _prepare(k1, oracle, a)
+    norm_sq = np.array([oracle.dot(x, x) for x in b], np.float32)
+    ids = np.tile(np.arange(6, dtype=np.uint32), (6, 1))
+    out = np.full((6, 6), np.nan, np.float32)
+    raw = np.ascontiguousarray(b, np.float32)
+    assert k3.emul_exact_l2(C.c_uint32(D), C.c_uint64(6), _p(raw, C.c_float), _p(norm_sq, C.c_float), _p(qT, C.c_float),
+                            _p(coeffs, C.c_float), C.c_uint32(6), _p(ids, C.c_uint32), C.c_uint32(6), _p(out, C.c_float)) == 0
+    for i in range(6):
+        qn = np.float32(oracle.dot(a[i], a[i]))
+        want = np.float32(np.float32(qn + norm_sq[i]) - np.float32(np.float32(2.0) * g[f"dot_{D}"][i]))
+        want = np.float32(0.0) if want < 0 else want
+        assert _bits(out[i, i:i + 1])[0] == _bits(np.array([want]))[0], i
+        for j in range(6):   # the other pairs against the oracle's dot
+            w = np.float32(np.float32(qn + norm_sq[j]) - np.float32(np.float32(2.0) * oracle.dot(a[i], b[j])))
+            assert _bits(out[i, j:j + 1])[0] == _bits(np.array([max(w, np.float32(0.0))]))[0], (i, j)
