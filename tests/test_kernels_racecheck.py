@@ -1,0 +1,67 @@
+"""Race check of the kernels' own source on the CPU (the analogue of compute-sanitizer's racecheck, without a GPU): the
+emulated harnesses of tests/native/ built with -fsanitize=thread.  Every CUDA thread is a host thread, __syncwarp /
+__syncthreads / the shuffles are barriers and the mbarrier stand-in is an acquire/release counter, so ThreadSanitizer sees
+exactly the happens-before edges the kernel's own synchronisation provides: a shared- or global-memory access pair that
+is not ordered by them is reported.  A self-test shows the check has teeth (a missing __syncwarp is found)."""
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+import common
+
+NATIVE = common.ROOT / "tests" / "native"
+
+
+def _libtsan():
+    r = subprocess.run(["g++", "-print-file-name=libtsan.so"], capture_output=True, text=True)
+    p = Path(r.stdout.strip())
+    return p if p.is_absolute() and p.exists() else None
+
+
+pytestmark = pytest.mark.skipif(_libtsan() is None, reason="libtsan not installed")
+
+
+@pytest.fixture(scope="module")
+def tsan_libs(tmp_path_factory):
+    out = tmp_path_factory.mktemp("tsan")
+    for name in ("race_probe", "query_prep_emul", "fastscan_emul", "search_emul", "exhaustive_emul", "neighbor_codes_emul"):
+        cmd = ["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
+               "-I/usr/local/cuda/include", "-I", str(NATIVE), str(NATIVE / f"{name}.cpp"), "-o", str(out / f"lib{name}.so")]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    return out
+
+
+def _races(tsan_libs, which, *extra):
+    env = dict(os.environ, LD_PRELOAD=str(_libtsan()), TSAN_OPTIONS="report_signal_unsafe=0 exitcode=0")
+    r = subprocess.run([sys.executable, str(NATIVE / "racecheck_driver.py"), which, str(tsan_libs), *map(str, extra)],
+                       capture_output=True, text=True, env=env, timeout=900)
+    assert "RESULTS_OK" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
+    sites = set()
+    for m in re.finditer(r"SUMMARY: ThreadSanitizer: data race (\S+):(\d+) in (.*)", r.stderr):
+        path = (NATIVE / m.group(1)).resolve() if not Path(m.group(1)).is_absolute() else Path(m.group(1))
+        line = path.read_text().splitlines()[int(m.group(2)) - 1].strip() if path.exists() else "?"
+        sites.add((path.name, line))
+    return sites
+
+
+def test_the_check_finds_a_missing_syncwarp(tsan_libs):
+    assert _races(tsan_libs, "probe", 1) == set()
+    assert any(name == "race_probe.cpp" for name, _ in _races(tsan_libs, "probe", 0))
+
+
+@pytest.mark.parametrize("which", ["k1", "k2", "k5", "n3"])
+def test_kernel_source_has_no_unordered_accesses(tsan_libs, which):
+    assert _races(tsan_libs, which) == set()
+
+
+def test_search_kernel_source_has_no_unordered_accesses(tsan_libs):
+    """K3.  The only reports are the two places in heap_pop where all 32 lanes of a warp store the same constant to the
+    warp's own state word (`last_valid = 0`): same value, same warp, no reader before the next warp barrier."""
+    sites = _races(tsan_libs, "k3")
+    benign = {s for s in sites if s[0] == "search.cu" and "w.ws->last_valid = 0u;" in s[1]}
+    assert sites - benign == set(), sites - benign
