@@ -22,7 +22,10 @@ def _libtsan():
     return p if p.is_absolute() and p.exists() else None
 
 
-pytestmark = pytest.mark.skipif(_libtsan() is None, reason="libtsan not installed")
+# Opt-in (CPHNSW_RACECHECK=1): instrumented runs of 256-thread blocks take minutes and their duration varies with the
+# host's load, so they stay out of the default CPU suite.
+pytestmark = pytest.mark.skipif(os.environ.get("CPHNSW_RACECHECK") != "1" or _libtsan() is None,
+                                reason="set CPHNSW_RACECHECK=1 (needs libtsan) to run the ThreadSanitizer race check")
 
 
 @pytest.fixture(scope="module")
