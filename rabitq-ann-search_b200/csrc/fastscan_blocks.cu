@@ -53,7 +53,7 @@ inline void fs_issue(void* dst, const void* src, uint32_t bytes, uint64_t* bar) 
     __atomic_fetch_add(bar, 1, __ATOMIC_RELEASE);
 }
 inline void fs_wait(uint64_t* bar, uint32_t phase) {
-    while ((__atomic_load_n(bar, __ATOMIC_ACQUIRE) & 1u) == phase) {}
+    while ((__atomic_load_n(bar, __ATOMIC_ACQUIRE) & 1u) == phase) std::this_thread::yield();
 }
 #endif
 

@@ -231,7 +231,7 @@ inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) 
     if (bar[1] == 0) __atomic_fetch_add(&bar[0], 1, __ATOMIC_RELEASE);
 }
 inline void mbar_wait(uint64_t* bar, uint32_t phase) {
-    while ((__atomic_load_n(&bar[0], __ATOMIC_ACQUIRE) & 1u) == phase) {}
+    while ((__atomic_load_n(&bar[0], __ATOMIC_ACQUIRE) & 1u) == phase) std::this_thread::yield();
 }
 inline void prefetch_l2(const void*) {}
 #endif
