@@ -76,6 +76,7 @@ typedef struct {
     uint64_t pops, expansions, exact_calls, beam_pushes, max_beam, nn_pushes;
     uint64_t lb_skips, gamma_terms, msb_skipped, estimated, descent_dists;
     uint64_t overflow_retries;  /* queries re-run with a larger frontier arena */
+    uint64_t kernel_launches;   /* kernels the call enqueued: K1, K3, and K3 again over the (usually empty) overflow list */
 } cphnsw_b200_stats;
 
 /* ---- lifetime: replaces PyIndexWrapper's unique_ptr<Index<...>> (src/bindings.cpp:39-75) ---- */
@@ -99,10 +100,24 @@ int cphnsw_b200_get_info(const cphnsw_b200_index* ix, cphnsw_b200_info* out);
  * (searches with k = 1, writes nothing). */
 int cphnsw_b200_search_batch(cphnsw_b200_index* ix, const float* queries, uint64_t nq, uint64_t k,
                              int64_t* ids, float* dists);
-/* Device buffers, asynchronous on `stream` unless a frontier arena overflows (then it
- * synchronises and re-runs the affected queries). */
+/* Device buffers; asynchronous: everything (K1, K3, and the re-run of any query whose frontier outgrew its
+ * arena) is enqueued on `stream` and the call returns without waiting for the device.  Results are ready in stream
+ * order.  Calls issued on different streams (or from different host threads) may overlap on the device: each works
+ * in its own lane of the handle (two lanes; a third call first waits for the oldest one), which is how the
+ * reference's concurrent-reader guarantee (Index::search takes a shared_lock and uses thread_local scratch,
+ * api/hnsw_index.hpp:172) is kept. */
 int cphnsw_b200_search_batch_device(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq,
                                     uint64_t k, int64_t* d_ids, float* d_dists, void* stream);
+/* search_batch in two halves, for callers that stream batches (src/bindings.cpp:177-218 has no counterpart: its
+ * OpenMP loop needs none).  submit copies the host queries in, enqueues the search and the copies of the results
+ * out on an internal stream and returns a ticket; wait blocks until that batch's ids/dists are in the host buffers.
+ * With two batches in flight the drain of one batch's persistent grid overlaps the start of the next.  For the
+ * copies to be asynchronous the host buffers should be page-locked.  The buffers must stay valid until wait. */
+int cphnsw_b200_search_batch_submit(cphnsw_b200_index* ix, const float* queries, uint64_t nq, uint64_t k,
+                                    int64_t* ids, float* dists, uint64_t* ticket);
+int cphnsw_b200_search_batch_wait(cphnsw_b200_index* ix, uint64_t ticket);
+/* Wait for every call in flight on this handle (all lanes); returns the first deferred error, if any. */
+int cphnsw_b200_synchronize(cphnsw_b200_index* ix);
 /* Counters of the last search_batch* call (synchronises). */
 int cphnsw_b200_last_stats(cphnsw_b200_index* ix, cphnsw_b200_stats* out);
 /* Device time of the kernels of the last search_batch* call, from CUDA events on the launching

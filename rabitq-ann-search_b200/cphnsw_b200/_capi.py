@@ -28,7 +28,7 @@ class Info(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "pops", "expansions", "exact_calls", "beam_pushes", "max_beam", "nn_pushes", "lb_skips",
-        "gamma_terms", "msb_skipped", "estimated", "descent_dists", "overflow_retries")]
+        "gamma_terms", "msb_skipped", "estimated", "descent_dists", "overflow_retries", "kernel_launches")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -58,6 +58,9 @@ SYMBOLS = {
     "cphnsw_b200_get_info": (C.c_int, [_P, C.POINTER(Info)]),
     "cphnsw_b200_search_batch": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P, _P]),
     "cphnsw_b200_search_batch_device": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P, _P, _P]),
+    "cphnsw_b200_search_batch_submit": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P, _P, C.POINTER(C.c_uint64)]),
+    "cphnsw_b200_search_batch_wait": (C.c_int, [_P, C.c_uint64]),
+    "cphnsw_b200_synchronize": (C.c_int, [_P]),
     "cphnsw_b200_last_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "cphnsw_b200_last_timings": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "cphnsw_b200_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),

@@ -158,13 +158,29 @@ class CPIndex:
         self._load_device(str(path))
 
     def _load_device(self, path: str) -> None:
-        _capi.check(self._h, self._lib.cphnsw_b200_load(self._h, path.encode()))
+        # Index::load validates before it commits anything (api/hnsw_index.hpp:305-443): read the header here, so a
+        # file made for another dim / bits is rejected while the device still holds the old index
+        try:
+            with open(path, "rb") as f:
+                hdr = f.read(68)
+        except OSError as e:
+            raise RuntimeError(f"Cannot open file for reading: {path}") from e
+        if len(hdr) == 68 and int.from_bytes(hdr[0:8], "little") == 0x57534E48504300 and int.from_bytes(hdr[8:12], "little") == 2:
+            fbits, fdim = int.from_bytes(hdr[20:24], "little"), int.from_bytes(hdr[24:28], "little")
+            if fdim != self._dim or fbits != self._bits:
+                raise RuntimeError(
+                    f"Parameter mismatch: file has dim={fdim}, bits={fbits}; index was created with "
+                    f"dim={self._dim}, bits={self._bits}.")
+        # (anything else -- magic, version, truncation -- is the native loader's to report, with the reference's messages)
+        rc = self._lib.cphnsw_b200_load(self._h, path.encode())
         info = _capi.Info()
-        _capi.check(self._h, self._lib.cphnsw_b200_get_info(self._h, C.byref(info)))
-        if info.dim != self._dim or info.bits != self._bits:
-            raise RuntimeError(
-                f"Parameter mismatch: file has dim={info.dim}, bits={info.bits}; index was created with "
-                f"dim={self._dim}, bits={self._bits}.")
+        still = self._lib.cphnsw_b200_get_info(self._h, C.byref(info)) == _capi.OK
+        if rc != _capi.OK:
+            # the native loader validates the file before it lets go of the old index; if it failed later (during
+            # the upload) nothing is left on the device and the object says so
+            if not still:
+                self._finalized, self._info = False, None
+            _capi.check(self._h, rc)
         self._info = info
         self._source_path = path
         self._finalized = True
@@ -201,6 +217,58 @@ class CPIndex:
         _capi.check(self._h, self._lib.cphnsw_b200_search_batch(
             self._h, q.ctypes.data, nq, k, ids.ctypes.data, dists.ctypes.data))
         return ids, dists
+
+    # ---- the same call in two halves: keep two batches in flight ---------------------------------
+    def search_batch_submit(self, queries, k: int = 10, out=None):
+        """Enqueue `search_batch(queries, k)` and return a ticket; `search_batch_wait(ticket)` returns the
+        (ids, distances) numpy arrays.  Two batches may be in flight per index: the drain of one batch's kernel
+        then overlaps the start of the next (that tail is ~15 % of a 10k-query batch).  `queries` may be a numpy
+        array or a CPU torch tensor -- page-locked memory (``tensor.pin_memory()``) makes the copies asynchronous;
+        `out` = (ids, dists) numpy arrays / CPU tensors to fill instead of fresh ones."""
+        k = int(k)
+        if k < 0:
+            raise ValueError("k must be non-negative")
+        q = queries.detach().numpy() if _is_torch(queries) else np.asarray(queries)
+        if q.ndim != 2 or q.shape[1] != self._dim:
+            raise ValueError("queries must be a (n, dim) array")
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        nq = q.shape[0]
+        if out is None:
+            ids, dists = np.empty((nq, k), np.int64), np.empty((nq, k), np.float32)
+        else:
+            ids, dists = (o.numpy() if _is_torch(o) else o for o in out)
+            if ids.shape != (nq, k) or dists.shape != (nq, k) or ids.dtype != np.int64 or dists.dtype != np.float32 \
+                    or not ids.flags.c_contiguous or not dists.flags.c_contiguous:
+                raise ValueError("out must be C-contiguous (int64 [nq,k], float32 [nq,k]) arrays")
+        self._require_finalized()
+        t = C.c_uint64(0)
+        _capi.check(self._h, self._lib.cphnsw_b200_search_batch_submit(
+            self._h, q.ctypes.data, nq, k, ids.ctypes.data, dists.ctypes.data, C.byref(t)))
+        self._pending = getattr(self, "_pending", {})
+        self._pending[t.value] = (q, ids, dists)   # keeps the buffers alive until the wait
+        return t.value
+
+    def search_batch_wait(self, ticket: int):
+        q_ids_dists = getattr(self, "_pending", {}).pop(int(ticket), None)
+        if q_ids_dists is None:
+            raise ValueError("unknown ticket")
+        _capi.check(self._h, self._lib.cphnsw_b200_search_batch_wait(self._h, int(ticket)))
+        return q_ids_dists[1], q_ids_dists[2]
+
+    def search_batches(self, batches, k: int = 10):
+        """Generator over (ids, distances) of each array in `batches`, with two batches in flight."""
+        prev = None
+        for b in batches:
+            t = self.search_batch_submit(b, k)
+            if prev is not None:
+                yield self.search_batch_wait(prev)
+            prev = t
+        if prev is not None:
+            yield self.search_batch_wait(prev)
+
+    def synchronize(self) -> None:
+        """Wait for every call in flight on this index (device-tensor searches are asynchronous)."""
+        _capi.check(self._h, self._lib.cphnsw_b200_synchronize(self._h))
 
     def _search_batch_cuda(self, queries, k: int):
         import torch

@@ -1,6 +1,12 @@
 // C ABI of the library (include/cphnsw_b200.h): index hand-off (save-file v2 reader, upload and
 // re-layout), the search entry points and the kernel-level hooks.  Host-side glue only; the
 // kernels are in query_prep.cu, fastscan_blocks.cu, search.cu, exhaustive.cu, relayout.cu.
+//
+// Concurrency.  The index itself is read-only after upload; everything a call writes lives in a Lane
+// (device_index.h).  A call takes the next lane round-robin, enqueues its work and leaves the lane "in flight";
+// the lane's next user first waits for that work (one event) -- so calls never share scratch, two host threads
+// can search one handle at the same time (as with the reference: api/hnsw_index.hpp:172), and nothing in the
+// search path synchronises the host with the device except the entry points that return host data.
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -9,6 +15,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <new>
 #include <random>
 #include <string>
 #include <vector>
@@ -20,12 +27,16 @@ using namespace cpb;
 
 namespace {
 
-thread_local std::string g_create_error;
+thread_local std::string g_create_error;   // errors without a handle (create)
+thread_local std::string g_last_error;     // what cphnsw_b200_last_error hands out (a copy: the handle's string may change)
 
 int fail(cphnsw_b200_index* ix, int code, const std::string& msg) {
-    if (ix) ix->err = msg; else g_create_error = msg;
+    if (ix) { std::lock_guard<std::mutex> g(ix->mu); ix->err = msg; }
+    else g_create_error = msg;
     return code;
 }
+// same, for code that already holds ix->mu
+int fail_locked(cphnsw_b200_index* ix, int code, const std::string& msg) { ix->err = msg; return code; }
 
 #define CUDA_TRY(ix, expr)                                                                         \
     do {                                                                                           \
@@ -33,6 +44,33 @@ int fail(cphnsw_b200_index* ix, int code, const std::string& msg) {
         if (_e != cudaSuccess)                                                                     \
             return fail(ix, CPHNSW_B200_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
     } while (0)
+
+// No C++ exception crosses the C boundary (std::bad_alloc from a corrupt file's sizes, ...).
+template <class F>
+int guarded(cphnsw_b200_index* ix, F&& body) {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        return fail(ix, CPHNSW_B200_ENOMEM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(ix, CPHNSW_B200_ERUNTIME, std::string("internal error: ") + e.what());
+    } catch (...) {
+        return fail(ix, CPHNSW_B200_ERUNTIME, "internal error");
+    }
+}
+
+// The caller's current device is restored on every exit path (a process whose torch device differs from the
+// index's must not find it switched).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        err = prev == dev ? cudaSuccess : cudaSetDevice(dev);
+        if (prev == dev) prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 template <typename T>
 int dev_alloc(cphnsw_b200_index* ix, T** out, size_t count, bool zero = false) {
@@ -57,15 +95,125 @@ int dev_upload(cphnsw_b200_index* ix, const T** out, const T* host, size_t count
     return 0;
 }
 
+// ---- lanes ------------------------------------------------------------------------------------------
+void destroy_lane(Lane& L) {
+    if (L.scratch) cudaFree(L.scratch);
+    if (L.bitmaps) cudaFree(L.bitmaps);
+    if (L.qstate) cudaFree(L.qstate);
+    if (L.stage) cudaFree(L.stage);
+    if (L.d_counters) cudaFree(L.d_counters);   // d_stats lives in the same allocation
+    if (L.h_counters) cudaFreeHost(L.h_counters);
+    if (L.stream) cudaStreamDestroy(L.stream);
+    for (auto& e : L.ev) if (e) cudaEventDestroy(e);
+    if (L.done) cudaEventDestroy(L.done);
+    L = Lane{};
+}
+
+int create_lane(cphnsw_b200_index* ix, Lane& L) {
+    if (L.created) return 0;
+    bool bad = cudaMalloc(reinterpret_cast<void**>(&L.d_counters), 32 + sizeof(Stats)) != cudaSuccess ||   // one memset clears both
+               cudaMallocHost(reinterpret_cast<void**>(&L.h_counters), 32) != cudaSuccess ||
+               cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess ||
+               cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming) != cudaSuccess;
+    for (auto& e : L.ev) bad = bad || cudaEventCreate(&e) != cudaSuccess;
+    if (bad) { cudaGetLastError(); destroy_lane(L); return fail(ix, CPHNSW_B200_ECUDA, "could not allocate the control buffers of a lane"); }
+    std::memset(L.h_counters, 0, 32);
+    L.d_stats = reinterpret_cast<Stats*>(L.d_counters + 8);
+    cudaMemset(L.d_counters, 0, 32 + sizeof(Stats));
+    L.created = true;
+    return 0;
+}
+
+// Wait for the lane's in-flight work and fold its deferred outcome (overflow counters) into the lane.  The caller
+// holds the lane (state 1).
+int finish_lane(cphnsw_b200_index* ix, Lane& L) {
+    if (!L.created) return 0;
+    cudaError_t e = cudaEventSynchronize(L.done);
+    if (e != cudaSuccess) {
+        L.status = CPHNSW_B200_ECUDA; L.status_msg = std::string("search: ") + cudaGetErrorString(e);
+        L.counters_pending = false;
+        return fail(ix, L.status, L.status_msg);
+    }
+    if (L.counters_pending) {
+        L.counters_pending = false;
+        L.overflow_retries = L.h_counters[1];
+        if (L.h_counters[3] != 0) {
+            L.status = CPHNSW_B200_ERUNTIME; L.status_msg = "internal error: frontier overflow with a full-size arena";
+            return fail(ix, L.status, L.status_msg);
+        }
+    }
+    return 0;
+}
+
+// Take the next lane (round-robin).  If its previous call is still in flight, wait for it first: a deferred error of
+// that call is reported here, once.
+int acquire_lane(cphnsw_b200_index* ix, Lane** out) {
+    int li;
+    bool inflight;
+    {
+        std::unique_lock<std::mutex> lk(ix->mu);
+        li = (int)(ix->next_lane++ % kLanes);
+        ix->cv.wait(lk, [&] { return ix->lanes[li].state != 1; });
+        inflight = ix->lanes[li].state == 2;
+        ix->lanes[li].state = 1;
+    }
+    Lane& L = ix->lanes[li];
+    int rc = create_lane(ix, L);
+    if (rc == 0 && inflight) rc = finish_lane(ix, L);
+    if (rc) {
+        std::lock_guard<std::mutex> g(ix->mu);
+        L.state = 0; L.status = 0;
+        ix->cv.notify_all();
+        return rc;
+    }
+    L.status = 0;
+    L.timed = false;
+    *out = &L;
+    return 0;
+}
+
+// Hand the lane back.  inflight: work was enqueued and `done` recorded on its stream.
+void release_lane(cphnsw_b200_index* ix, Lane* L, bool inflight, bool is_search = false) {
+    std::lock_guard<std::mutex> g(ix->mu);
+    L->state = inflight ? 2 : 0;
+    if (is_search) ix->last_lane = (int)(L - ix->lanes);
+    ix->cv.notify_all();
+}
+
+// Every lane idle (state 0), all deferred outcomes folded in.  Returns the first deferred error.
+int drain_lanes(cphnsw_b200_index* ix) {
+    int first = 0;
+    for (int i = 0; i < kLanes; ++i) {
+        Lane& L = ix->lanes[i];
+        bool inflight;
+        {
+            std::unique_lock<std::mutex> lk(ix->mu);
+            ix->cv.wait(lk, [&] { return L.state != 1; });
+            inflight = L.state == 2;
+            if (inflight) L.state = 1;
+        }
+        if (!inflight) continue;
+        const int rc = finish_lane(ix, L);
+        if (rc && !first) first = rc;
+        std::lock_guard<std::mutex> g(ix->mu);
+        L.state = 0;
+        ix->cv.notify_all();
+    }
+    return first;
+}
+
 void release_index(cphnsw_b200_index* ix) {
+    drain_lanes(ix);
     for (void* p : ix->allocs) cudaFree(p);
     ix->allocs.clear();
     ix->device_bytes = 0;
     ix->loaded = false;
     ix->dev = DevIndex{};
     ix->frontier_budget = 0;
-    // the bitmap arena is laid out for one n
-    if (ix->bitmaps) { cudaFree(ix->bitmaps); ix->bitmaps = nullptr; ix->bitmaps_bytes = 0; }
+    ix->occ_key[0] = 0;
+    // the bitmap arenas are laid out for one n
+    for (auto& L : ix->lanes)
+        if (L.bitmaps) { cudaFree(L.bitmaps); L.bitmaps = nullptr; L.bitmaps_bytes = 0; }
 }
 
 uint32_t next_pow2(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
@@ -109,14 +257,14 @@ int ensure_buffer(cphnsw_b200_index* ix, void** buf, size_t* have, size_t want, 
 
 struct QStateView { float* qT; uint32_t* uplanes; float* coeffs; uint8_t* ubytes; };
 
-int ensure_qstate(cphnsw_b200_index* ix, uint64_t nq, QStateView* v) {
+int ensure_qstate(cphnsw_b200_index* ix, Lane& L, uint64_t nq, QStateView* v) {
     const DevIndex& d = ix->dev;
     const size_t qT = (size_t)nq * d.D * 4, up = (size_t)nq * 16 * d.nch * 4, co = (size_t)nq * kCoeffStride * 4;
     const size_t a = (qT + 255) & ~(size_t)255, b = (up + 255) & ~(size_t)255, c = (co + 255) & ~(size_t)255;
     const size_t ub = (size_t)nq * d.nch * 128;
-    int rc = ensure_buffer(ix, &ix->qstate, &ix->qstate_bytes, a + b + c + ub + 256, false);
+    int rc = ensure_buffer(ix, &L.qstate, &L.qstate_bytes, a + b + c + ub + 256, false);
     if (rc) return rc;
-    uint8_t* p = static_cast<uint8_t*>(ix->qstate);
+    uint8_t* p = static_cast<uint8_t*>(L.qstate);
     v->qT = reinterpret_cast<float*>(p);
     v->uplanes = reinterpret_cast<uint32_t*>(p + a);
     v->coeffs = reinterpret_cast<float*>(p + a + b);
@@ -127,9 +275,23 @@ int ensure_qstate(cphnsw_b200_index* ix, uint64_t nq, QStateView* v) {
 int require_loaded(cphnsw_b200_index* ix) {
     if (!ix) return fail(nullptr, CPHNSW_B200_EINVAL, "null index handle");
     if (!ix->loaded) return fail(ix, CPHNSW_B200_ERUNTIME, "Index has no finalized data on the device (load or upload first).");
-    cudaError_t e = cudaSetDevice(ix->device);
-    if (e != cudaSuccess) return fail(ix, CPHNSW_B200_ECUDA, cudaGetErrorString(e));
     return 0;
+}
+
+// A call that works in a lane: device guard, lane acquisition, `body(lane)` enqueues on `stream`, then the lane is
+// left in flight behind an event on that stream.
+template <class F>
+int with_lane(cphnsw_b200_index* ix, cudaStream_t stream, bool is_search, F&& body) {
+    DeviceGuard dg(ix->device);
+    if (dg.err != cudaSuccess) return fail(ix, CPHNSW_B200_ECUDA, cudaGetErrorString(dg.err));
+    Lane* L = nullptr;
+    int rc = acquire_lane(ix, &L);
+    if (rc) return rc;
+    rc = guarded(ix, [&] { return body(*L); });
+    const bool recorded = cudaEventRecord(L->done, stream) == cudaSuccess;
+    if (!recorded) cudaGetLastError();
+    release_lane(ix, L, recorded, is_search && rc == 0);
+    return rc;
 }
 
 }  // namespace
@@ -138,52 +300,55 @@ extern "C" {
 
 int cphnsw_b200_create(int device, cphnsw_b200_index** out) {
     if (!out) return fail(nullptr, CPHNSW_B200_EINVAL, "out is null");
-    int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0)
-        return fail(nullptr, CPHNSW_B200_ECUDA,
-                    std::string("no CUDA device: this library has no CPU path (") + cudaGetErrorString(e) + ")");
-    if (device < 0 || device >= ndev) return fail(nullptr, CPHNSW_B200_EINVAL, "device ordinal out of range");
-    e = cudaSetDevice(device);
-    if (e != cudaSuccess) return fail(nullptr, CPHNSW_B200_ECUDA, cudaGetErrorString(e));
-    cudaDeviceProp prop;
-    e = cudaGetDeviceProperties(&prop, device);
-    if (e != cudaSuccess) return fail(nullptr, CPHNSW_B200_ECUDA, cudaGetErrorString(e));
-    if (prop.major != 10)
-        return fail(nullptr, CPHNSW_B200_ECUDA, "this build carries sm_100a code only (B200); found sm_" +
-                                                    std::to_string(prop.major) + std::to_string(prop.minor));
-    auto* ix = new cphnsw_b200_index();
-    ix->device = device;
-    ix->num_sms = prop.multiProcessorCount;
-    if (cudaMalloc(reinterpret_cast<void**>(&ix->d_stats), sizeof(Stats)) != cudaSuccess ||
-        cudaMalloc(reinterpret_cast<void**>(&ix->d_counters), 16) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        [&] { for (auto& e : ix->ev) if (cudaEventCreate(&e) != cudaSuccess) return true; return false; }()) {
-        delete ix;
-        return fail(nullptr, CPHNSW_B200_ECUDA, "could not allocate control buffers");
-    }
-    *out = ix;
-    return 0;
+    return guarded(nullptr, [&]() -> int {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            return fail(nullptr, CPHNSW_B200_ECUDA,
+                        std::string("no CUDA device: this library has no CPU path (") + cudaGetErrorString(e) + ")");
+        if (device < 0 || device >= ndev) return fail(nullptr, CPHNSW_B200_EINVAL, "device ordinal out of range");
+        DeviceGuard dg(device);
+        if (dg.err != cudaSuccess) return fail(nullptr, CPHNSW_B200_ECUDA, cudaGetErrorString(dg.err));
+        cudaDeviceProp prop;
+        e = cudaGetDeviceProperties(&prop, device);
+        if (e != cudaSuccess) return fail(nullptr, CPHNSW_B200_ECUDA, cudaGetErrorString(e));
+        if (prop.major != 10)
+            return fail(nullptr, CPHNSW_B200_ECUDA, "this build carries sm_100a code only (B200); found sm_" +
+                                                        std::to_string(prop.major) + std::to_string(prop.minor));
+        auto* ix = new cphnsw_b200_index();
+        ix->device = device;
+        ix->num_sms = prop.multiProcessorCount;
+        if (cudaMalloc(reinterpret_cast<void**>(&ix->d_problems), 16) != cudaSuccess) {
+            delete ix;
+            return fail(nullptr, CPHNSW_B200_ECUDA, "could not allocate control buffers");
+        }
+        *out = ix;
+        return 0;
+    });
 }
 
 void cphnsw_b200_destroy(cphnsw_b200_index* ix) {
     if (!ix) return;
-    cudaSetDevice(ix->device);
-    release_index(ix);
-    if (ix->scratch) cudaFree(ix->scratch);
-    if (ix->bitmaps) cudaFree(ix->bitmaps);
-    if (ix->qstate) cudaFree(ix->qstate);
-    if (ix->stage) cudaFree(ix->stage);
-    if (ix->d_stats) cudaFree(ix->d_stats);
-    if (ix->d_counters) cudaFree(ix->d_counters);
-    if (ix->enc_signs) cudaFree(ix->enc_signs);
-    if (ix->enc_scratch) cudaFree(ix->enc_scratch);
-    if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
-    for (auto& e : ix->ev) if (e) cudaEventDestroy(e);
+    try {
+        DeviceGuard dg(ix->device);
+        release_index(ix);
+        for (auto& L : ix->lanes) destroy_lane(L);
+        if (ix->d_problems) cudaFree(ix->d_problems);
+        if (ix->enc_signs) cudaFree(ix->enc_signs);
+        if (ix->enc_scratch) cudaFree(ix->enc_scratch);
+        if (ix->enc_done) cudaEventDestroy(ix->enc_done);
+    } catch (...) {
+    }
     delete ix;
 }
 
-const char* cphnsw_b200_last_error(const cphnsw_b200_index* ix) { return ix ? ix->err.c_str() : g_create_error.c_str(); }
+const char* cphnsw_b200_last_error(const cphnsw_b200_index* ix) {
+    if (!ix) return g_create_error.c_str();
+    auto* m = const_cast<cphnsw_b200_index*>(ix);
+    std::lock_guard<std::mutex> g(m->mu);
+    g_last_error = ix->err;
+    return g_last_error.c_str();
+}
 
 int cphnsw_b200_set_option(cphnsw_b200_index* ix, const char* name, int64_t value) {
     if (!ix || !name) return fail(ix, CPHNSW_B200_EINVAL, "null argument");
@@ -198,9 +363,9 @@ int cphnsw_b200_set_option(cphnsw_b200_index* ix, const char* name, int64_t valu
     return 0;
 }
 
-int cphnsw_b200_upload(cphnsw_b200_index* ix, const cphnsw_b200_host_index* h) {
-    if (!ix || !h) return fail(ix, CPHNSW_B200_EINVAL, "null argument");
-    CUDA_TRY(ix, cudaSetDevice(ix->device));
+static int upload_impl(cphnsw_b200_index* ix, const cphnsw_b200_host_index* h) {
+    DeviceGuard dg(ix->device);
+    CUDA_TRY(ix, dg.err);
     // the factory's checks (src/bindings.cpp:77-113)
     if (h->bits != 1 && h->bits != 2 && h->bits != 4)
         return fail(ix, CPHNSW_B200_EINVAL, "Unsupported bits=" + std::to_string(h->bits) + ". Supported: 1, 2, 4.");
@@ -287,7 +452,7 @@ int cphnsw_b200_upload(cphnsw_b200_index* ix, const cphnsw_b200_host_index* h) {
 
     // records and raw vectors: copy as they are, re-lay out on the device
     ix->dev = d;
-    CUDA_TRY(ix, cudaMemset(ix->d_counters, 0, 16));
+    CUDA_TRY(ix, cudaMemset(ix->d_problems, 0, 16));
     const size_t chunk_bytes = (size_t)256 << 20;
     void* stage = nullptr;
     CUDA_TRY(ix, cudaMalloc(&stage, chunk_bytes));
@@ -297,7 +462,7 @@ int cphnsw_b200_upload(cphnsw_b200_index* ix, const cphnsw_b200_host_index* h) {
         for (uint64_t first = 0; first < d.n; first += per) {
             const uint32_t cnt = (uint32_t)std::min<uint64_t>(per, d.n - first);
             cudaError_t e = cudaMemcpy(stage, h->search_data + first * h->rec_size, (size_t)cnt * h->rec_size, cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) e = launch_relayout_blocks(d, static_cast<const uint8_t*>(stage), h->rec_size, h->nb_off, first, cnt, ix->d_counters + 2, 0);
+            if (e == cudaSuccess) e = launch_relayout_blocks(d, static_cast<const uint8_t*>(stage), h->rec_size, h->nb_off, first, cnt, ix->d_problems + 2, 0);
             if (e == cudaSuccess) e = cudaDeviceSynchronize();
             if (e != cudaSuccess) return cleanup(fail(ix, CPHNSW_B200_ECUDA, std::string("re-layout of neighbour blocks: ") + cudaGetErrorString(e)));
         }
@@ -312,15 +477,19 @@ int cphnsw_b200_upload(cphnsw_b200_index* ix, const cphnsw_b200_host_index* h) {
     }
     cudaFree(stage);
     uint32_t problems[4] = {0, 0, 0, 0};
-    CUDA_TRY(ix, cudaMemcpy(problems, ix->d_counters, 16, cudaMemcpyDeviceToHost));
+    CUDA_TRY(ix, cudaMemcpy(problems, ix->d_problems, 16, cudaMemcpyDeviceToHost));
     if (problems[3]) { release_index(ix); return fail(ix, CPHNSW_B200_ERUNTIME, "Index is corrupt: neighbour id out of range in " + std::to_string(problems[3]) + " blocks."); }
     ix->dev.dup_neighbors = problems[2];
     ix->loaded = true;
     return 0;
 }
 
-int cphnsw_b200_load(cphnsw_b200_index* ix, const char* path) {
-    if (!ix || !path) return fail(ix, CPHNSW_B200_EINVAL, "null argument");
+int cphnsw_b200_upload(cphnsw_b200_index* ix, const cphnsw_b200_host_index* h) {
+    if (!ix || !h) return fail(ix, CPHNSW_B200_EINVAL, "null argument");
+    return guarded(ix, [&] { return upload_impl(ix, h); });
+}
+
+static int load_impl(cphnsw_b200_index* ix, const char* path) {
     const int fd = open(path, O_RDONLY);
     if (fd < 0) return fail(ix, CPHNSW_B200_ERUNTIME, std::string("Cannot open file for reading: ") + path);
     struct stat sb;
@@ -330,7 +499,8 @@ int cphnsw_b200_load(cphnsw_b200_index* ix, const char* path) {
     close(fd);
     if (map == MAP_FAILED) return fail(ix, CPHNSW_B200_ERUNTIME, "mmap of the index file failed");
     const uint8_t* p = static_cast<const uint8_t*>(map);
-    auto done = [&](int code) { munmap(map, fsize); return code; };
+    struct Unmap { void* p; size_t n; ~Unmap() { munmap(p, n); } } unmap{map, fsize};   // also when an exception unwinds
+    auto done = [](int code) { return code; };
 
     // header (api/hnsw_index.hpp:217-245)
     if (rd<uint64_t>(p, 0) != 0x57534E48504300ull) return done(fail(ix, CPHNSW_B200_ERUNTIME, "Invalid magic bytes (not a CP-HNSW index file)."));
@@ -352,8 +522,12 @@ int cphnsw_b200_load(cphnsw_b200_index* ix, const char* path) {
     h.calibration = p + off; off += 248 + 72;   // CalibrationSnapshot, IndexProfile
     h.nb_off = code_bytes(h.D, h.bits);
     h.rec_size = (uint64_t)h.nb_off + nb_bytes(h.D, h.bits);
+    // n comes from the file: bound it by what the file can hold before any size is computed from it (a vertex takes
+    // at least 8 + 4 D + rec_size bytes), so none of the products below can wrap
+    const uint64_t per_vertex = 8 + (uint64_t)4 * h.D + h.rec_size;
+    if (h.n == 0 || h.n >= 0xFFFFFFFFull || h.n > fsize / per_vertex) return done(fail(ix, CPHNSW_B200_ERUNTIME, "Index file is truncated."));
     const size_t need = off + (size_t)4 * h.dim + (size_t)8 * h.n + (size_t)4 * h.n * h.D + (size_t)h.n * h.rec_size + 4;
-    if (h.n == 0 || need > fsize) return done(fail(ix, CPHNSW_B200_ERUNTIME, "Index file is truncated."));
+    if (need > fsize) return done(fail(ix, CPHNSW_B200_ERUNTIME, "Index file is truncated."));
     h.centroid = reinterpret_cast<const float*>(p + off); off += (size_t)4 * h.dim;
     off += (size_t)4 * h.n;   // node_levels (build-time only)
     h.norm_sq = reinterpret_cast<const float*>(p + off); off += (size_t)4 * h.n;
@@ -365,6 +539,7 @@ int cphnsw_b200_load(cphnsw_b200_index* ix, const char* path) {
     for (uint32_t L = 0; L < n_layers; ++L) {
         if (off + 4 > fsize) return done(fail(ix, CPHNSW_B200_ERUNTIME, "Index file is truncated."));
         const uint32_t ne = rd<uint32_t>(p, off); off += 4;
+        if ((uint64_t)ne > (fsize - off) / 8) return done(fail(ix, CPHNSW_B200_ERUNTIME, "Index file is truncated."));   // 8 bytes per edge record at least
         nodes[L].reserve(ne); offs[L].reserve(ne + 1); offs[L].push_back(0);
         for (uint32_t e = 0; e < ne; ++e) {
             if (off + 8 > fsize) return done(fail(ix, CPHNSW_B200_ERUNTIME, "Index file is truncated."));
@@ -388,7 +563,12 @@ int cphnsw_b200_load(cphnsw_b200_index* ix, const char* path) {
     }
     h.n_layers = n_layers;
     h.layer_nodes = pn.data(); h.layer_offs = po.data(); h.layer_nbrs = pb.data(); h.layer_sizes = sizes.data();
-    return done(cphnsw_b200_upload(ix, &h));
+    return done(upload_impl(ix, &h));
+}
+
+int cphnsw_b200_load(cphnsw_b200_index* ix, const char* path) {
+    if (!ix || !path) return fail(ix, CPHNSW_B200_EINVAL, "null argument");
+    return guarded(ix, [&] { return load_impl(ix, path); });
 }
 
 int cphnsw_b200_get_info(const cphnsw_b200_index* ix, cphnsw_b200_info* out) {
@@ -409,7 +589,8 @@ int cphnsw_b200_get_info(const cphnsw_b200_index* ix, cphnsw_b200_info* out) {
 // ---------------------------------------------------------------------------------------------------
 // search
 // ---------------------------------------------------------------------------------------------------
-static int run_search(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq, uint64_t k_user, int64_t* d_ids,
+// Enqueue K1 + K3 (+ the overflow re-run) for one batch on `stream`, in lane L.  Nothing here waits for the device.
+static int run_search(cphnsw_b200_index* ix, Lane& L, const float* d_queries, uint64_t nq, uint64_t k_user, int64_t* d_ids,
                       float* d_dists, uint32_t* d_entry_out, cudaStream_t stream) {
     const DevIndex& d = ix->dev;
     if (nq == 0) return 0;
@@ -418,21 +599,26 @@ static int run_search(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq
     const uint32_t k = (uint32_t)std::max<uint64_t>(k_user, 1);   // hnsw_index.hpp:187
 
     QStateView qs;
-    int rc = ensure_qstate(ix, nq, &qs);
+    int rc = ensure_qstate(ix, L, nq, &qs);
     if (rc) return rc;
     PrepOut po{};
     po.coeffs = qs.coeffs; po.uplanes = qs.uplanes; po.qT = qs.qT;
-    CUDA_TRY(ix, cudaEventRecord(ix->ev[0], stream));
-    CUDA_TRY(ix, launch_query_prep(d, d_queries, (uint32_t)nq, 0, po, stream));
-    CUDA_TRY(ix, cudaEventRecord(ix->ev[1], stream));
 
-    // launch geometry: persistent grid, one warp per in-flight query; as much of the frontier heap in
-    // shared memory as still lets the requested number of warps reside
+    // launch geometry: persistent grid, one warp per in-flight query
     const bool stats = ix->collect_stats != 0;
     int warps = (int)ix->warps_per_cta;
     const size_t smem_budget = 220 * 1024;
-    while (warps > 1 && search_smem_per_warp(d, k) * warps > smem_budget) --warps;
-    int per_sm = search_max_ctas_per_sm(d, k, warps, stats);
+    const size_t spw = search_smem_per_warp(d, k);
+    while (warps > 1 && spw * warps > smem_budget) --warps;
+    int per_sm;
+    {   // the occupancy query costs tens of microseconds: once per (shared memory per warp, warps, stats)
+        std::lock_guard<std::mutex> g(ix->mu);
+        if (ix->occ_key[0] != (int)spw || ix->occ_key[1] != warps || ix->occ_key[2] != (int)stats) {
+            ix->occ_key[3] = search_max_ctas_per_sm(d, k, warps, stats);
+            ix->occ_key[0] = (int)spw; ix->occ_key[1] = warps; ix->occ_key[2] = (int)stats;
+        }
+        per_sm = ix->occ_key[3];
+    }
     if (per_sm <= 0) return fail(ix, CPHNSW_B200_ECUDA, "search kernel cannot be resident (shared memory / registers)");
     per_sm = std::min<int>(per_sm, (int)ix->ctas_per_sm);
     int ctas = ix->num_sms * per_sm;
@@ -457,83 +643,74 @@ static int run_search(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq
     a.nq = (uint32_t)nq; a.query_list = nullptr; a.k = k; a.kout = (uint32_t)k_user;
     a.ids = d_ids; a.dists = d_dists; a.qT = qs.qT; a.uplanes = qs.uplanes; a.coeffs = qs.coeffs;
     a.entry_out = d_entry_out;
-    // frontier arena per slot: the option if set, else as much as an 8 GiB (or an eighth of free HBM) budget
-    // gives every slot -- a frontier can hold at most n entries, and re-running an overflowed query
-    // throws its first attempt away, so be generous where memory allows (1-bit indexes reach 40k+)
+    // frontier arena per slot: the option if set, else as much as this lane's share of HBM (4 GiB, or a sixteenth of
+    // what is free) gives every slot -- a frontier can hold at most n entries, and a query whose frontier outgrows
+    // its arena is run again from scratch, so be generous where memory allows (1-bit indexes reach 40k+)
     const size_t slots = (size_t)ctas * warps;
     uint64_t cap64 = (uint64_t)ix->beam_capacity;
     if (cap64 == 0) {
+        std::lock_guard<std::mutex> g(ix->mu);
         if (ix->frontier_budget == 0) {   // once per index: the answer must not drift from call to call
             size_t free_b = 0, total_b = 0;
             cudaMemGetInfo(&free_b, &total_b);
-            ix->frontier_budget = std::min<size_t>((size_t)8 << 30, (free_b + ix->scratch_bytes) / 8);
+            size_t held = 0;
+            for (const auto& l : ix->lanes) held += l.scratch_bytes;
+            ix->frontier_budget = std::min<size_t>((size_t)4 << 30, (free_b + held) / (8 * kLanes));
         }
         cap64 = std::max<uint64_t>(4096, ix->frontier_budget / (slots * 16));
     }
-    uint32_t cap = (uint32_t)std::min<uint64_t>(cap64, d.n + 1);
+    const uint32_t cap_full = (uint32_t)d.n + 1;   // each id enters the frontier at most once: this cannot overflow
+    const uint32_t cap = (uint32_t)std::min<uint64_t>(cap64, cap_full);
     layout(cap, a);
+    // re-run of overflowed queries, enqueued behind the first pass with no host round trip: the same kernel over the
+    // device-side list of overflowed queries, with full-size arenas carved from the same scratch (the first pass is
+    // complete by then), as many slots as fit
+    const bool may_overflow = cap < cap_full && !d_entry_out;
+    SearchArgs b = a;
+    size_t rslots = 0;
+    if (may_overflow) layout(cap_full, b);
     const size_t list_bytes = ((size_t)nq * 4 + 255) & ~(size_t)255;
-    rc = ensure_buffer(ix, &ix->scratch, &ix->scratch_bytes, list_bytes + slots * a.slot_stride, false);
-    if (rc) return rc;
-    rc = ensure_buffer(ix, &ix->bitmaps, &ix->bitmaps_bytes, slots * (size_t)a.bitmap_words * 4, true);
-    if (rc) return rc;
-    a.bitmaps = static_cast<uint32_t*>(ix->bitmaps);
-    a.overflow_list = static_cast<uint32_t*>(ix->scratch);
-    a.scratch = static_cast<uint8_t*>(ix->scratch) + list_bytes;
-    a.counters = ix->d_counters;
-    a.stats = ix->d_stats;
-    CUDA_TRY(ix, cudaMemsetAsync(ix->d_counters, 0, 16, stream));
-    CUDA_TRY(ix, cudaMemsetAsync(ix->d_stats, 0, sizeof(Stats), stream));
-    CUDA_TRY(ix, cudaEventRecord(ix->ev[2], stream));
-    CUDA_TRY(ix, launch_search(d, a, ctas, warps, stats, stream));
-    CUDA_TRY(ix, cudaEventRecord(ix->ev[3], stream));
-
-    // frontier overflow: re-run those queries with an arena that cannot overflow (each id enters
-    // the frontier at most once, so n entries always suffice)
-    uint32_t counters[4];
-    CUDA_TRY(ix, cudaMemcpyAsync(counters, ix->d_counters, 16, cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(ix, cudaStreamSynchronize(stream));
-    ix->last_stats.overflow_retries = 0;
-    cudaEventElapsedTime(&ix->prep_ms, ix->ev[0], ix->ev[1]);
-    cudaEventElapsedTime(&ix->search_ms, ix->ev[2], ix->ev[3]);
-    if (counters[1] > 0) {
-        const uint32_t nover = counters[1];
-        std::vector<uint32_t> list(nover);
-        CUDA_TRY(ix, cudaMemcpy(list.data(), a.overflow_list, (size_t)nover * 4, cudaMemcpyDeviceToHost));
-        SearchArgs b = a;
-        layout((uint32_t)d.n + 1, b);
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        const size_t budget = std::max<size_t>(b.slot_stride, (free_b + ix->scratch_bytes) / 2);
-        size_t rslots = std::min<size_t>(nover, budget / b.slot_stride);
-        int rwarps = (int)std::min<size_t>(warps, rslots);
-        int rctas = (int)std::max<size_t>(1, rslots / rwarps);
-        rc = ensure_buffer(ix, &ix->scratch, &ix->scratch_bytes, list_bytes + (size_t)rctas * rwarps * b.slot_stride, false);
-        if (rc) return rc;
-        // the first pass left every bitmap clean, so the same bitmap arena serves the re-run
-        rc = ensure_buffer(ix, &ix->bitmaps, &ix->bitmaps_bytes, (size_t)rctas * rwarps * b.bitmap_words * 4, true);
-        if (rc) return rc;
-        b.bitmaps = static_cast<uint32_t*>(ix->bitmaps);
-        b.overflow_list = static_cast<uint32_t*>(ix->scratch);
-        b.scratch = static_cast<uint8_t*>(ix->scratch) + list_bytes;
-        uint32_t* d_list = nullptr;
-        CUDA_TRY(ix, cudaMalloc(reinterpret_cast<void**>(&d_list), (size_t)nover * 4));
-        cudaMemcpy(d_list, list.data(), (size_t)nover * 4, cudaMemcpyHostToDevice);
-        b.query_list = d_list; b.nq = nover;
-        cudaMemsetAsync(ix->d_counters, 0, 16, stream);
-        cudaEventRecord(ix->ev[4], stream);
-        cudaError_t e = launch_search(d, b, rctas, rwarps, stats, stream);
-        cudaEventRecord(ix->ev[5], stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(counters, ix->d_counters, 16, cudaMemcpyDeviceToHost, stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-        cudaFree(d_list);
-        if (e != cudaSuccess) return fail(ix, CPHNSW_B200_ECUDA, std::string("overflow re-run: ") + cudaGetErrorString(e));
-        if (counters[1] != 0) return fail(ix, CPHNSW_B200_ERUNTIME, "internal error: frontier overflow with a full-size arena");
-        ix->last_stats.overflow_retries = nover;
-        float rerun_ms = 0.0f;
-        cudaEventElapsedTime(&rerun_ms, ix->ev[4], ix->ev[5]);
-        ix->search_ms += rerun_ms;
+    size_t arena_bytes = slots * a.slot_stride;
+    if (may_overflow) {
+        arena_bytes = std::max(arena_bytes, b.slot_stride);
+        rslots = std::min<size_t>({arena_bytes / b.slot_stride, (size_t)256, (size_t)nq});
     }
+    rc = ensure_buffer(ix, &L.scratch, &L.scratch_bytes, 2 * list_bytes + arena_bytes, false);
+    if (rc) return rc;
+    int rwarps = 0, rctas = 0;
+    if (may_overflow) {
+        rwarps = (int)std::min<size_t>(warps, rslots);
+        rctas = (int)std::max<size_t>(1, rslots / rwarps);
+        rslots = (size_t)rwarps * rctas;
+    }
+    rc = ensure_buffer(ix, &L.bitmaps, &L.bitmaps_bytes, std::max(slots, rslots) * (size_t)a.bitmap_words * 4, true);
+    if (rc) return rc;
+    a.bitmaps = static_cast<uint32_t*>(L.bitmaps);
+    a.overflow_list = static_cast<uint32_t*>(L.scratch);
+    a.scratch = static_cast<uint8_t*>(L.scratch) + 2 * list_bytes;
+    a.counters = L.d_counters;
+    a.stats = L.d_stats;
+    CUDA_TRY(ix, cudaMemsetAsync(L.d_counters, 0, 32 + sizeof(Stats), stream));
+    CUDA_TRY(ix, cudaEventRecord(L.ev[0], stream));
+    CUDA_TRY(ix, launch_query_prep(d, d_queries, (uint32_t)nq, 0, po, stream));
+    CUDA_TRY(ix, cudaEventRecord(L.ev[1], stream));
+    CUDA_TRY(ix, cudaEventRecord(L.ev[2], stream));
+    CUDA_TRY(ix, launch_search(d, a, ctas, warps, stats, stream));
+    if (may_overflow) {
+        b.bitmaps = a.bitmaps;   // the first pass leaves every bitmap clean
+        b.scratch = a.scratch;
+        b.query_list = a.overflow_list;                                   // what the first pass listed ...
+        b.nq_ptr = L.d_counters + 1;                                      // ... and how many
+        b.nq = (uint32_t)nq;
+        b.overflow_list = a.overflow_list + list_bytes / 4;               // (cannot happen; checked when the lane is next used)
+        b.counters = L.d_counters + 2;
+        CUDA_TRY(ix, launch_search(d, b, rctas, rwarps, stats, stream));
+    }
+    CUDA_TRY(ix, cudaEventRecord(L.ev[3], stream));
+    CUDA_TRY(ix, cudaMemcpyAsync(L.h_counters, L.d_counters, 32, cudaMemcpyDeviceToHost, stream));
+    L.counters_pending = true;
+    L.timed = true;
+    L.launches = 2 + (may_overflow ? 1 : 0);
     return 0;
 }
 
@@ -542,7 +719,73 @@ int cphnsw_b200_search_batch_device(cphnsw_b200_index* ix, const float* d_querie
     int rc = require_loaded(ix);
     if (rc) return rc;
     if (nq && (!d_queries || (k && (!d_ids || !d_dists)))) return fail(ix, CPHNSW_B200_EINVAL, "null buffer");
-    return run_search(ix, d_queries, nq, k, d_ids, d_dists, nullptr, static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return with_lane(ix, st, true, [&](Lane& L) { return run_search(ix, L, d_queries, nq, k, d_ids, d_dists, nullptr, st); });
+}
+
+// Host buffers -> lane staging -> K1/K3 -> host buffers, all on the lane's own stream; returns with the lane held.
+static int enqueue_host_search(cphnsw_b200_index* ix, Lane& L, const float* queries, uint64_t nq, uint64_t k, int64_t* ids,
+                               float* dists) {
+    const DevIndex& d = ix->dev;
+    const size_t qb = ((size_t)nq * d.dim * 4 + 255) & ~(size_t)255, ib = ((size_t)nq * k * 8 + 255) & ~(size_t)255,
+                 db = (size_t)nq * k * 4;
+    int rc = ensure_buffer(ix, &L.stage, &L.stage_bytes, qb + ib + db + 256, false);
+    if (rc) return rc;
+    uint8_t* s = static_cast<uint8_t*>(L.stage);
+    float* d_q = reinterpret_cast<float*>(s);
+    int64_t* d_i = reinterpret_cast<int64_t*>(s + qb);
+    float* d_d = reinterpret_cast<float*>(s + qb + ib);
+    cudaStream_t st = L.stream;
+    CUDA_TRY(ix, cudaMemcpyAsync(d_q, queries, (size_t)nq * d.dim * 4, cudaMemcpyHostToDevice, st));
+    rc = run_search(ix, L, d_q, nq, k, d_i, d_d, nullptr, st);
+    if (rc) return rc;
+    if (k) {
+        CUDA_TRY(ix, cudaMemcpyAsync(ids, d_i, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ix, cudaMemcpyAsync(dists, d_d, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+    }
+    return 0;
+}
+
+int cphnsw_b200_search_batch_submit(cphnsw_b200_index* ix, const float* queries, uint64_t nq, uint64_t k, int64_t* ids,
+                                    float* dists, uint64_t* ticket) {
+    int rc = require_loaded(ix);
+    if (rc) return rc;
+    if (!ticket) return fail(ix, CPHNSW_B200_EINVAL, "null argument");
+    if (nq && (!queries || (k && (!ids || !dists)))) return fail(ix, CPHNSW_B200_EINVAL, "null buffer");
+    DeviceGuard dg(ix->device);
+    CUDA_TRY(ix, dg.err);
+    Lane* L = nullptr;
+    rc = acquire_lane(ix, &L);
+    if (rc) return rc;
+    rc = nq ? guarded(ix, [&] { return enqueue_host_search(ix, *L, queries, nq, k, ids, dists); }) : 0;
+    const bool recorded = cudaEventRecord(L->done, L->stream) == cudaSuccess;
+    {
+        std::lock_guard<std::mutex> g(ix->mu);
+        L->ticket = ++ix->next_ticket;
+        *ticket = L->ticket;
+        L->state = recorded ? 2 : 0;
+        if (rc == 0) ix->last_lane = (int)(L - ix->lanes);
+        ix->cv.notify_all();
+    }
+    return rc;
+}
+
+int cphnsw_b200_search_batch_wait(cphnsw_b200_index* ix, uint64_t ticket) {
+    if (!ix) return fail(nullptr, CPHNSW_B200_EINVAL, "null index handle");
+    Lane* L = nullptr;
+    {
+        std::unique_lock<std::mutex> lk(ix->mu);
+        if (ticket == 0 || ticket > ix->next_ticket) return fail_locked(ix, CPHNSW_B200_EINVAL, "unknown ticket");
+        for (auto& l : ix->lanes) if (l.ticket == ticket) L = &l;
+        if (!L) return 0;   // its lane has been reused since: that user waited for it (and reported its outcome)
+        ix->cv.wait(lk, [&] { return L->state != 1 || L->ticket != ticket; });
+        if (L->ticket != ticket || L->state == 0) return L->ticket == ticket ? L->status : 0;
+        L->state = 1;
+    }
+    DeviceGuard dg(ix->device);
+    const int rc = finish_lane(ix, *L);
+    release_lane(ix, L, false);
+    return rc;
 }
 
 int cphnsw_b200_search_batch(cphnsw_b200_index* ix, const float* queries, uint64_t nq, uint64_t k, int64_t* ids,
@@ -550,32 +793,49 @@ int cphnsw_b200_search_batch(cphnsw_b200_index* ix, const float* queries, uint64
     int rc = require_loaded(ix);
     if (rc) return rc;
     if (nq == 0) return 0;
-    if (!queries || (k && (!ids || !dists))) return fail(ix, CPHNSW_B200_EINVAL, "null buffer");
-    const DevIndex& d = ix->dev;
-    const size_t qb = ((size_t)nq * d.dim * 4 + 255) & ~(size_t)255, ib = ((size_t)nq * k * 8 + 255) & ~(size_t)255,
-                 db = (size_t)nq * k * 4;
-    rc = ensure_buffer(ix, &ix->stage, &ix->stage_bytes, qb + ib + db + 256, false);
-    if (rc) return rc;
-    uint8_t* s = static_cast<uint8_t*>(ix->stage);
-    float* d_q = reinterpret_cast<float*>(s);
-    int64_t* d_i = reinterpret_cast<int64_t*>(s + qb);
-    float* d_d = reinterpret_cast<float*>(s + qb + ib);
-    cudaStream_t st = ix->own_stream;
-    CUDA_TRY(ix, cudaMemcpyAsync(d_q, queries, (size_t)nq * d.dim * 4, cudaMemcpyHostToDevice, st));
-    rc = run_search(ix, d_q, nq, k, d_i, d_d, nullptr, st);
-    if (rc) return rc;
-    if (k) {
-        CUDA_TRY(ix, cudaMemcpyAsync(ids, d_i, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(ix, cudaMemcpyAsync(dists, d_d, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
-    }
-    CUDA_TRY(ix, cudaStreamSynchronize(st));
+    uint64_t ticket = 0;
+    rc = cphnsw_b200_search_batch_submit(ix, queries, nq, k, ids, dists, &ticket);
+    const int rw = ticket ? cphnsw_b200_search_batch_wait(ix, ticket) : 0;
+    return rc ? rc : rw;
+}
+
+int cphnsw_b200_synchronize(cphnsw_b200_index* ix) {
+    if (!ix) return fail(nullptr, CPHNSW_B200_EINVAL, "null index handle");
+    DeviceGuard dg(ix->device);
+    CUDA_TRY(ix, dg.err);
+    return drain_lanes(ix);
+}
+
+// The lane of the most recent search, idle (its deferred outcome folded in), held by the caller.
+static int hold_last_lane(cphnsw_b200_index* ix, Lane** out) {
+    std::unique_lock<std::mutex> lk(ix->mu);
+    if (ix->last_lane < 0) return fail_locked(ix, CPHNSW_B200_ERUNTIME, "no search has run on this handle yet");
+    Lane& L = ix->lanes[ix->last_lane];
+    ix->cv.wait(lk, [&] { return L.state != 1; });
+    const bool inflight = L.state == 2;
+    L.state = 1;
+    lk.unlock();
+    int rc = inflight ? finish_lane(ix, L) : 0;
+    if (rc) { release_lane(ix, &L, false); return rc; }
+    *out = &L;
     return 0;
 }
 
 int cphnsw_b200_last_timings(cphnsw_b200_index* ix, float* prep_ms, float* search_ms) {
     if (!ix) return CPHNSW_B200_EINVAL;
-    if (prep_ms) *prep_ms = ix->prep_ms;
-    if (search_ms) *search_ms = ix->search_ms;
+    DeviceGuard dg(ix->device);
+    Lane* L = nullptr;
+    int rc = hold_last_lane(ix, &L);
+    if (rc) return rc;
+    float p = 0.0f, s = 0.0f;
+    if (L->timed) {
+        cudaEventSynchronize(L->ev[3]);
+        cudaEventElapsedTime(&p, L->ev[0], L->ev[1]);
+        cudaEventElapsedTime(&s, L->ev[2], L->ev[3]);
+    }
+    release_lane(ix, L, false);
+    if (prep_ms) *prep_ms = p;
+    if (search_ms) *search_ms = s;
     return 0;
 }
 
@@ -583,14 +843,19 @@ int cphnsw_b200_last_stats(cphnsw_b200_index* ix, cphnsw_b200_stats* out) {
     int rc = require_loaded(ix);
     if (rc) return rc;
     if (!out) return fail(ix, CPHNSW_B200_EINVAL, "null argument");
+    DeviceGuard dg(ix->device);
+    Lane* L = nullptr;
+    rc = hold_last_lane(ix, &L);
+    if (rc) return rc;
     Stats s;
-    CUDA_TRY(ix, cudaDeviceSynchronize());
-    CUDA_TRY(ix, cudaMemcpy(&s, ix->d_stats, sizeof(s), cudaMemcpyDeviceToHost));
-    const uint64_t retries = ix->last_stats.overflow_retries;
+    const cudaError_t e = cudaMemcpy(&s, L->d_stats, sizeof(s), cudaMemcpyDeviceToHost);
+    const uint64_t retries = L->overflow_retries, launches = L->launches;
+    release_lane(ix, L, false);
+    if (e != cudaSuccess) return fail(ix, CPHNSW_B200_ECUDA, cudaGetErrorString(e));
     out->pops = s.pops; out->expansions = s.expansions; out->exact_calls = s.exact_calls;
     out->beam_pushes = s.beam_pushes; out->max_beam = s.max_beam; out->nn_pushes = s.nn_pushes;
     out->lb_skips = s.lb_skips; out->gamma_terms = s.gamma_terms; out->msb_skipped = s.msb_skipped;
-    out->estimated = s.estimated; out->descent_dists = s.descent_dists; out->overflow_retries = retries;
+    out->estimated = s.estimated; out->descent_dists = s.descent_dists; out->overflow_retries = retries; out->kernel_launches = launches;
     return 0;
 }
 
@@ -603,17 +868,19 @@ int cphnsw_b200_prepare_queries(cphnsw_b200_index* ix, const float* d_queries, u
     if (rc) return rc;
     if (nq == 0) return 0;
     if (!d_queries) return fail(ix, CPHNSW_B200_EINVAL, "null buffer");
-    // the hook's coeffs are [nq][3]; the kernels' own stride is kCoeffStride, so go through qstate
-    QStateView qs;
-    rc = ensure_qstate(ix, nq, &qs);
-    if (rc) return rc;
-    PrepOut po{};
-    po.lut = d_lut; po.coeffs = qs.coeffs; po.rotated = d_rotated; po.uplanes = d_uplanes; po.qT = nullptr;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CUDA_TRY(ix, launch_query_prep(ix->dev, d_queries, (uint32_t)nq, center, po, st));
-    if (d_coeffs)
-        CUDA_TRY(ix, cudaMemcpy2DAsync(d_coeffs, 12, qs.coeffs, kCoeffStride * 4, 12, nq, cudaMemcpyDeviceToDevice, st));
-    return 0;
+    return with_lane(ix, st, false, [&](Lane& L) -> int {
+        // the hook's coeffs are [nq][3]; the kernels' own stride is kCoeffStride, so go through qstate
+        QStateView qs;
+        int r = ensure_qstate(ix, L, nq, &qs);
+        if (r) return r;
+        PrepOut po{};
+        po.lut = d_lut; po.coeffs = qs.coeffs; po.rotated = d_rotated; po.uplanes = d_uplanes; po.qT = nullptr;
+        CUDA_TRY(ix, launch_query_prep(ix->dev, d_queries, (uint32_t)nq, center, po, st));
+        if (d_coeffs)
+            CUDA_TRY(ix, cudaMemcpy2DAsync(d_coeffs, 12, qs.coeffs, kCoeffStride * 4, 12, nq, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    });
 }
 
 int cphnsw_b200_fastscan_blocks(cphnsw_b200_index* ix, const uint32_t* d_uplanes, const float* d_coeffs, uint64_t nq,
@@ -626,20 +893,22 @@ int cphnsw_b200_fastscan_blocks(cphnsw_b200_index* ix, const uint32_t* d_uplanes
     if (nblocks == 0) return 0;
     if (!d_uplanes || !d_coeffs || !d_dqp || nq == 0) return fail(ix, CPHNSW_B200_EINVAL, "null buffer");
     if (!d_vertex_ids && first_vertex + nblocks > ix->dev.n) return fail(ix, CPHNSW_B200_EINVAL, "vertex range out of bounds");
-    // widen the hook's [nq][3] coefficients to the kernels' stride
-    QStateView qs;
-    rc = ensure_qstate(ix, nq, &qs);
-    if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CUDA_TRY(ix, cudaMemsetAsync(qs.coeffs, 0, (size_t)nq * kCoeffStride * 4, st));
-    CUDA_TRY(ix, cudaMemcpy2DAsync(qs.coeffs, kCoeffStride * 4, d_coeffs, 12, 12, nq, cudaMemcpyDeviceToDevice, st));
-    FastScanArgs a{};
-    a.uplanes = d_uplanes; a.coeffs = qs.coeffs; a.nq = (uint32_t)nq; a.query_of_block = d_query_of_block;
-    a.vertex_ids = d_vertex_ids; a.first_vertex = first_vertex; a.nblocks = nblocks; a.dqp = d_dqp;
-    a.slack_level = d_slack_level; a.nbit = d_nbit; a.msb = d_msb; a.msb2 = d_msb2; a.est = d_est; a.lower = d_lower;
-    a.msb_lower = d_msb_lower;
-    CUDA_TRY(ix, launch_fastscan_blocks(ix->dev, a, ix->num_sms, st));
-    return 0;
+    return with_lane(ix, st, false, [&](Lane& L) -> int {
+        // widen the hook's [nq][3] coefficients to the kernels' stride
+        QStateView qs;
+        int r = ensure_qstate(ix, L, nq, &qs);
+        if (r) return r;
+        CUDA_TRY(ix, cudaMemsetAsync(qs.coeffs, 0, (size_t)nq * kCoeffStride * 4, st));
+        CUDA_TRY(ix, cudaMemcpy2DAsync(qs.coeffs, kCoeffStride * 4, d_coeffs, 12, 12, nq, cudaMemcpyDeviceToDevice, st));
+        FastScanArgs a{};
+        a.uplanes = d_uplanes; a.coeffs = qs.coeffs; a.nq = (uint32_t)nq; a.query_of_block = d_query_of_block;
+        a.vertex_ids = d_vertex_ids; a.first_vertex = first_vertex; a.nblocks = nblocks; a.dqp = d_dqp;
+        a.slack_level = d_slack_level; a.nbit = d_nbit; a.msb = d_msb; a.msb2 = d_msb2; a.est = d_est; a.lower = d_lower;
+        a.msb_lower = d_msb_lower;
+        CUDA_TRY(ix, launch_fastscan_blocks(ix->dev, a, ix->num_sms, st));
+        return 0;
+    });
 }
 
 int cphnsw_b200_exact_l2(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq, const uint32_t* d_ids, uint64_t m,
@@ -648,15 +917,17 @@ int cphnsw_b200_exact_l2(cphnsw_b200_index* ix, const float* d_queries, uint64_t
     if (rc) return rc;
     if (nq == 0 || m == 0) return 0;
     if (!d_queries || !d_ids || !d_out) return fail(ix, CPHNSW_B200_EINVAL, "null buffer");
-    QStateView qs;
-    rc = ensure_qstate(ix, nq, &qs);
-    if (rc) return rc;
-    PrepOut po{};
-    po.coeffs = qs.coeffs; po.qT = qs.qT;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CUDA_TRY(ix, launch_query_prep(ix->dev, d_queries, (uint32_t)nq, 0, po, st));
-    CUDA_TRY(ix, launch_exact_l2(ix->dev, qs.qT, qs.coeffs, (uint32_t)nq, d_ids, (uint32_t)m, d_out, st));
-    return 0;
+    return with_lane(ix, st, false, [&](Lane& L) -> int {
+        QStateView qs;
+        int r = ensure_qstate(ix, L, nq, &qs);
+        if (r) return r;
+        PrepOut po{};
+        po.coeffs = qs.coeffs; po.qT = qs.qT;
+        CUDA_TRY(ix, launch_query_prep(ix->dev, d_queries, (uint32_t)nq, 0, po, st));
+        CUDA_TRY(ix, launch_exact_l2(ix->dev, qs.qT, qs.coeffs, (uint32_t)nq, d_ids, (uint32_t)m, d_out, st));
+        return 0;
+    });
 }
 
 int cphnsw_b200_greedy_descent(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq, uint32_t* d_entry,
@@ -665,24 +936,20 @@ int cphnsw_b200_greedy_descent(cphnsw_b200_index* ix, const float* d_queries, ui
     if (rc) return rc;
     if (nq == 0) return 0;
     if (!d_queries || !d_entry) return fail(ix, CPHNSW_B200_EINVAL, "null buffer");
-    return run_search(ix, d_queries, nq, 1, nullptr, nullptr, d_entry, static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return with_lane(ix, st, false, [&](Lane& L) { return run_search(ix, L, d_queries, nq, 1, nullptr, nullptr, d_entry, st); });
 }
 
 }  // extern "C"
 
 extern "C" {
 
-static int run_exhaustive(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq, uint64_t k, uint64_t kprime,
+static int run_exhaustive(cphnsw_b200_index* ix, Lane& L, const float* d_queries, uint64_t nq, uint64_t k, uint64_t kprime,
                           uint64_t id_begin, uint64_t id_end, int64_t* d_ids, float* d_dists, uint32_t* d_sums,
                           float* d_est, cudaStream_t st) {
     const DevIndex& d = ix->dev;
-    if (d.B != 1) return fail(ix, CPHNSW_B200_EINVAL, "the exhaustive scan is defined for bits=1 indexes (per-vertex 1-bit codes)");
-    if (id_end > d.n || id_begin > id_end) return fail(ix, CPHNSW_B200_EINVAL, "id range out of bounds");
-    if (nq == 0) return 0;
-    if (nq > 0x7FFFFFFFull || k > 0x7FFFFFFFull) return fail(ix, CPHNSW_B200_EINVAL, "argument too large");
-    if (kprime > 1024) return fail(ix, CPHNSW_B200_EINVAL, "kprime (rerank depth) must be <= 1024");
     QStateView qs;
-    int rc = ensure_qstate(ix, nq, &qs);
+    int rc = ensure_qstate(ix, L, nq, &qs);
     if (rc) return rc;
     PrepOut po{};
     po.coeffs = qs.coeffs; po.uplanes = qs.uplanes; po.qT = qs.qT; po.ubytes = qs.ubytes;
@@ -694,10 +961,19 @@ static int run_exhaustive(cphnsw_b200_index* ix, const float* d_queries, uint64_
     a.id_begin = id_begin; a.id_end = id_end; a.k = (uint32_t)k; a.kprime = (uint32_t)kprime;
     a.sums = d_sums; a.est = d_est; a.ids = d_ids; a.dists = d_dists;
     const size_t wb = exhaustive_workspace_bytes(d, (uint32_t)nq, id_end - id_begin, (uint32_t)kprime, ix->num_sms);
-    rc = ensure_buffer(ix, &ix->scratch, &ix->scratch_bytes, wb + 256, false);
+    rc = ensure_buffer(ix, &L.scratch, &L.scratch_bytes, wb + 256, false);
     if (rc) return rc;
-    a.workspace = ix->scratch; a.workspace_bytes = wb;
+    a.workspace = L.scratch; a.workspace_bytes = wb;
     CUDA_TRY(ix, launch_exhaustive(d, a, ix->num_sms, st));
+    return 0;
+}
+
+static int check_exhaustive(cphnsw_b200_index* ix, uint64_t nq, uint64_t k, uint64_t kprime, uint64_t id_begin, uint64_t id_end) {
+    const DevIndex& d = ix->dev;
+    if (d.B != 1) return fail(ix, CPHNSW_B200_EINVAL, "the exhaustive scan is defined for bits=1 indexes (per-vertex 1-bit codes)");
+    if (id_end > d.n || id_begin > id_end) return fail(ix, CPHNSW_B200_EINVAL, "id range out of bounds");
+    if (nq > 0x7FFFFFFFull || k > 0x7FFFFFFFull) return fail(ix, CPHNSW_B200_EINVAL, "argument too large");
+    if (kprime > 1024) return fail(ix, CPHNSW_B200_EINVAL, "kprime (rerank depth) must be <= 1024");
     return 0;
 }
 
@@ -707,8 +983,12 @@ int cphnsw_b200_exhaustive_search(cphnsw_b200_index* ix, const float* d_queries,
     if (rc) return rc;
     if (nq && (!d_queries || (k && (!d_ids || !d_dists)))) return fail(ix, CPHNSW_B200_EINVAL, "null buffer");
     if (kprime < k) kprime = k;
-    return run_exhaustive(ix, d_queries, nq, k, kprime, id_begin, id_end, d_ids, d_dists, nullptr, nullptr,
-                          static_cast<cudaStream_t>(stream));
+    if ((rc = check_exhaustive(ix, nq, k, kprime, id_begin, id_end))) return rc;
+    if (nq == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return with_lane(ix, st, false, [&](Lane& L) {
+        return run_exhaustive(ix, L, d_queries, nq, k, kprime, id_begin, id_end, d_ids, d_dists, nullptr, nullptr, st);
+    });
 }
 
 int cphnsw_b200_exhaustive_estimates(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq, uint64_t id_begin,
@@ -716,8 +996,12 @@ int cphnsw_b200_exhaustive_estimates(cphnsw_b200_index* ix, const float* d_queri
     int rc = require_loaded(ix);
     if (rc) return rc;
     if (nq && !d_queries) return fail(ix, CPHNSW_B200_EINVAL, "null buffer");
-    return run_exhaustive(ix, d_queries, nq, 0, 0, id_begin, id_end, nullptr, nullptr, d_sums, d_est,
-                          static_cast<cudaStream_t>(stream));
+    if ((rc = check_exhaustive(ix, nq, 0, 0, id_begin, id_end))) return rc;
+    if (nq == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return with_lane(ix, st, false, [&](Lane& L) {
+        return run_exhaustive(ix, L, d_queries, nq, 0, 0, id_begin, id_end, nullptr, nullptr, d_sums, d_est, st);
+    });
 }
 
 int cphnsw_b200_unique_topk(cphnsw_b200_index* ix, const int64_t* d_ids_in, const float* d_dists_in, uint64_t nq,
@@ -727,13 +1011,14 @@ int cphnsw_b200_unique_topk(cphnsw_b200_index* ix, const int64_t* d_ids_in, cons
     if (nq == 0 || k_out == 0) return 0;
     if (!d_ids_in || !d_dists_in || !d_ids_out || !d_dists_out) return fail(ix, CPHNSW_B200_EINVAL, "null buffer");
     if (k_in > 0x7FFFFFFFull || k_out > 0x7FFFFFFFull) return fail(ix, CPHNSW_B200_EINVAL, "argument too large");
-    CUDA_TRY(ix, cudaSetDevice(ix->device));
+    DeviceGuard dg(ix->device);
+    CUDA_TRY(ix, dg.err);
     CUDA_TRY(ix, launch_unique_topk(d_ids_in, d_dists_in, nq, (uint32_t)k_in, (uint32_t)k_out, d_id_map, map_size, d_ids_out,
                                     d_dists_out, static_cast<cudaStream_t>(stream)));
     return 0;
 }
 
-int cphnsw_b200_neighbor_codes(cphnsw_b200_index* ix, uint32_t dim, uint32_t bits, uint64_t rotation_seed,
+static int neighbor_codes_impl(cphnsw_b200_index* ix, uint32_t dim, uint32_t bits, uint64_t rotation_seed,
                                const float* d_vectors, uint64_t row_stride, uint64_t n_vectors,
                                const uint32_t* d_parent_ids, const uint32_t* d_nbr_ids, uint64_t n_parents,
                                uint8_t* d_codes, float* d_aux, uint8_t* d_blocks, uint64_t block_stride, void* stream) {
@@ -745,7 +1030,11 @@ int cphnsw_b200_neighbor_codes(cphnsw_b200_index* ix, uint32_t dim, uint32_t bit
     if (!d_vectors || !d_nbr_ids || (!d_codes && !d_aux && !d_blocks)) return fail(ix, CPHNSW_B200_EINVAL, "null buffer");
     if (row_stride < dim) return fail(ix, CPHNSW_B200_EINVAL, "row_stride is smaller than dim");
     if (n_vectors >= kInvalid || n_parents > 0x7FFFFFFFull * 8) return fail(ix, CPHNSW_B200_EINVAL, "argument too large");
-    CUDA_TRY(ix, cudaSetDevice(ix->device));
+    DeviceGuard dg(ix->device);
+    CUDA_TRY(ix, dg.err);
+    std::lock_guard<std::mutex> enc(ix->enc_mu);   // the sign table and the tile scratch belong to one call at a time:
+    if (ix->enc_done) cudaEventSynchronize(ix->enc_done);   // the previous call's kernel has left them
+    else if (cudaEventCreateWithFlags(&ix->enc_done, cudaEventDisableTiming) != cudaSuccess) { ix->enc_done = nullptr; cudaGetLastError(); }
     const uint32_t D = next_pow2(dim) < 16 ? 16 : next_pow2(dim);
     if (d_blocks && (block_stride < nb_bytes(D, bits) || block_stride % 4 != 0 || reinterpret_cast<uintptr_t>(d_blocks) % 4 != 0))
         return fail(ix, CPHNSW_B200_EINVAL, "block_stride must be a multiple of 4 and at least the block size (" +
@@ -777,7 +1066,19 @@ int cphnsw_b200_neighbor_codes(cphnsw_b200_index* ix, uint32_t dim, uint32_t bit
         a.tile_u = reinterpret_cast<uint8_t*>(a.tile_x + (size_t)a.total_warps * D * 32);
     }
     CUDA_TRY(ix, launch_neighbor_codes(a, bits, plan, static_cast<cudaStream_t>(stream)));
+    if (ix->enc_done) cudaEventRecord(ix->enc_done, static_cast<cudaStream_t>(stream));
     return 0;
+}
+
+int cphnsw_b200_neighbor_codes(cphnsw_b200_index* ix, uint32_t dim, uint32_t bits, uint64_t rotation_seed,
+                               const float* d_vectors, uint64_t row_stride, uint64_t n_vectors,
+                               const uint32_t* d_parent_ids, const uint32_t* d_nbr_ids, uint64_t n_parents,
+                               uint8_t* d_codes, float* d_aux, uint8_t* d_blocks, uint64_t block_stride, void* stream) {
+    if (!ix) return CPHNSW_B200_EINVAL;
+    return guarded(ix, [&] {
+        return neighbor_codes_impl(ix, dim, bits, rotation_seed, d_vectors, row_stride, n_vectors, d_parent_ids, d_nbr_ids,
+                                   n_parents, d_codes, d_aux, d_blocks, block_stride, stream);
+    });
 }
 
 }  // extern "C"

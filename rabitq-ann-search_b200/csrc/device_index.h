@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -88,6 +90,42 @@ struct Stats {
 
 }  // namespace cpb
 
+namespace cpb {
+
+// Everything one in-flight call needs beyond the (read-only) index: scratch arenas, the prepared-query state, staging
+// buffers of the host-buffer entry points, counters and events.  A handle owns kLanes of them, handed out round-robin,
+// so two calls can be in flight at once -- from two host threads (the reference's search is safe for concurrent
+// callers: shared_lock + thread_local scratch, api/hnsw_index.hpp:172) or pipelined from one (submit / wait): the
+// tail of one batch's persistent grid then overlaps the head of the next.
+constexpr int kLanes = 2;
+struct Lane {
+    bool created = false;
+    void* scratch = nullptr;      // frontier arenas, overflow lists, K5 workspace
+    size_t scratch_bytes = 0;
+    void* bitmaps = nullptr;      // zero between searches; slot i at i * bitmap_words
+    size_t bitmaps_bytes = 0;
+    void* qstate = nullptr;       // K1 outputs
+    size_t qstate_bytes = 0;
+    void* stage = nullptr;        // device copies of host queries / results
+    size_t stage_bytes = 0;
+    Stats* d_stats = nullptr;
+    uint32_t* d_counters = nullptr;   // [0] work counter, [1] overflowed queries, [2] re-run work counter, [3] re-run overflows
+    uint32_t* h_counters = nullptr;   // pinned copy, valid once `done` has completed
+    cudaStream_t stream = nullptr;    // the host-buffer entry points run here
+    cudaEvent_t ev[4] = {};           // K1 begin / end, K3 begin / end (re-run included)
+    cudaEvent_t done = nullptr;       // recorded after the last operation of a call
+    int state = 0;                    // 0 free, 1 held by a host thread, 2 work in flight (nobody holds it)
+    uint64_t ticket = 0;              // of the call that used the lane last
+    bool counters_pending = false;    // h_counters belongs to an unfinished search
+    bool timed = false;               // ev[] belong to the last call
+    int status = 0;                   // outcome of the last finished call
+    std::string status_msg;
+    uint64_t overflow_retries = 0;
+    uint64_t launches = 0;            // kernels the last search enqueued
+};
+
+}  // namespace cpb
+
 struct cphnsw_b200_index {
     int device = 0;
     bool loaded = false;
@@ -103,28 +141,22 @@ struct cphnsw_b200_index {
     int64_t collect_stats = 0;        // per-batch counters (costs registers: off on the fast path)
     int64_t exhaustive_tensor_cores = 2;  // K5 scan: 2 = tcgen05 kind::f16 with the screen folded in, 1 = tcgen05 kind::i8 (each where
                                           // applicable, else the next), 0 = popcount form
-    // scratch, grown on demand
-    void* scratch = nullptr;
-    size_t scratch_bytes = 0;
-    size_t frontier_budget = 0;  // bytes of HBM the frontier arenas may take (fixed when first needed)
-    void* bitmaps = nullptr;   // zero between searches; slot i at i * bitmap_words
-    size_t bitmaps_bytes = 0;
-    void* qstate = nullptr;
-    size_t qstate_bytes = 0;
-    void* stage = nullptr;
-    size_t stage_bytes = 0;
-    void* h_stage = nullptr;  // pinned
-    size_t h_stage_bytes = 0;
-    cpb::Stats* d_stats = nullptr;
-    uint32_t* d_counters = nullptr;  // [0] work counter, [1] overflow count
-    float* enc_signs = nullptr;      // rotation sign diagonals of the build-side encoder (neighbor_codes), [3][enc_signs_D]
+    size_t frontier_budget = 0;  // bytes of HBM the frontier arenas of ONE lane may take (fixed when first needed)
+    // lanes: per-call state.  mu guards the lane states, the ticket counter and err.
+    std::mutex mu;
+    std::condition_variable cv;
+    cpb::Lane lanes[cpb::kLanes];
+    uint64_t next_lane = 0, next_ticket = 0;
+    int last_lane = -1;          // lane of the most recent search (last_stats / last_timings)
+    int occ_key[4] = {0, 0, 0, 0};   // cached occupancy query of the search kernel: smem per warp, warps, stats -> CTAs per SM
+    uint32_t* d_problems = nullptr;  // re-layout diagnostics (upload): [2] duplicate neighbour ids, [3] ids out of range
+    // build side (neighbor_codes): one call at a time (enc_mu)
+    std::mutex enc_mu;
+    float* enc_signs = nullptr;      // rotation sign diagonals of the build-side encoder, [3][enc_signs_D]
     uint32_t enc_signs_D = 0;
     uint64_t enc_signs_seed = 0;
     void* enc_scratch = nullptr;     // global-tile mode of neighbor_codes
     size_t enc_scratch_bytes = 0;
+    cudaEvent_t enc_done = nullptr;  // after the last neighbor_codes kernel
     int64_t neighbor_codes_tile = 0; // option: where the per-warp tiles live: 1 = shared memory, else global memory / L2 (results identical)
-    cphnsw_b200_stats last_stats{};
-    cudaStream_t own_stream = nullptr;
-    cudaEvent_t ev[6] = {};  // prep begin/end, search begin/end, re-run begin/end
-    float prep_ms = 0.0f, search_ms = 0.0f;
 };

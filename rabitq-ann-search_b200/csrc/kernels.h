@@ -46,6 +46,7 @@ cudaError_t launch_fastscan_blocks(const DevIndex& ix, const FastScanArgs& a, in
 // ---- K3 (+K4 fused) layer-0 Distance-Adaptive Beam Search (search.cu) --------------------------
 struct SearchArgs {
     uint32_t nq;               // work items
+    const uint32_t* nq_ptr;    // not NULL: the number of work items is read from device memory (re-run of overflowed queries)
     const uint32_t* query_list;  // NULL = identity; else work item i is query query_list[i]
     uint32_t k;                // max(user k, 1)
     uint32_t kout;             // user k (row stride of the outputs)

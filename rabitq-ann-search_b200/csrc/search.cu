@@ -263,6 +263,20 @@ __device__ __forceinline__ void nn_push(const WarpCtx& w, uint32_t& m, uint32_t 
     m = newm;
 }
 
+// The same list with entry j in lane j's registers (k <= 32): one ballot finds the insertion point, one shuffle moves
+// the tail up.  `worst` = distance of the last entry (warp-uniform), i.e. nn.worst_distance().
+__device__ __forceinline__ void nn_push_reg(float& d, uint32_t& id, float& worst, uint32_t& m, uint32_t k, uint32_t lane,
+                                            uint32_t nid, float dist) {
+    if (m == k && !(dist < worst)) return;
+    const uint32_t pos = __popc(__ballot_sync(kFull, lane < m && d <= dist));   // the entries that stay are a prefix
+    const float du = __shfl_up_sync(kFull, d, 1);
+    const uint32_t iu = __shfl_up_sync(kFull, id, 1);
+    if (lane > pos) { d = du; id = iu; }
+    else if (lane == pos) { d = dist; id = nid; }
+    m = m < k ? m + 1 : k;
+    worst = __shfl_sync(kFull, d, m - 1);
+}
+
 __device__ __forceinline__ float exact_group(const DevIndex& ix, const WarpCtx& w, uint32_t id, bool active,
                                              float qn) {
     const uint32_t l = w.lane & 7u;
@@ -336,7 +350,8 @@ __device__ __forceinline__ uint32_t greedy_descent(const DevIndex& ix, const War
 
 // DT = 128: the padded dimension is the compile-time constant 128 (SIFT/Deep shapes: one 128-dim chunk per
 // code plane, 16-step distance chains, constant shared-memory offsets); DT = 0: any supported dimension.
-template <int B, bool STATS, int DT>
+// NNR: the result list lives in registers (lane j = entry j; k <= 32) instead of shared memory.
+template <int B, bool STATS, int DT, bool NNR>
 __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const SearchArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -344,6 +359,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
     const uint32_t aux_off = B * nch * 512;
     const uint32_t block_stride = DT ? ((aux_off + 644 + 127) & ~127u) : ix.block_stride;
     const uint32_t k = a.k;
+    const uint32_t nq_work = a.nq_ptr ? *a.nq_ptr : a.nq;
 
     // ---- carve shared memory -------------------------------------------------------------------
     const size_t per_warp = smem_per_warp(D, B, k);
@@ -370,7 +386,9 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
     uint8_t* arena = a.scratch + (size_t)slot * a.slot_stride;
     w.hg = reinterpret_cast<uint4*>(arena + a.heap_off);
     w.bitmap = a.bitmaps + (size_t)slot * a.bitmap_words;
-    if (k <= kNNSmem) {
+    if (NNR) {
+        w.nn_d = nullptr; w.nn_i = nullptr;
+    } else if (k <= kNNSmem) {
         w.nn_d = reinterpret_cast<float*>(sm);
         w.nn_i = reinterpret_cast<uint32_t*>(sm + (size_t)nn_smem_entries(k) * 4);
     } else {
@@ -388,7 +406,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
         uint32_t wi = 0;
         if (lane == 0) wi = atomicAdd(a.counters, 1u);
         wi = __shfl_sync(kFull, wi, 0);
-        if (wi >= a.nq) break;
+        if (wi >= nq_work) break;
         const uint32_t q = a.query_list ? a.query_list[wi] : wi;
 
         // ---- stage the prepared query --------------------------------------------------------
@@ -414,6 +432,8 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
 
         // ---- layer-0 search state (search/rabitq_search.hpp:77-97) ----------------------------
         uint32_t heap_n = 0, nn_m = 0;
+        float nnr_d = 0.0f, nnr_worst = FLT_MAX;   // NNR: this lane's entry, and the last entry's distance
+        uint32_t nnr_i = 0;
         int slack_batch_count = 0;
         bool overflow = false;
         uint32_t max_beam = 0;
@@ -439,7 +459,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             const float cur_lower = __uint_as_float(top.x);
             const uint32_t cur = top.y;
             const bool full0 = nn_m >= k;
-            float worst = full0 ? w.nn_d[k - 1] : FLT_MAX;
+            float worst = full0 ? (NNR ? nnr_worst : w.nn_d[k - 1]) : FLT_MAX;
             const bool terminate = full0 && cur_est >= __fmul_rn(ws->gamma_q, worst);   // :120
             const bool lbskip = full0 && cur_lower > worst;                          // :122
             const bool expand = !terminate && !lbskip;
@@ -481,7 +501,8 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                                                            w.qrow, T, true);
                 exact_dist = exact_from_dot(ws->qn, *reinterpret_cast<const float*>(aux + 644), dot);   // norm_sq rides in the block
             }
-            nn_push(w, nn_m, k, cur, exact_dist);
+            if (NNR) nn_push_reg(nnr_d, nnr_i, nnr_worst, nn_m, k, lane, cur, exact_dist);
+            else nn_push(w, nn_m, k, cur, exact_dist);
             if (STATS) { ++st.exact_calls; ++st.nn_pushes; ++st.expansions; }
             // (count == 0 -> `continue` in the reference: no lane is valid, nothing below acts)
             const float dqp = exact_dist;
@@ -518,7 +539,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             if (STATS) st.estimated += __popc(rem);
 
             if (B > 1 && count > 0 && (STATS || (!warmup && rem))) {
-                const float w0 = w.nn_d[nn_m - 1];   // nn.worst_distance() (:179), the k-th distance when nn is full
+                const float w0 = NNR ? nnr_worst : w.nn_d[nn_m - 1];   // nn.worst_distance() (:179), the k-th distance when nn is full
                 const unsigned cand = __ballot_sync(kFull, isnew && !(lower >= w0));
                 if (STATS || cand) {
                     const float nop = reinterpret_cast<const float*>(aux + 128)[lane];
@@ -552,8 +573,9 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                     rem &= rem - 1;
                     const float ex = __shfl_sync(kFull, myex, j);
                     const uint32_t id = __shfl_sync(kFull, nid, j);
-                    const float dabs = nn_m >= k ? __fmul_rn(ws->gamma_q, w.nn_d[k - 1]) : FLT_MAX;   // :230-232
-                    nn_push(w, nn_m, k, id, ex);
+                    const float dabs = nn_m >= k ? __fmul_rn(ws->gamma_q, NNR ? nnr_worst : w.nn_d[k - 1]) : FLT_MAX;   // :230-232
+                    if (NNR) nn_push_reg(nnr_d, nnr_i, nnr_worst, nn_m, k, lane, id, ex);
+                    else nn_push(w, nn_m, k, id, ex);
                     if (STATS) ++st.nn_pushes;
                     if (ex < dabs) {
                         if (heap_n >= a.beam_capacity) { overflow = true; break; }
@@ -563,7 +585,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                     }
                 }
             } else if (rem) {
-                worst = w.nn_d[k - 1];
+                worst = NNR ? nnr_worst : w.nn_d[k - 1];
                 // distances that may be needed: every new slot that passes both tests under the
                 // current k-th distance (the k-th distance only shrinks, so this is a superset)
                 const unsigned spec = __ballot_sync(kFull, isnew && !(lower >= worst) && est < worst);
@@ -593,7 +615,8 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                         const float ex = __shfl_sync(kFull, myex, first), ed = __shfl_sync(kFull, est, first);
                         const float lo = __shfl_sync(kFull, lower, first);
                         const uint32_t id = __shfl_sync(kFull, nid, first);
-                        nn_push(w, nn_m, k, id, ex);
+                        if (NNR) nn_push_reg(nnr_d, nnr_i, nnr_worst, nn_m, k, lane, id, ex);
+                        else nn_push(w, nn_m, k, id, ex);
                         if (STATS) ++st.nn_pushes;
                         if (ex < dabs) {
                             if (heap_n >= a.beam_capacity) { overflow = true; break; }
@@ -618,7 +641,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                             if (lane == 0) { ws->ratio_sum = rs; ws->ratio_sq_sum = rq; ws->ratio_count = rc; ws->gamma_q = gq; }
                             __syncwarp();
                         }
-                        worst = w.nn_d[k - 1];
+                        worst = NNR ? nnr_worst : w.nn_d[k - 1];
                     }
                 }
             }
@@ -630,6 +653,12 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
         __syncwarp();
         if (overflow) {
             if (lane == 0) { const uint32_t o = atomicAdd(a.counters + 1, 1u); a.overflow_list[o] = q; }
+        } else if (NNR) {
+            if (lane < a.kout) {
+                const bool have = lane < nn_m;
+                a.ids[(size_t)q * a.kout + lane] = have ? (int64_t)nnr_i : (int64_t)-1;
+                a.dists[(size_t)q * a.kout + lane] = have ? nnr_d : FLT_MAX;
+            }
         } else if (a.kout > 0) {
             for (uint32_t j = lane; j < a.kout; j += 32) {
                 const bool have = j < nn_m;
@@ -673,17 +702,20 @@ size_t search_smem_per_warp(const DevIndex& ix, uint32_t k) { return smem_per_wa
 typedef void (*SearchKernel)(const DevIndex, const SearchArgs);
 
 template <int DT>
-static SearchKernel pick_kernel_d(uint32_t B, bool stats) {
-    if (stats) return B == 1 ? search_kernel<1, true, DT> : B == 2 ? search_kernel<2, true, DT> : search_kernel<4, true, DT>;
-    return B == 1 ? search_kernel<1, false, DT> : B == 2 ? search_kernel<2, false, DT> : search_kernel<4, false, DT>;
+static SearchKernel pick_kernel_d(uint32_t B, bool stats, bool nnr) {
+    if (stats) return B == 1 ? search_kernel<1, true, DT, false> : B == 2 ? search_kernel<2, true, DT, false> : search_kernel<4, true, DT, false>;
+    if (nnr) return B == 1 ? search_kernel<1, false, DT, true> : B == 2 ? search_kernel<2, false, DT, true> : search_kernel<4, false, DT, true>;
+    return B == 1 ? search_kernel<1, false, DT, false> : B == 2 ? search_kernel<2, false, DT, false> : search_kernel<4, false, DT, false>;
 }
-static SearchKernel pick_kernel(const DevIndex& ix, bool stats) {
-    return ix.D == 128 ? pick_kernel_d<128>(ix.B, stats) : pick_kernel_d<0>(ix.B, stats);
+// the result list is held in registers when it fits one entry per lane (the counting build keeps the shared-memory list)
+static SearchKernel pick_kernel(const DevIndex& ix, bool stats, uint32_t k) {
+    const bool nnr = k <= 32;
+    return ix.D == 128 ? pick_kernel_d<128>(ix.B, stats, nnr) : pick_kernel_d<0>(ix.B, stats, nnr);
 }
 
 int search_max_ctas_per_sm(const DevIndex& ix, uint32_t k, int warps_per_cta, bool stats) {
     const size_t smem = search_smem_per_warp(ix, k) * warps_per_cta;
-    SearchKernel kern = pick_kernel(ix, stats);
+    SearchKernel kern = pick_kernel(ix, stats, k);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;
@@ -699,7 +731,7 @@ int search_max_ctas_per_sm(const DevIndex& ix, uint32_t k, int warps_per_cta, bo
 cudaError_t launch_search(const DevIndex& ix, const SearchArgs& a, int ctas, int warps_per_cta, bool stats,
                           cudaStream_t stream) {
     const size_t smem = search_smem_per_warp(ix, a.k) * warps_per_cta;
-    SearchKernel kern = pick_kernel(ix, stats);
+    SearchKernel kern = pick_kernel(ix, stats, a.k);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<ctas, warps_per_cta * 32, smem, stream>>>(ix, a);

@@ -76,6 +76,12 @@ inline T __shfl_sync(unsigned, T v, int src) {
 
 template <typename T>
 inline T __shfl_xor_sync(unsigned m, T v, int lane_mask) { return __shfl_sync(m, v, (int)(threadIdx.x & 31) ^ lane_mask); }
+// shfl.up: lanes below delta keep their own value
+template <typename T>
+inline T __shfl_up_sync(unsigned m, T v, unsigned delta) {
+    const int lane = (int)(threadIdx.x & 31);
+    return __shfl_sync(m, v, lane >= (int)delta ? lane - (int)delta : lane);
+}
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
 

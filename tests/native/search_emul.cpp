@@ -86,14 +86,23 @@ extern "C" int emul_search(uint32_t dim, uint32_t bits, const uint8_t* records, 
     a.scratch = scratch.data() + (128 - reinterpret_cast<uintptr_t>(scratch.data()) % 128) % 128;
     a.bitmaps = bitmaps.data(); a.overflow_list = over.data(); a.counters = counters; a.stats = &st;
     const bool stats = stats_out != nullptr;
+    // the same selection as the launcher's pick_kernel: counting build keeps the shared-memory result list, otherwise the
+    // list lives in registers when k <= 32
+    const bool nnr = !stats && k <= 32;
     auto kern = [&](int) {
+#define CPB_EMUL_PICK(BITS, ST, DTV, NN) search_kernel<BITS, ST, DTV, NN>(ix, a)
+#define CPB_EMUL_BITS(ST, DTV, NN) do { if (bits == 1) CPB_EMUL_PICK(1, ST, DTV, NN); else if (bits == 2) CPB_EMUL_PICK(2, ST, DTV, NN); else CPB_EMUL_PICK(4, ST, DTV, NN); } while (0)
         if (D == 128) {
-            if (stats) { if (bits == 1) search_kernel<1, true, 128>(ix, a); else if (bits == 2) search_kernel<2, true, 128>(ix, a); else search_kernel<4, true, 128>(ix, a); }
-            else { if (bits == 1) search_kernel<1, false, 128>(ix, a); else if (bits == 2) search_kernel<2, false, 128>(ix, a); else search_kernel<4, false, 128>(ix, a); }
+            if (stats) CPB_EMUL_BITS(true, 128, false);
+            else if (nnr) CPB_EMUL_BITS(false, 128, true);
+            else CPB_EMUL_BITS(false, 128, false);
         } else {
-            if (stats) { if (bits == 1) search_kernel<1, true, 0>(ix, a); else if (bits == 2) search_kernel<2, true, 0>(ix, a); else search_kernel<4, true, 0>(ix, a); }
-            else { if (bits == 1) search_kernel<1, false, 0>(ix, a); else if (bits == 2) search_kernel<2, false, 0>(ix, a); else search_kernel<4, false, 0>(ix, a); }
+            if (stats) CPB_EMUL_BITS(true, 0, false);
+            else if (nnr) CPB_EMUL_BITS(false, 0, true);
+            else CPB_EMUL_BITS(false, 0, false);
         }
+#undef CPB_EMUL_BITS
+#undef CPB_EMUL_PICK
     };
     cuda_emul::launch(kern, (unsigned)ctas, warps * 32, smem_raw, smem, 0);
     if (overflowed) *overflowed = counters[1];

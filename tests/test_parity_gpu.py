@@ -6,6 +6,9 @@ relative tolerance BASELINE.json's north_star allows; REL_TOL documents that all
 """
 import ctypes as C
 
+import os
+import sys
+
 import numpy as np
 import pytest
 
@@ -309,6 +312,39 @@ def test_search_reference_built_index(oracle, n, dim, bits, clusters, k):
     assert np.array_equal(gi, wi) and np.array_equal(_bits(gd), _bits(wd))
     # relative tolerance statement of the north star (implied by equality)
     assert np.all(np.abs(gd - wd) <= REL_TOL * np.maximum(np.abs(wd), 1e-30))
+
+
+@needs_ref
+@pytest.mark.parametrize("n,dim,bits,k,nq", [(250_000, 128, 4, 10, 400), (100_000, 960, 2, 100, 200)])
+def test_search_reference_built_index_at_scale(n, dim, bits, k, nq):
+    """BASELINE configs 2 and 3 at the largest sizes a test run can build (the index comes from the reference's own
+    build code through oracle/_ref/refbuild, exactly as bench.py obtains its index -- 250k is past the point where the
+    stock calibration stops converging, so this also covers the relaxed-calibration files the bench searches): ids as
+    multisets and distance bits against the reference module, for the counting kernels and for the fast ones."""
+    import argparse
+
+    sys.path.insert(0, str(common.ROOT))
+    import bench
+
+    if not (common.ROOT / "oracle" / "_ref" / "refbuild").exists():
+        pytest.skip("oracle/_ref/refbuild not present")
+    args = argparse.Namespace(n=n, dim=dim, bits=bits, clusters=0, seed=1234)
+    path, _ = bench.obtain_index(args, 0, 1)
+    ix = common.gpu_index_from(path)
+    q = common.queries_for(dim, nq)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
+    ref = co.ref_module().CPIndex(dim=dim, bits=bits)
+    ref.load(str(path))
+    rid, rd = ref.search_batch(q, k)
+    wi, wd = common.sorted_rows(rid, rd)
+    for stats in (1, 0):
+        ix.set_option("collect_stats", stats)
+        ids, dists = ix.search_batch(q, k)
+        gi, gd = common.sorted_rows(ids, dists)
+        assert np.array_equal(gi, wi), f"ids differ from the reference (collect_stats={stats})"
+        assert np.array_equal(_bits(gd), _bits(wd)), f"distance bits differ from the reference (collect_stats={stats})"
+    st = ix.last_stats()
+    assert st["overflow_retries"] == 0
 
 
 @needs_ref
