@@ -135,8 +135,8 @@ struct cphnsw_b200_index {
     std::vector<void*> allocs;  // everything dev points to
     int num_sms = 148;
     // options (do not change results)
-    int64_t warps_per_cta = 8;
-    int64_t ctas_per_sm = 4;
+    int64_t warps_per_cta = 2;       // small CTAs: a CTA leaves the SM as soon as its warps run out of queries, so the next batch moves in
+    int64_t ctas_per_sm = 16;
     int64_t beam_capacity = 0;        // frontier entries per in-flight query (first attempt); 0 = sized from free HBM
     int64_t collect_stats = 0;        // per-batch counters (costs registers: off on the fast path)
     int64_t exhaustive_tensor_cores = 2;  // K5 scan: 2 = tcgen05 kind::f16 with the screen folded in, 1 = tcgen05 kind::i8 (each where

@@ -66,6 +66,7 @@ struct SearchArgs {
     uint32_t* overflow_list;   // queries whose frontier overflowed (to be re-run)
     Stats* stats;              // may be NULL
     uint32_t* entry_out;       // descent-only mode: layer-0 entry point per query (else NULL)
+    uint32_t warp_smem;        // bytes of shared memory per warp (filled in by launch_search)
 };
 size_t search_smem_per_warp(const DevIndex& ix, uint32_t k);
 int search_max_ctas_per_sm(const DevIndex& ix, uint32_t k, int warps_per_cta, bool stats);

@@ -54,7 +54,7 @@ __host__ __device__ inline uint32_t stage_raw_off(uint32_t aux_off) { return (bl
 __host__ __device__ inline size_t smem_per_warp(uint32_t D, uint32_t B, uint32_t k) {
     const uint32_t T = D / 8, nch = (D > 128 ? D : 128) / 128, aux_off = B * nch * 512;
     size_t s = (size_t)stage_raw_off(aux_off) + (size_t)D * 4 + 16 + 64;   // staged block + raw vector + mbarrier + WarpState
-    s += (size_t)8 * (T + 4) * 4 + (size_t)nch * 64 + (size_t)(kHC + 1) * 12 + (size_t)nn_smem_entries(k) * 8;
+    s += (size_t)8 * (T + 4) * 4 + (size_t)nch * 64 + (size_t)(kHC + 1) * 16 + (size_t)nn_smem_entries(k) * 8;
     return (s + 127) & ~(size_t)127;
 }
 
@@ -62,11 +62,10 @@ struct WarpCtx {
     // shared memory
     float* qrow;      // this lane's accumulator row of the query
     const uint4* uq;  // query bit-planes
-    float* ks;        // frontier keys   [0, kHC)
-    uint2* ps;        // frontier payload {lower bound bits, id}
+    uint4* hs;        // frontier entries {key, lower bound bits, id, -} [0, kHC); physical index = logical + 1 here and in
+                      // the arena, so a sibling pair is one aligned 32-byte unit (one sector in HBM)
     // arena
-    uint4* hg;        // frontier entries {key, lower, id, -} beyond kHC; physical index = logical + 1
-                      // (a sibling pair is one aligned 32-B sector)
+    uint4* hg;        // frontier entries beyond kHC
     uint32_t* bitmap;
     float* nn_d;
     uint32_t* nn_i;
@@ -89,15 +88,16 @@ struct WarpState {
 };
 static_assert(sizeof(WarpState) <= 64, "WarpState must fit its shared-memory slot");
 
-__device__ __forceinline__ float kget(const WarpCtx& w, uint32_t i) {
-    return i < kHC ? w.ks[i] : *reinterpret_cast<const float*>(w.hg + i + 1);
-}
+// Entry i wherever it lives: one generic address (the shared window or the arena), so reads and writes of entries are
+// single 16-byte accesses with no branch on the address space.
+__device__ __forceinline__ uint4* eptr(const WarpCtx& w, uint32_t i) { return (i < kHC ? w.hs : w.hg) + (i + 1); }
+__device__ __forceinline__ float kget(const WarpCtx& w, uint32_t i) { return __uint_as_float(eptr(w, i)->x); }
 __device__ __forceinline__ void eget(const WarpCtx& w, uint32_t i, float& key, uint2& pay) {
-    if (i < kHC) { key = w.ks[i]; pay = w.ps[i]; }
-    else { const uint4 e = w.hg[i + 1]; key = __uint_as_float(e.x); pay = make_uint2(e.y, e.z); }
+    const uint4 e = *eptr(w, i);
+    key = __uint_as_float(e.x); pay = make_uint2(e.y, e.z);
 }
 __device__ __forceinline__ void eset(const WarpCtx& w, uint32_t i, float key, uint2 pay) {
-    if (i < kHC) { w.ks[i] = key; w.ps[i] = pay; } else w.hg[i + 1] = make_uint4(__float_as_uint(key), pay.x, pay.y, 0u);
+    *eptr(w, i) = make_uint4(__float_as_uint(key), pay.x, pay.y, 0u);
 }
 
 // Lane L < 31 owns sibling pair L of the 5-level subtree under the hole (pair L = the children of subtree
@@ -149,13 +149,12 @@ __device__ __forceinline__ uint32_t pop_step(const WarpCtx& w, uint32_t& hole, u
     const uint32_t p = SMEM ? L : ((hole + 1) << (dlev - 1)) - 1 + jpair;
     const uint32_t left = 2 * p + 1;
     const bool hl = L < 31 && left < len, hr = L < 31 && left + 1 < len;
-    float kl = 0.0f, kr = 0.0f;
-    uint4 el = make_uint4(0, 0, 0, 0), er = el;   // HBM part: whole entries, one 32-B sector per pair
-    if (SMEM) { if (hl) kl = w.ks[left]; if (hr) kr = w.ks[left + 1]; }
-    else {
-        if (hl) { el = w.hg[left + 1]; kl = __uint_as_float(el.x); }
-        if (hr) { er = w.hg[left + 2]; kr = __uint_as_float(er.x); }
-    }
+    // whole entries, the pair is one aligned 32-byte unit; below a hole outside shared memory every child is in the arena
+    // loaded unconditionally (an absent child reads the pair at the end of the heap, inside the arena: len + 2 <= capacity + 1;
+    // its keys are never used: hl / hr gate every decision)
+    const uint4* pair = SMEM ? w.hs + ((L < 31 ? left : 0u) + 1) : w.hg + ((left < len ? left : len) + 1);
+    const uint4 el = pair[0], er = pair[1];
+    const float kl = __uint_as_float(el.x), kr = __uint_as_float(er.x);
     const bool right = hr && !(kr > kl);           // __adjust_heap: the right child unless right > left
     const bool ok = hl && (right ? kr : kl) <= vk;  // the preferred child still moves up
     const unsigned rmask = __ballot_sync(kFull, right);
@@ -164,14 +163,11 @@ __device__ __forceinline__ uint32_t pop_step(const WarpCtx& w, uint32_t& hole, u
     const bool mv = ok && (omask & wk.x) == wk.x && (rmask & wk.x) == wk.y;
     const unsigned M = __ballot_sync(kFull, mv);   // the pairs on the walk: one per level, top down
     const uint32_t src = left + (right ? 1u : 0u);
-    float mk = 0.0f;
-    uint2 mp = make_uint2(0, 0);
-    if (mv) {
-        if (SMEM) { mk = w.ks[src]; mp = w.ps[src]; }
-        else { mk = right ? kr : kl; mp = right ? make_uint2(er.y, er.z) : make_uint2(el.y, el.z); }
-    }
     __syncwarp();
-    if (mv) { if (SMEM) { w.ks[p] = mk; w.ps[p] = mp; } else eset(w, p, mk, mp); }
+    if (mv) {
+        const uint4 e = right ? er : el;
+        if (SMEM) w.hs[p + 1] = e; else *eptr(w, p) = e;
+    }
     if (M) hole = __shfl_sync(kFull, src, 31 - __clz(M));
     return __popc(M);
 }
@@ -351,6 +347,13 @@ __device__ __forceinline__ uint32_t greedy_descent(const DevIndex& ix, const War
 // DT = 128: the padded dimension is the compile-time constant 128 (SIFT/Deep shapes: one 128-dim chunk per
 // code plane, 16-step distance chains, constant shared-memory offsets); DT = 0: any supported dimension.
 // NNR: the result list lives in registers (lane j = entry j; k <= 32) instead of shared memory.
+// (Tried and not kept, again: an L2 prefetch of the block most likely to be expanded next -- the smaller child of the
+// frontier's root -- one expansion ahead: 3 % slower with it on, and its mere presence behind a flag cost 9 %, the register
+// allocation of this kernel being what it is.)
+// (Tried and not kept: instantiations with the CTA shape and the per-warp shared-memory stride as compile-time constants.
+// They remove the ~60 instructions per expansion that re-derive lane / warp / base from the thread id -- the kernel lives
+// at the 64-register cap -- but run slower: 788 instead of 820 instructions per expansion, 66 % instead of 71 % issue
+// utilisation, 3 % fewer QPS.  The kernel is bound by the latency of its dependent chain, not by issue slots.)
 template <int B, bool STATS, int DT, bool NNR>
 __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const SearchArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -362,8 +365,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
     const uint32_t nq_work = a.nq_ptr ? *a.nq_ptr : a.nq;
 
     // ---- carve shared memory -------------------------------------------------------------------
-    const size_t per_warp = smem_per_warp(D, B, k);
-    uint8_t* sm = smem_raw + (size_t)warp * per_warp;
+    uint8_t* sm = smem_raw + warp * a.warp_smem;   // smem_per_warp(D, B, k), computed by the launcher
     WarpCtx w;
     w.lane = lane;
     w.D = D; w.T = T;
@@ -378,8 +380,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
     w.ws = ws;
     float* qs = reinterpret_cast<float*>(sm);                     sm += (size_t)8 * Tp * 4;
     uint4* uqs = reinterpret_cast<uint4*>(sm);                    sm += (size_t)nch * 64;
-    w.ps = reinterpret_cast<uint2*>(sm);                          sm += (size_t)(kHC + 1) * 8;
-    w.ks = reinterpret_cast<float*>(sm);                          sm += (size_t)(kHC + 1) * 4;
+    w.hs = reinterpret_cast<uint4*>(sm);                          sm += (size_t)(kHC + 1) * 16;
     w.qrow = qs + (size_t)(lane & 7u) * Tp;
     w.uq = uqs;
     const uint32_t slot = blockIdx.x * nwarps + warp;
@@ -443,8 +444,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             const float d0 = exact_group(ix, w, ep, true, qn);
             if (STATS) { ++st.exact_calls; ++st.beam_pushes; ++st.estimated; }
             if (lane == 0) {
-                w.ks[0] = d0;
-                w.ps[0] = make_uint2(__float_as_uint(0.0f), ep);
+                w.hs[1] = make_uint4(__float_as_uint(d0), __float_as_uint(0.0f), ep, 0u);
                 atomicOr(&w.bitmap[ep >> 5], 1u << (ep & 31));
                 dirty |= 1u << (ep >> a.chunk_shift);
             }
@@ -454,10 +454,9 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
 
         while (heap_n > 0) {
             // ---- pop (:110-117).  is_visited() can never hit: see file header ---------------------
-            const float cur_est = w.ks[0];
-            const uint2 top = w.ps[0];
-            const float cur_lower = __uint_as_float(top.x);
-            const uint32_t cur = top.y;
+            const uint4 top = w.hs[1];
+            const float cur_est = __uint_as_float(top.x), cur_lower = __uint_as_float(top.y);
+            const uint32_t cur = top.z;
             const bool full0 = nn_m >= k;
             float worst = full0 ? (NNR ? nnr_worst : w.nn_d[k - 1]) : FLT_MAX;
             const bool terminate = full0 && cur_est >= __fmul_rn(ws->gamma_q, worst);   // :120
@@ -701,11 +700,14 @@ size_t search_smem_per_warp(const DevIndex& ix, uint32_t k) { return smem_per_wa
 #ifndef CPB_HOST_EMULATION   // tests/native/ compiles the kernels of this file for the host
 typedef void (*SearchKernel)(const DevIndex, const SearchArgs);
 
+template <int DT, bool ST, bool NN>
+static SearchKernel pick_kernel_b(uint32_t B) {
+    return B == 1 ? search_kernel<1, ST, DT, NN> : B == 2 ? search_kernel<2, ST, DT, NN> : search_kernel<4, ST, DT, NN>;
+}
 template <int DT>
 static SearchKernel pick_kernel_d(uint32_t B, bool stats, bool nnr) {
-    if (stats) return B == 1 ? search_kernel<1, true, DT, false> : B == 2 ? search_kernel<2, true, DT, false> : search_kernel<4, true, DT, false>;
-    if (nnr) return B == 1 ? search_kernel<1, false, DT, true> : B == 2 ? search_kernel<2, false, DT, true> : search_kernel<4, false, DT, true>;
-    return B == 1 ? search_kernel<1, false, DT, false> : B == 2 ? search_kernel<2, false, DT, false> : search_kernel<4, false, DT, false>;
+    if (stats) return pick_kernel_b<DT, true, false>(B);
+    return nnr ? pick_kernel_b<DT, false, true>(B) : pick_kernel_b<DT, false, false>(B);
 }
 // the result list is held in registers when it fits one entry per lane (the counting build keeps the shared-memory list)
 static SearchKernel pick_kernel(const DevIndex& ix, bool stats, uint32_t k) {
@@ -734,7 +736,9 @@ cudaError_t launch_search(const DevIndex& ix, const SearchArgs& a, int ctas, int
     SearchKernel kern = pick_kernel(ix, stats, a.k);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<ctas, warps_per_cta * 32, smem, stream>>>(ix, a);
+    SearchArgs b = a;
+    b.warp_smem = (uint32_t)search_smem_per_warp(ix, a.k);
+    kern<<<ctas, warps_per_cta * 32, smem, stream>>>(ix, b);
     return cudaGetLastError();
 }
 

@@ -67,6 +67,7 @@ extern "C" int emul_search(uint32_t dim, uint32_t bits, const uint8_t* records, 
     const int need = (int)((nq + warps - 1) / warps);
     if (ctas > need) ctas = need;
     SearchArgs a{};
+    a.warp_smem = (uint32_t)search_smem_per_warp(ix, k);
     a.nq = nq; a.query_list = nullptr; a.k = k; a.kout = k_user; a.ids = ids; a.dists = dists;
     a.qT = qT; a.uplanes = uplanes; a.coeffs = coeffs; a.entry_out = nullptr;
     const uint32_t words = (uint32_t)((n + 31) / 32);

@@ -229,14 +229,14 @@ def _search(k1, k3, oracle, dim, bits, records, rec_size, nb_off, raw, norm_sq, 
     return ids, dists, over.value, stats
 
 
-@pytest.mark.parametrize("bits,k", [(1, 10), (2, 50), (4, 10), (4, 1)])
-def test_search_kernel_source_reproduces_the_reference_results(k1, k3, oracle, bits, k):
+@pytest.mark.parametrize("bits,k,warps", [(1, 10, 2), (2, 50, 4), (4, 10, 1), (4, 1, 4)])
+def test_search_kernel_source_reproduces_the_reference_results(k1, k3, oracle, bits, k, warps):
     """Index files built and saved by the unmodified reference, and its own search_batch results on them (e2e_golden):
     re-layout kernels + K1 + the search kernel, all from the product's source, on host threads -- ids and distance bits."""
     g = np.load(common.GOLDEN / "e2e_golden.npz")
     sf = co_SaveFile(common.GOLDEN / f"ref_n300_d24_b{bits}.bin")
     ids, dists, over, _ = _search(k1, k3, oracle, sf.dim, bits, sf.search_data, sf.rec_size, sf.nb_off, sf.raw, sf.norm_sq, sf.calib_bytes,
-                                  sf.max_level, sf.entry_point, sf.layers, g["queries"], k)
+                                  sf.max_level, sf.entry_point, sf.layers, g["queries"], k, warps=warps, ctas=2 * (4 // warps))   # warps = 1: the single-warp-CTA build
     assert over == 0
     gi, gd = common.sorted_rows(ids, dists)
     wi, wd = common.sorted_rows(g[f"ids_b{bits}_k{k}"], g[f"dists_b{bits}_k{k}"])
