@@ -57,7 +57,7 @@ struct DevIndex {
     const uint8_t* blocks;
     uint32_t block_stride, aux_off;
     uint32_t dup_neighbors;  // != 0: some block lists a neighbour id twice (never seen from the reference's builder)
-    // raw vectors, accumulator-major: rawT[id][l*T + t] = raw[id][8t + l]  (l = 0..7)
+    // raw vectors, accumulator-major with a bank swizzle: rawT[id][l*T + raw_chunk_pos(l, t, T)] = raw[id][8t + l]  (l = 0..7; device_math.cuh)
     const float* rawT;
     const float* norm_sq;
     const float* signs;     // [3][D]

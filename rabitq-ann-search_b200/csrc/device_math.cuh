@@ -270,6 +270,17 @@ __device__ __forceinline__ float nbit_est(const QParams& p, uint32_t nbit, float
 // four such groups (g = lane>>3) on four vectors at once.  qrow = this lane's row of the query
 // in shared memory (row stride T+4 floats: conflict-free for 128-bit reads).
 // ---------------------------------------------------------------------------------------------
+// Bank swizzle of the accumulator-major layout.  Row l (T floats) is read by lane l in 16-byte chunks, all eight rows at
+// the same chunk index at once: with a row stride of T floats those eight reads fall on the same shared-memory banks
+// (4-way conflicts at T = 16: 48 of the 157 shared-memory wavefronts of an expansion).  So chunk j of row l is STORED at
+// chunk position j ^ raw_swizzle(l, T / 4): the eight rows then cover eight different 16-byte bank groups, with no padding
+// (the order in which a chain consumes its elements is unchanged).
+__host__ __device__ __forceinline__ uint32_t raw_swizzle(uint32_t l, uint32_t nv) { return nv >= 8 ? l : (l * nv) >> 3; }
+// position (in floats) of element t of row l inside the row
+__host__ __device__ __forceinline__ uint32_t raw_chunk_pos(uint32_t l, uint32_t t, uint32_t T) {
+    return (T & 3u) ? t : ((((t >> 2) ^ raw_swizzle(l, T >> 2)) << 2) | (t & 3u));
+}
+
 __device__ __forceinline__ float group_reduce8(float acc) {
     acc = __fadd_rn(acc, __shfl_xor_sync(kFull, acc, 4));  // s[l] = acc[l] + acc[l+4]
     acc = __fadd_rn(acc, __shfl_xor_sync(kFull, acc, 1));  // s0+s1 | s2+s3
@@ -277,7 +288,8 @@ __device__ __forceinline__ float group_reduce8(float acc) {
     return acc;
 }
 
-// XSMEM: xrow points into shared memory (a staged vector) instead of HBM.
+// XSMEM: xrow points into shared memory (a staged vector) instead of HBM.  xrow = row (lane & 7) of a vector in the
+// swizzled accumulator-major layout (raw_chunk_pos); qrow = the same row of the query, unswizzled, row stride T + 4.
 template <bool L2, bool XSMEM = false>
 __device__ __forceinline__ float group_chain(const float* __restrict__ xrow, const float* __restrict__ qrow,
                                              uint32_t T, bool active) {
@@ -287,9 +299,10 @@ __device__ __forceinline__ float group_chain(const float* __restrict__ xrow, con
             const float4* xp = reinterpret_cast<const float4*>(xrow);
             const float4* qp = reinterpret_cast<const float4*>(qrow);
             const uint32_t nv = T >> 2;
+            const uint32_t sw = raw_swizzle(threadIdx.x & 7u, nv);
 #pragma unroll 4
             for (uint32_t j = 0; j < nv; ++j) {
-                const float4 x = XSMEM ? xp[j] : __ldg(xp + j);
+                const float4 x = XSMEM ? xp[j ^ sw] : __ldg(xp + (j ^ sw));
                 const float4 q = qp[j];
                 if (L2) {
                     float d;

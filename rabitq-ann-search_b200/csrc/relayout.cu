@@ -89,7 +89,8 @@ __global__ void relayout_raw_kernel(const DevIndex ix, const float* __restrict__
     for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
         const size_t v = o / D;
         const uint32_t i = (uint32_t)(o % D);
-        const_cast<float*>(ix.rawT)[(first + v) * D + (size_t)(i & 7u) * T + (i >> 3)] = raw[o];
+        const uint32_t l = i & 7u, t = i >> 3;
+        const_cast<float*>(ix.rawT)[(first + v) * D + (size_t)l * T + raw_chunk_pos(l, t, T)] = raw[o];
     }
 }
 
