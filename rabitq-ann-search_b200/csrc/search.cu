@@ -204,9 +204,17 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+// The records an expansion reads (3 KB at a random place of a multi-GB index) are never read again by this query and
+// hardly ever by another before L2 has turned over: they are fetched with an evict-first policy, which leaves L2 to the
+// data that IS re-read -- the "estimated" bitmaps (32 atomics per expansion) and the frontier arenas.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
     uint32_t done;
@@ -221,7 +229,8 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // current one (the kernel reserves 16 bytes per barrier); a bulk copy is a memcpy by the issuing thread
 inline void mbar_init(uint64_t* bar, uint32_t) { bar[1] = 0; __atomic_store_n(&bar[0], 0, __ATOMIC_RELEASE); }
 inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { bar[1] = bytes; }
-inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+inline uint64_t l2_evict_first_policy() { return 0; }
+inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t) {
     memcpy(dst, src, bytes);
     bar[1] -= bytes;
     if (bar[1] == 0) __atomic_fetch_add(&bar[0], 1, __ATOMIC_RELEASE);
@@ -467,8 +476,9 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             // start the HBM reads of this expansion before the heap work: neighbour block and raw vector
             if (expand && lane == 0) {
                 mbar_expect_tx(mbar, blk_bytes + D * 4);
-                bulk_g2s(stage, ix.blocks + (size_t)cur * block_stride, blk_bytes, mbar);
-                bulk_g2s(stage + raw_off, ix.rawT + (size_t)cur * D, D * 4, mbar);
+                const uint64_t pol = l2_evict_first_policy();
+                bulk_g2s(stage, ix.blocks + (size_t)cur * block_stride, blk_bytes, mbar, pol);
+                bulk_g2s(stage + raw_off, ix.rawT + (size_t)cur * D, D * 4, mbar, pol);
             }
             heap_pop(w, heap_n);
             --heap_n;
