@@ -25,6 +25,7 @@ from pathlib import Path
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent
+T_START = time.time()
 sys.path.insert(0, str(ROOT / "rabitq-ann-search_b200"))
 TMP_CACHE = Path("/tmp/cphnsw_b200_bench_cache")
 # The reference's NNDescent build depends on its OpenMP thread count (16 threads and 32 threads give graphs that cost
@@ -592,7 +593,10 @@ def main():
     ap.add_argument("--no-stream", action="store_true", help="skip the K2 FastScan streaming micro-benchmark")
     ap.add_argument("--no-gate", action="store_true", help="skip the recall@10 >= 0.95 operating point")
     ap.add_argument("--gate", type=float, default=0.95)
-    ap.add_argument("--gate-bits", default="4", help="code widths swept for the recall gate on the n x dim shape, in this order (each needs its own index)")
+    ap.add_argument("--gate-bits", default="4,2", help="code widths swept live for the recall gate on the n x dim shape, in this order (each needs its own "
+                                                     "index: ~105 s of build per width at 1M); 1-bit at 1M runs at ~300 QPS and is reported from the recorded "
+                                                     "sweep profiles/recall_sweep_1m_r02.json unless asked for here")
+    ap.add_argument("--time-budget", type=float, default=240.0, help="seconds of wall time after which optional extras (further gate widths) are skipped")
     ap.add_argument("--gate-ks", default="20,40,80,160", help="k_search values of the sweep")
     ap.add_argument("--inflight", type=int, default=2, help="batches in flight (1 = each step waits for the previous one)")
     ap.add_argument("--opt", action="append", default=[], help="library tuning option name=value (does not change results)")
@@ -879,6 +883,10 @@ def main():
             ks_list = [int(x) for x in args.gate_ks.split(",")]
             sweeps, gate = [], None
             for gb in [int(x) for x in args.gate_bits.split(",") if x]:
+                need_s = 0.0 if gb == args.bits else 130.0 * args.n / 1e6      # index build + sweep of another width
+                if time.time() - T_START + need_s > args.time_budget:
+                    log(f"[bench] recall sweep at {gb} bits skipped: time budget ({args.time_budget:.0f} s)")
+                    continue
                 try:
                     sw = recall_sweep(args, local, torch, cphnsw_b200, args.n, gb, ks_list, ix=ix if gb == args.bits else None)
                 except Exception as e:  # noqa: BLE001 - a secondary figure must not take the bench line down
@@ -892,6 +900,15 @@ def main():
                                                            "note": "no (bits, k_search) tried clears the gate on this data; both arms return identical ids, "
                                                                    "so this is the reference's own search quality (SURVEY H5)"}
             line["recall_gate"]["sweeps"] = [{k_: v for k_, v in sw.items() if k_ in ("bits", "n", "curve", "reached", "index_file")} for sw in sweeps]
+            rec = ROOT / "profiles" / "recall_sweep_1m_r02.json"
+            if rec.exists() and args.n == 1_000_000 and args.dim == 128 and not args.clusters:
+                try:      # widths not swept live in this run, as recorded by the builder with the same code path (file says how)
+                    rj = json.loads(rec.read_text())
+                    live = {sw["bits"] for sw in sweeps}
+                    line["recall_gate"]["sweeps_recorded"] = {"source": "profiles/recall_sweep_1m_r02.json", "how": rj.get("how"),
+                                                              "sweeps": [sw for sw in rj.get("sweeps", []) if sw.get("bits") not in live]}
+                except ValueError:
+                    pass
             del ix
             if not gate or gate["n"] != 100_000:
                 try:      # BASELINE configs[0]: the shape on which the reference itself is known to clear the gate
