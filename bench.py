@@ -467,17 +467,14 @@ def run_c4(args, rank, world, local):
     gq = torch.Generator(device=dev); gq.manual_seed(99)
     q_dev = torch.randn((nq, dim), generator=gq, device=dev)
     q_pin = q_dev.cpu().pin_memory()
-    all_i = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
-    all_d = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
 
-    def step_dev(q):
-        ids, d = hooks.exhaustive_search(ix, q, k, kp)
-        ids = torch.where(ids >= 0, ids + b, ids)          # shard-local -> global ids
+    def step_dev(q, kp_=None):
+        kp_ = kp if kp_ is None else kp_
         if world == 1:
-            return ids, d
-        dist.all_gather_into_tensor(all_i, ids)
-        dist.all_gather_into_tensor(all_d, d)
-        return sharding.merge_topk_device(all_i, all_d, k)
+            return hooks.exhaustive_search(ix, q, k, kp_)           # one scan of the whole database
+        # shards scan their ranges in pieces, exchange thresholds (all-reduce(min) of nq floats), all-gather their k' candidates
+        # (key + exact distance) and merge: the same result as the single scan (tests/test_exhaustive_gpu.py, test_multigpu_gpu.py)
+        return sharding.exhaustive_search_db_sharded_device(ix, q, k, kp_, m, n, b, prefix=args.c4_prefix, growth=args.c4_growth)
 
     def barrier():
         if world > 1:
@@ -491,20 +488,22 @@ def run_c4(args, rank, world, local):
         dist.all_reduce(t_, op=dist.ReduceOp.MAX)
         return float(t_.item())
 
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    def timed(kp_, steps, warmup):
+        evs_ = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        for _ in range(warmup):
+            step_dev(q_dev, kp_)
+        barrier()
+        t0_ = time.time()
+        evs_[0].record()
+        for i in range(steps):
+            out = step_dev(q_dev, kp_)
+            evs_[i + 1].record()
+        barrier()
+        return max_over_ranks(evs_[0].elapsed_time(evs_[-1])), [evs_[i].elapsed_time(evs_[i + 1]) for i in range(steps)], out, t0_
+
     with ClockSampler(local) as clocks:
-        for _ in range(args.warmup):
-            step_dev(q_dev)
-        barrier()
-        t_begin = time.time()
-        evs[0].record()
-        for i in range(args.steps):
-            out_i, out_d = step_dev(q_dev)
-            evs[i + 1].record()
-        barrier()
+        dev_ms, step_ms, (out_i, out_d), t_begin = timed(kp, args.steps, args.warmup)
         clocks.window(t_begin, time.time())
-    dev_ms = max_over_ranks(evs[0].elapsed_time(evs[-1]))
-    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     value = nq * args.steps / (dev_ms / 1e3)
     # e2e: queries from pinned host memory, results back to the host, every step
     ids_pin = torch.empty((nq, k), dtype=torch.int64).pin_memory()
@@ -517,7 +516,7 @@ def run_c4(args, rank, world, local):
         torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t1)
 
-    # roofline of the scan kernel: tensor pipe, 2 D int8 operations per (vertex, query) pair of this rank's shard
+    # roofline of the scan kernel: tensor pipe, 2 D operations per (vertex, query) pair of this rank's shard
     pairs = float(m) * nq
     scan_ms = float(np.mean(step_ms))
     peaks = {}
@@ -525,46 +524,60 @@ def run_c4(args, rank, world, local):
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
     except (OSError, ValueError):
         pass
-    bf16 = float(peaks.get("bf16_tflops", peaks.get("bf16_tfs", 1650.0)))
+    bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1420.0)))
     achieved = pairs * 2 * D / (scan_ms / 1e3) / 1e12
     form = {2: ("exhaustive_scan_tc16_kernel (tcgen05.mma kind::f16, M=128 N=256 K=16 x 9: 128 code dimensions + 16 threshold columns, "
-                "f32 accumulators in TMEM)", "f16 x f16 -> f32 (tcgen05 kind::f16)", bf16, "MEASURED_PEAKS bf16 (f16 runs at the same rate)", "TFLOP/s"),
+                "f32 accumulators in TMEM)", "f16 x f16 -> f32 (tcgen05 kind::f16)", bf16, "MEASURED_PEAKS bf16_tflops_sustained (f16 runs at the bf16 rate; "
+                "the kernel is timed inside a step)", "TFLOP/s"),
             1: ("exhaustive_scan_tc_kernel (tcgen05.mma kind::i8, M=128 N=256 K=32)", "u8 x u8 -> s32 (tcgen05 kind::i8) + f32", 2.0 * bf16,
-                "2 x MEASURED_PEAKS bf16 (int8 dense rate is twice bf16)", "TOP/s"),
-            0: ("exhaustive_scan_kernel (popcount form)", "u32 popcount sums + f32", 2.0 * bf16, "2 x MEASURED_PEAKS bf16 (int8 dense rate)", "TOP/s")}[args.scan_form]
+                "2 x MEASURED_PEAKS bf16 sustained (int8 dense rate is twice bf16)", "TOP/s"),
+            0: ("exhaustive_scan_kernel (popcount form)", "u32 popcount sums + f32", 2.0 * bf16, "2 x MEASURED_PEAKS bf16 sustained (int8 dense rate)", "TOP/s")}[args.scan_form]
+    pieces = sharding.scan_pieces(m, world, n, args.c4_prefix, args.c4_growth) if world > 1 else [(0, m)]
     line = {"metric": "QPS (exhaustive batched scan, queries/s over the whole database)", "value": value, "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": form[1], "data": "synthetic",
             "config": {"workload": f"c4: {n}x{dim} synthetic iid N(0,1), 1-bit RaBitQ codes, exhaustive scan, {nq} queries, k={k}, k'={kp}",
-                       "parallelism": f"database sharded x{world}, per-shard top-k, NCCL all-gather, device merge",
+                       "parallelism": f"database sharded x{world}: {len(pieces)} scan pieces per shard, thresholds exchanged by NCCL all-reduce(min) between "
+                                      f"them, all-gather of k' candidates (key + exact distance), merge kernel; result = one scan of the whole database",
                        "l2": "the scan streams codes + 256-query operands; candidate lists live in L2 by design"},
             "e2e": {"value": nq * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * k * 12},
-            "gpu_launches": (9 if args.scan_form == 2 else 5) * args.steps,
+            "gpu_launches": (9 if args.scan_form == 2 else 5) * args.steps if world == 1 else (6 * len(pieces) + 2) * args.steps,
             "roofline": {"bound": "tensor", "kernel": form[0], "achieved": achieved, "peak": form[2], "peak_source": form[3], "unit": form[4],
                          "frac": achieved / form[2], "traffic": None, "pairs_per_s_per_gpu": pairs / (scan_ms / 1e3),
                          "algorithmic_ops_per_pair": 2 * D,
-                         "note": "whole step timed (prep + threshold prefix pass + scan + select/rerank + merge); the scan kernel is > 90% of it "
-                                 "(DESIGN.md section 4, K5)"},
+                         "note": "whole step timed (K1 + threshold prefix + scan + select / re-rank, and for N > 1 the exchanges and the merge); the scan "
+                                 "kernel is ~90% of it at N = 1 (DESIGN.md section 4, K5)"},
             "clocks": clocks.summary(), "step_ms": [round(x, 3) for x in step_ms]}
-    if rank == 0:
-        # recall@10 of the 1-bit estimate + exact rerank against brute force, on a sample of the queries (shard 0's view
-        # is the whole database only at N = 1; otherwise scored on the merged result against this rank's shard is not
-        # meaningful, so N > 1 skips it)
-        if world == 1 and not args.no_recall:
-            ns = min(nq, 500)
-            qs = q_dev[:ns]
-            bd = torch.full((ns, k), float("inf"), device=dev); bi = torch.zeros((ns, k), dtype=torch.int64, device=dev)
-            for s in range(0, m, chunk):
-                bb = base[s:s + chunk]
-                dd = (qs * qs).sum(1, keepdim=True) - 2.0 * (qs @ bb.T) + (bb * bb).sum(1)[None, :]
-                td, ti = torch.topk(dd, k, dim=1, largest=False)
-                cd, ci = torch.cat([bd, td], 1), torch.cat([bi, ti + s], 1)
-                bd, sel = torch.topk(cd, k, dim=1, largest=False)
-                bi = torch.gather(ci, 1, sel)
-            line["recall_at_10"] = recall_at_k(out_i[:ns].cpu().numpy(), bi.cpu().numpy())
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if rank == 0 and world == 1 and not args.no_recall:
+        # recall@10 of (1-bit estimate -> k' candidates -> exact re-rank) against brute force, per re-rank depth k': the
+        # operating point is a choice of k' (the scan's tensor-core forms reach k' = 256; beyond, the popcount form)
+        ns = min(nq, 500)
+        qs = q_dev[:ns]
+        bd = torch.full((ns, k), float("inf"), device=dev); bi = torch.zeros((ns, k), dtype=torch.int64, device=dev)
+        for s_ in range(0, m, chunk):
+            bb = base[s_:s_ + chunk]
+            dd = (qs * qs).sum(1, keepdim=True) - 2.0 * (qs @ bb.T) + (bb * bb).sum(1)[None, :]
+            td, ti = torch.topk(dd, k, dim=1, largest=False)
+            cd, ci = torch.cat([bd, td], 1), torch.cat([bi, ti + s_], 1)
+            bd, sel = torch.topk(cd, k, dim=1, largest=False)
+            bi = torch.gather(ci, 1, sel)
+        gt = bi.cpu().numpy()
+        line["recall_at_10"] = recall_at_k(out_i[:ns].cpu().numpy(), gt)
+        curve = []
+        for kp_ in sorted({100, 256, 1024} | {kp}):
+            oi, _ = hooks.exhaustive_search(ix, qs, k, kp_)
+            entry = {"kprime": kp_, "recall_at_10": recall_at_k(oi.cpu().numpy(), gt)}
+            if kp_ != kp and kp_ <= 256:
+                ms_, _, _, _ = timed(kp_, 2, 1)
+                entry["qps"] = nq * 2 / (ms_ / 1e3)
+            elif kp_ == kp:
+                entry["qps"] = value
+            curve.append(entry)
+            log(f"[bench] c4: k'={kp_}: recall@{k} = {entry['recall_at_10']:.4f}" + (f" at {entry['qps']:.0f} QPS" if "qps" in entry else ""))
+        line["recall_by_kprime"] = curve
+    del ix, base
+    torch.cuda.empty_cache()
+    return line
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -576,7 +589,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
                     help="c2: BASELINE configs[1], graph search (the default and the headline); c4: configs[3], exhaustive scan")
-    ap.add_argument("--kprime", type=int, default=100, help="c4: rerank depth")
+    ap.add_argument("--kprime", type=int, default=256, help="c4: re-rank depth (256 = the most the tensor-core scan forms keep per query)")
+    ap.add_argument("--c4-n", type=int, default=10_000_000, help="database size of the c4 sub-run of the default workload")
+    ap.add_argument("--c4-prefix", type=int, default=65536, help="c4, N > 1: vertices (over all shards) scanned before the first threshold exchange")
+    ap.add_argument("--c4-growth", type=int, default=4, help="c4, N > 1: each later scan piece covers growth - 1 times what has been scanned")
+    ap.add_argument("--no-c4", action="store_true", help="default workload: skip the c4 (exhaustive scan, DB-sharded) sub-run")
     ap.add_argument("--scan-form", type=int, default=2, choices=[0, 1, 2],
                     help="c4: 2 = tcgen05 kind::f16 scan with the candidate screen folded into the contraction (default), "
                          "1 = tcgen05 kind::i8 scan + float screen, 0 = popcount scan; results are identical")
@@ -621,7 +638,11 @@ def main():
             import torch.distributed as dist
 
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        run_c4(args, rank, world, local)
+        line = run_c4(args, rank, world, local)
+        if rank == 0:
+            print(json.dumps(line))
+        if world > 1:
+            torch.distributed.destroy_process_group()
         return
     metric = "QPS (search_batch queries/s; recall@10 of the reference on the same index reported beside it)"
 
@@ -653,7 +674,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from datetime import timedelta
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=timedelta(minutes=8))   # (rank 0 may build the index: ~2 min)
     import cphnsw_b200
 
     path, src = obtain_index(args, rank, world)
@@ -859,6 +882,20 @@ def main():
                                    # SURVEY 8(d)'s figure counts what a block READS; this stand-alone kernel also writes est + lower (2 x 128 B per block)
                                    "output_bytes_per_block": 256, "achieved_with_output": nblk * (fs_bytes + 256) / (fs_ms / 1e3) / 1e9,
                                    "frac_with_output": nblk * (fs_bytes + 256) / (fs_ms / 1e3) / 1e9 / peak}
+
+    # -- BASELINE config 4 beside it: the exhaustive batched scan over 10M x 96 1-bit codes, database sharded over the ranks
+    #    (strong scaling; NCCL threshold exchange + all-gather + merge kernel).  All ranks take part.
+    if not args.no_c4:
+        import copy
+
+        ca = copy.copy(args)
+        ca.n, ca.steps, ca.warmup = args.c4_n, max(2, min(args.steps, 5)), max(1, min(args.warmup, 2))
+        try:
+            c4 = run_c4(ca, rank, world, local)
+            line["c4"] = {k_: c4[k_] for k_ in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "config", "e2e",
+                                                "gpu_launches", "roofline", "clocks", "step_ms", "recall_at_10", "recall_by_kprime") if k_ in c4}
+        except Exception as e:  # noqa: BLE001 - a secondary figure must not take the bench line down
+            log(f"[bench] rank {rank}: c4 sub-run skipped: {type(e).__name__}: {e}")
 
     if rank == 0:
         ids_np = ids_dev.cpu().numpy()

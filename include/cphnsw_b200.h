@@ -163,6 +163,26 @@ int cphnsw_b200_greedy_descent(cphnsw_b200_index* ix, const float* d_queries, ui
 int cphnsw_b200_exhaustive_search(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq,
                                   uint64_t k, uint64_t kprime, uint64_t id_begin, uint64_t id_end,
                                   int64_t* d_ids, float* d_dists, void* stream);
+/* The scan in pieces -- a database sharded over GPUs, each shard scanned range by range -- with the single-scan result:
+ * writes to d_keys_out [nq][kprime] the kprime smallest keys (estimate bits << 32 | id, ascending, 0xFF..FF padding) of
+ * d_prior_keys (the keys_out of earlier ranges of this index; may be NULL) and the vertices of [id_begin, id_end).
+ * d_tau_in [nq] (may be NULL; FLT_MAX = none): upper bounds of the final kprime-th estimate learnt elsewhere (other
+ * shards, through an all-reduce(min) of d_tau_out) -- pairs above them are dropped early, which is what keeps a shard's
+ * work proportional to its size.  d_tau_out [nq] (may be NULL): the estimate of the kprime-th key written (FLT_MAX while
+ * there are fewer).  The last piece passes d_dists_out [nq][kprime]: the exact distances (search/rabitq_search.hpp:88-93)
+ * of the keys, whose ids are then also shifted by id_offset (shard-local -> global; must stay below 2^32). */
+int cphnsw_b200_exhaustive_candidates(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq, uint64_t kprime,
+                                      uint64_t id_begin, uint64_t id_end, uint64_t id_offset,
+                                      const uint64_t* d_prior_keys, const float* d_tau_in, uint64_t* d_keys_out,
+                                      float* d_dists_out, float* d_tau_out, void* stream);
+/* Merge of `lists` candidate lists (d_keys [lists][nq][kprime] with d_dists alongside: what every shard wrote, gathered):
+ * the kprime smallest keys overall, then the k smallest (distance, id) of those -- exactly what
+ * cphnsw_b200_exhaustive_search returns on the whole database.  d_tau_out [nq] (may be NULL): the estimate of the
+ * kprime-th smallest key; with k == 0 or d_ids_out == NULL only that is computed (then d_dists may be NULL).
+ * lists * kprime <= 16384. */
+int cphnsw_b200_merge_candidates(cphnsw_b200_index* ix, const uint64_t* d_keys, const float* d_dists, uint64_t lists,
+                                 uint64_t nq, uint64_t kprime, uint64_t k, int64_t* d_ids_out, float* d_dists_out,
+                                 float* d_tau_out, void* stream);
 /* Estimator only: integer sums [nq][id_end-id_begin] u32 and estimates f32 (either may be NULL). */
 int cphnsw_b200_exhaustive_estimates(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq,
                                      uint64_t id_begin, uint64_t id_end,

@@ -139,6 +139,44 @@ def neighbor_codes(ix, vectors: torch.Tensor, nbr_ids: torch.Tensor, parent_ids:
     return (codes, aux, blk) if blocks else (codes, aux)
 
 
+def exhaustive_candidates(ix, queries: torch.Tensor, kprime: int, id_begin: int, id_end: int, id_offset: int = 0,
+                          prior_keys: torch.Tensor | None = None, tau_in: torch.Tensor | None = None, want_dists: bool = False):
+    """One piece of a scan done in pieces (cphnsw_b200_exhaustive_candidates): the kprime smallest (estimate, id) keys of
+    `prior_keys` U [id_begin, id_end) as an int64 tensor [nq, kprime] holding the uint64 bit patterns (estimate bits << 32 |
+    id; -1 = padding), their exact distances [nq, kprime] when want_dists (the last piece: ids are then shifted by
+    id_offset), and tau [nq] = the estimate of the kprime-th key (FLT_MAX while fewer).  tau_in [nq]: bounds from elsewhere."""
+    dev = _dev(ix)
+    q = queries.to(dev, torch.float32).contiguous()
+    nq = q.shape[0]
+    keys = torch.empty((nq, kprime), dtype=torch.int64, device=dev)
+    dists = torch.empty((nq, kprime), dtype=torch.float32, device=dev) if want_dists else None
+    tau = torch.empty((nq,), dtype=torch.float32, device=dev)
+    pk = None if prior_keys is None else prior_keys.to(dev, torch.int64).contiguous()
+    ti = None if tau_in is None else tau_in.to(dev, torch.float32).contiguous()
+    assert pk is None or tuple(pk.shape) == (nq, kprime)
+    assert ti is None or tuple(ti.shape) == (nq,)
+    _capi.check(ix.handle, ix._lib.cphnsw_b200_exhaustive_candidates(
+        ix.handle, q.data_ptr(), nq, kprime, id_begin, id_end, id_offset, _ptr(pk), _ptr(ti), keys.data_ptr(), _ptr(dists),
+        tau.data_ptr(), _stream(ix)))
+    return keys, dists, tau
+
+
+def merge_candidates(ix, keys: torch.Tensor, dists: torch.Tensor | None, k: int):
+    """cphnsw_b200_merge_candidates: keys int64 [lists, nq, kprime] (+ dists float32 alongside) -> (ids int64 [nq, k], dists
+    float32 [nq, k], tau float32 [nq]); with dists None or k == 0 only tau (ids, dists are None)."""
+    dev = _dev(ix)
+    kk = keys.to(dev, torch.int64).contiguous()
+    lists, nq, kp = kk.shape
+    dd = None if dists is None else dists.to(dev, torch.float32).contiguous()
+    tau = torch.empty((nq,), dtype=torch.float32, device=dev)
+    want = dd is not None and k > 0
+    ids = torch.empty((nq, k), dtype=torch.int64, device=dev) if want else None
+    out = torch.empty((nq, k), dtype=torch.float32, device=dev) if want else None
+    _capi.check(ix.handle, ix._lib.cphnsw_b200_merge_candidates(
+        ix.handle, kk.data_ptr(), _ptr(dd), lists, nq, kp, k if want else 0, _ptr(ids), _ptr(out), tau.data_ptr(), _stream(ix)))
+    return ids, out, tau
+
+
 def upload_arrays(ix, *, D, bits, dim, search_data, raw, norm_sq, calibration, centroid=None, max_level=0,
                   entry_point=0, graph_entry_point=0, rotation_seed=42, layers=()):
     """cphnsw_b200_upload from numpy arrays laid out like the reference's in-memory index.

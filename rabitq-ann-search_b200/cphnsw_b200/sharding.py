@@ -6,10 +6,12 @@ Two modes:
   src/bindings.cpp:196-200): every rank holds the whole index, searches a contiguous slice of the
   queries, and the slices are concatenated.  No data-path collective; the optional all-gather only
   serves callers that want the full result on every rank.
-* exhaustive scan -- the database is split into contiguous internal-id ranges, every rank scans its
-  range for all queries and keeps a local top-k; one all-gather of [nq, k] (id, distance) pairs and a
-  local k-way merge ordered by (distance, id) give the global top-k.  Exact: the global top-k is a
-  subset of the union of the per-shard top-k lists.
+* exhaustive scan -- the database is split into contiguous internal-id ranges; every rank scans its range
+  for all queries and keeps its k' best (estimate, id) candidates with their exact distances; one
+  all-gather of those and a merge on every rank (the k' best estimates overall, then the k best
+  distances among them) give exactly what one scan of the whole database gives.  Thresholds are
+  exchanged on the way (all-reduce(min) of nq floats at a few points) so that a shard's work shrinks with
+  its size instead of every shard re-discovering them.
 
 `local_search` arguments make the plumbing testable on CPU (gloo) with any callable.
 """
@@ -108,23 +110,91 @@ def search_batch_query_sharded(local_search, queries: np.ndarray, k: int, gather
     return out_i, out_d
 
 
-def exhaustive_search_db_sharded(local_scan, n: int, queries: np.ndarray, k: int, kprime: int, group=None):
-    """Exhaustive scan with the database split across ranks.
+def scan_pieces(n_local: int, world: int, n_total: int | None = None, prefix: int = 65536, growth: int = 4) -> list[tuple[int, int]]:
+    """Ranges [begin, end) in which a shard of n_local vertices is scanned.  The first piece is the shard's part of the
+    threshold prefix (the shards' first pieces together hold `prefix` vertices, what a single scan uses to find its
+    first thresholds); every later piece is `growth` - 1 times what has been scanned so far, so thresholds are exchanged
+    after 1/world of the prefix, then at geometrically spaced points -- a handful of all-reduces of nq floats.
+    The plan is laid out for the largest shard (ceil(n_total / world)) and clipped to n_local, so that every rank makes
+    the same number of exchanges (a smaller shard's last piece may be empty)."""
+    world = max(world, 1)
+    n_ref = max(n_local, -(-(n_total if n_total is not None else n_local * world) // world))
+    first = max(1024, -(-prefix // world))
+    out, b, size = [], 0, first
+    while True:
+        e = min(n_ref, b + size)
+        if n_ref - e < size // 2:     # do not leave a sliver
+            e = n_ref
+        out.append((min(b, n_local), min(e, n_local)))
+        if e >= n_ref:
+            return out
+        size = e * (growth - 1)
+        b = e
 
-    local_scan(queries, k, kprime, id_begin, id_end) -> (ids [nq,k] global internal ids, dists [nq,k]) is the
-    rank's own scan of its id range.  One all-gather (NCCL over NVLink when the group is nccl) of the
-    per-shard top-k, then a local merge; every rank returns the global result."""
+
+def _all_gather_stacked(t, world, group):
+    """[world, *t.shape] on every rank (one NCCL all-gather into a single tensor; gloo gathers into a list)."""
     import torch
 
     dist = _dist()
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    b, e = db_shard(n, rank, world)
-    ids, dists = local_scan(queries, k, kprime, b, e)
-    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-    ti = torch.as_tensor(ids, device=dev).to(torch.int64).contiguous()
-    td = torch.as_tensor(dists, device=dev).to(torch.float32).contiguous()
-    all_i = [torch.empty_like(ti) for _ in range(world)]
-    all_d = [torch.empty_like(td) for _ in range(world)]
-    dist.all_gather(all_i, ti, group=group)
-    dist.all_gather(all_d, td, group=group)
-    return merge_topk(torch.stack(all_i).cpu().numpy(), torch.stack(all_d).cpu().numpy(), k)
+    t = t.contiguous()
+    if dist.get_backend(group) == "nccl":
+        out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t, group=group)
+        return out
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t, group=group)
+    return torch.stack(parts)
+
+
+def exhaustive_search_db_sharded(local_candidates, merge_candidates, n_local: int, n_total: int, id_offset: int, queries, k: int,
+                                 kprime: int, group=None, prefix: int = 65536, growth: int = 4):
+    """Exhaustive scan with the database split across the ranks of `group`; returns on every rank what ONE scan of the
+    whole database returns: the kprime smallest (estimate, id) overall, exact distances, the k smallest (distance, id).
+
+    local_candidates(queries, kprime, begin, end, id_offset, prior_keys, tau_in, want_dists) -> (keys, dists, tau) and
+    merge_candidates(keys [lists, nq, kprime], dists | None, k) -> (ids, dists, tau) are hooks.exhaustive_candidates /
+    hooks.merge_candidates bound to the rank's index (tests pass CPU stand-ins); tensors live wherever those put them.
+
+    Every shard scans its range in pieces (scan_pieces).  After the first piece the shards all-gather their candidate
+    keys and take the kprime-th smallest of the union as the first common threshold; after every later piece one
+    all-reduce(min) of the per-query thresholds (nq floats).  A threshold is only ever an upper bound of the final
+    kprime-th estimate, so dropping pairs above it cannot change the result -- it only keeps a shard from collecting
+    candidates the other shards have already ruled out.  At the end: one all-gather of every shard's kprime keys +
+    exact distances, merged on every rank."""
+    import torch
+
+    dist = _dist() if group is not None or _dist().is_initialized() else None
+    world = dist.get_world_size(group) if dist else 1
+    pieces = scan_pieces(n_local, world, n_total, prefix, growth)
+    keys = dists = tau = None
+    for c, (b, e) in enumerate(pieces):
+        last = c == len(pieces) - 1
+        keys, dists, tau_local = local_candidates(queries, kprime, b, e, id_offset, keys, tau, last)
+        if last:
+            break
+        if world == 1:
+            tau = tau_local
+        elif c == 0:
+            tau = merge_candidates(_all_gather_stacked(keys, world, group), None, 0)[2]
+        else:
+            tau = tau_local.clone()
+            dist.all_reduce(tau, op=dist.ReduceOp.MIN, group=group)
+    if world == 1:
+        return merge_candidates(keys[None], dists[None], k)[:2]
+    return merge_candidates(_all_gather_stacked(keys, world, group), _all_gather_stacked(dists, world, group), k)[:2]
+
+
+def exhaustive_search_db_sharded_device(ix, queries, k: int, kprime: int, n_local: int, n_total: int, id_offset: int, group=None,
+                                        prefix: int = 65536, growth: int = 4):
+    """exhaustive_search_db_sharded on the rank's `ix` (a cphnsw_b200.CPIndex holding the shard); CUDA tensors throughout,
+    NCCL for the exchanges."""
+    from . import hooks
+
+    def cand(q, kp, b, e, off, prior, tau, want):
+        return hooks.exhaustive_candidates(ix, q, kp, b, e, off, prior, tau, want)
+
+    def merge(keys, dists, kk):
+        return hooks.merge_candidates(ix, keys, dists, kk)
+
+    return exhaustive_search_db_sharded(cand, merge, n_local, n_total, id_offset, queries, k, kprime, group, prefix, growth)

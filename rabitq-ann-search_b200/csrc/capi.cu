@@ -944,9 +944,18 @@ int cphnsw_b200_greedy_descent(cphnsw_b200_index* ix, const float* d_queries, ui
 
 extern "C" {
 
+struct CandArgs {   // candidate mode of the scan (kernels.h: ExhaustiveArgs)
+    const unsigned long long* prior_keys = nullptr;
+    const float* tau_in = nullptr;
+    unsigned long long* keys = nullptr;
+    float* dists = nullptr;
+    float* tau_out = nullptr;
+    uint64_t id_offset = 0;
+};
+
 static int run_exhaustive(cphnsw_b200_index* ix, Lane& L, const float* d_queries, uint64_t nq, uint64_t k, uint64_t kprime,
                           uint64_t id_begin, uint64_t id_end, int64_t* d_ids, float* d_dists, uint32_t* d_sums,
-                          float* d_est, cudaStream_t st) {
+                          float* d_est, cudaStream_t st, const CandArgs* cand = nullptr) {
     const DevIndex& d = ix->dev;
     QStateView qs;
     int rc = ensure_qstate(ix, L, nq, &qs);
@@ -960,6 +969,10 @@ static int run_exhaustive(cphnsw_b200_index* ix, Lane& L, const float* d_queries
     a.use_tensor_cores = (int)ix->exhaustive_tensor_cores;
     a.id_begin = id_begin; a.id_end = id_end; a.k = (uint32_t)k; a.kprime = (uint32_t)kprime;
     a.sums = d_sums; a.est = d_est; a.ids = d_ids; a.dists = d_dists;
+    if (cand) {
+        a.prior_keys = cand->prior_keys; a.tau_in = cand->tau_in; a.cand_keys = cand->keys; a.cand_dists = cand->dists;
+        a.tau_out = cand->tau_out; a.id_offset = cand->id_offset;
+    }
     const size_t wb = exhaustive_workspace_bytes(d, (uint32_t)nq, id_end - id_begin, (uint32_t)kprime, ix->num_sms);
     rc = ensure_buffer(ix, &L.scratch, &L.scratch_bytes, wb + 256, false);
     if (rc) return rc;
@@ -989,6 +1002,39 @@ int cphnsw_b200_exhaustive_search(cphnsw_b200_index* ix, const float* d_queries,
     return with_lane(ix, st, false, [&](Lane& L) {
         return run_exhaustive(ix, L, d_queries, nq, k, kprime, id_begin, id_end, d_ids, d_dists, nullptr, nullptr, st);
     });
+}
+
+int cphnsw_b200_exhaustive_candidates(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq, uint64_t kprime, uint64_t id_begin,
+                                      uint64_t id_end, uint64_t id_offset, const uint64_t* d_prior_keys, const float* d_tau_in,
+                                      uint64_t* d_keys_out, float* d_dists_out, float* d_tau_out, void* stream) {
+    int rc = require_loaded(ix);
+    if (rc) return rc;
+    if (nq && (!d_queries || !d_keys_out)) return fail(ix, CPHNSW_B200_EINVAL, "null buffer");
+    if (kprime == 0) return fail(ix, CPHNSW_B200_EINVAL, "kprime must be at least 1");
+    if ((rc = check_exhaustive(ix, nq, 0, kprime, id_begin, id_end))) return rc;
+    if (id_offset + ix->dev.n > 0xFFFFFFFFull) return fail(ix, CPHNSW_B200_EINVAL, "global ids must stay below 2^32");
+    if (nq == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CandArgs c;
+    c.prior_keys = reinterpret_cast<const unsigned long long*>(d_prior_keys); c.tau_in = d_tau_in;
+    c.keys = reinterpret_cast<unsigned long long*>(d_keys_out); c.dists = d_dists_out; c.tau_out = d_tau_out; c.id_offset = id_offset;
+    return with_lane(ix, st, false, [&](Lane& L) {
+        return run_exhaustive(ix, L, d_queries, nq, 0, kprime, id_begin, id_end, nullptr, nullptr, nullptr, nullptr, st, &c);
+    });
+}
+
+int cphnsw_b200_merge_candidates(cphnsw_b200_index* ix, const uint64_t* d_keys, const float* d_dists, uint64_t lists, uint64_t nq,
+                                 uint64_t kprime, uint64_t k, int64_t* d_ids_out, float* d_dists_out, float* d_tau_out, void* stream) {
+    if (!ix) return CPHNSW_B200_EINVAL;
+    if (nq == 0 || lists == 0) return 0;
+    if (!d_keys || (k && d_ids_out && (!d_dists || !d_dists_out))) return fail(ix, CPHNSW_B200_EINVAL, "null buffer");
+    if (kprime == 0 || kprime > 1024 || k > kprime || nq > 0x7FFFFFFFull || lists * kprime > 16384)
+        return fail(ix, CPHNSW_B200_EINVAL, "merge_candidates: need 1 <= kprime <= 1024, k <= kprime, lists * kprime <= 16384");
+    DeviceGuard dg(ix->device);
+    CUDA_TRY(ix, dg.err);
+    CUDA_TRY(ix, launch_merge_candidates(reinterpret_cast<const unsigned long long*>(d_keys), d_dists, (uint32_t)lists, (uint32_t)nq,
+                                         (uint32_t)kprime, (uint32_t)k, d_ids_out, d_dists_out, d_tau_out, static_cast<cudaStream_t>(stream)));
+    return 0;
 }
 
 int cphnsw_b200_exhaustive_estimates(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq, uint64_t id_begin,

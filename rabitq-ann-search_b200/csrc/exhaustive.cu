@@ -147,11 +147,22 @@ __global__ void __launch_bounds__(kExThreads) exhaustive_select_rerank_kernel(co
     for (uint32_t i = threadIdx.x; i < sort_n; i += blockDim.x) {
         unsigned long long key = kNoKey;
         if (i < total) { const uint32_t s = i / kp, j = i % kp; key = partial[((size_t)s * a.nq + q) * kp + j]; }
+        else if (a.prior_keys && i < total + kp) key = a.prior_keys[(size_t)q * kp + (i - total)];   // one more "slice": earlier pieces
         keys[i] = key;
     }
     for (uint32_t i = threadIdx.x; i < D; i += blockDim.x) qs[(i / T) * Tp + (i % T)] = a.qT[(size_t)q * D + i];
     __syncthreads();
     bitonic_sort(keys, sort_n);
+    if (a.cand_keys) {   // candidate mode: the k' best keys themselves (ascending), the threshold they imply
+        const bool final_piece = a.cand_dists != nullptr;
+        for (uint32_t j = threadIdx.x; j < kp; j += blockDim.x) {
+            const unsigned long long key = keys[j];
+            a.cand_keys[(size_t)q * kp + j] = (key != kNoKey && final_piece) ? key + a.id_offset : key;   // ids stay below 2^32 (checked by the caller)
+        }
+        if (a.tau_out && threadIdx.x == 0)
+            a.tau_out[q] = (kp && keys[kp - 1] != kNoKey) ? __uint_as_float((uint32_t)(keys[kp - 1] >> 32)) : FLT_MAX;
+        if (!final_piece) return;
+    }
     // exact distances of the k' best (estimate, id): 8 lanes per vector, the reference's accumulator order
     const float qn = a.coeffs[(size_t)q * kCoeffStride + 3];
     const uint32_t g = threadIdx.x >> 3, l = threadIdx.x & 7u, ngroups = blockDim.x >> 3;
@@ -161,10 +172,15 @@ __global__ void __launch_bounds__(kExThreads) exhaustive_select_rerank_kernel(co
         const bool act = key != kNoKey;
         const uint32_t id = act ? (uint32_t)key : 0u;
         const float dot = group_chain<false>(ix.rawT + (size_t)id * D + (size_t)l * T, qs + (size_t)l * Tp, T, act);
+        const float ex = act ? exact_from_dot(qn, __ldg(ix.norm_sq + id), dot) : FLT_MAX;
         __syncthreads();
-        if (j < kp && l == 0) keys[j] = act ? make_key(exact_from_dot(qn, __ldg(ix.norm_sq + id), dot), id) : kNoKey;
+        if (j < kp && l == 0) {
+            keys[j] = act ? make_key(ex, id) : kNoKey;
+            if (a.cand_dists) a.cand_dists[(size_t)q * kp + j] = ex;
+        }
         __syncthreads();
     }
+    if (a.cand_keys) return;
     // re-sort the first k' by (distance, id); entries beyond k' are not results
     for (uint32_t i = kp + threadIdx.x; i < sort_n; i += blockDim.x) keys[i] = kNoKey;
     __syncthreads();
@@ -188,7 +204,7 @@ static uint32_t pick_slices(uint64_t m, uint32_t kprime, uint32_t nq, int num_sm
     uint64_t s = ((uint64_t)8 * num_sms + qtiles - 1) / qtiles;          // enough CTAs for ~8 per SM
     const uint64_t by_len = (m + 4095) / 4096;                            // never shorter than 4 K vertices
     if (s > by_len) s = by_len;
-    const uint64_t cap = kprime ? (16384 / (uint64_t)kprime) : 64;
+    const uint64_t cap = kprime ? (16384 / (uint64_t)kprime > 1 ? 16384 / (uint64_t)kprime - 1 : 1) : 64;   // - 1: room for the list of earlier pieces
     if (s > cap) s = cap;
     if (s > 64) s = 64;
     return (uint32_t)(s < 1 ? 1 : s);
@@ -211,7 +227,9 @@ cudaError_t launch_exhaustive(const DevIndex& ix, const ExhaustiveArgs& a, int n
     const size_t smem = (size_t)kQT * cap * 8 + (size_t)kQT * ix.nch * 64 + (size_t)kQT * 16;
     cudaError_t e = cudaFuncSetAttribute(exhaustive_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    if (tc && a.use_tensor_cores >= 2 && exhaustive_tc16_applicable(ix, a.kprime)) {
+    // (a short range with no thresholds handed in would be scanned twice by the f16 form -- once by its own threshold
+    //  prefix -- so it goes to the i8 form directly; results are identical)
+    if (tc && a.use_tensor_cores >= 2 && exhaustive_tc16_applicable(ix, a.kprime) && (a.tau_in || m > 65536 || a.sums || a.est)) {
         e = launch_exhaustive_scan_tc16(ix, a, num_sms, partial, &nslices, stream);
         if (e != cudaSuccess) return e;
     } else if (tc) {
@@ -223,9 +241,9 @@ cudaError_t launch_exhaustive(const DevIndex& ix, const ExhaustiveArgs& a, int n
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    if (a.kprime && a.k) {
+    if (a.kprime && (a.k || a.cand_keys)) {
         uint32_t sort_n = 1;
-        while (sort_n < nslices * a.kprime) sort_n <<= 1;
+        while (sort_n < (nslices + (a.prior_keys ? 1u : 0u)) * a.kprime) sort_n <<= 1;
         const size_t smem2 = (((size_t)sort_n * 8 + 15) & ~(size_t)15) + (size_t)8 * (ix.T + 4) * 4;
         e = cudaFuncSetAttribute(exhaustive_select_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
         if (e != cudaSuccess) return e;
@@ -235,6 +253,70 @@ cudaError_t launch_exhaustive(const DevIndex& ix, const ExhaustiveArgs& a, int n
     return e;
 }
 
+#endif
+
+// ---- merge of per-shard candidate lists ---------------------------------------------------------------------------
+// One CTA per query.  Pass 1: all keys into shared memory, sorted: the k'-th smallest is the cut.  Pass 2: the entries at
+// or under the cut (at most k': keys are distinct, ids being global) are collected as (distance, id) keys, sorted, and the
+// k best written -- what a single scan of the whole database returns (same candidates, same tie rules).
+__global__ void __launch_bounds__(kExThreads) merge_candidates_kernel(const unsigned long long* __restrict__ gkeys,
+                                                                      const float* __restrict__ gdists, uint32_t lists, uint32_t nq,
+                                                                      uint32_t kp, uint32_t k, uint32_t sort_n, int64_t* __restrict__ ids_out,
+                                                                      float* __restrict__ dists_out, float* __restrict__ tau_out) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);   // [sort_n]
+    CPB_BLOCK_SHARED unsigned long long cut;
+    CPB_BLOCK_SHARED uint32_t cnt;
+    const uint32_t q = blockIdx.x, total = lists * kp;
+    for (uint32_t i = threadIdx.x; i < sort_n; i += blockDim.x)
+        keys[i] = i < total ? gkeys[((size_t)(i / kp) * nq + q) * kp + (i % kp)] : kNoKey;
+    __syncthreads();
+    bitonic_sort(keys, sort_n);
+    if (threadIdx.x == 0) {
+        cut = kp ? keys[kp - 1] : 0ull;   // kNoKey when fewer than k' candidates exist: everything is kept
+        cnt = 0;
+        if (tau_out) tau_out[q] = (kp && keys[kp - 1] != kNoKey) ? __uint_as_float((uint32_t)(keys[kp - 1] >> 32)) : FLT_MAX;
+    }
+    __syncthreads();
+    if (!gdists || !k || !ids_out) return;
+    const unsigned long long c = cut;
+    uint32_t n2 = 1;
+    while (n2 < kp) n2 <<= 1;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) keys[i] = kNoKey;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+        const size_t o = ((size_t)(i / kp) * nq + q) * kp + (i % kp);
+        const unsigned long long key = gkeys[o];
+        if (key != kNoKey && key <= c) {
+            const uint32_t slot = atomicAdd(&cnt, 1u);
+            if (slot < n2) keys[slot] = make_key(gdists[o], (uint32_t)key);
+        }
+    }
+    __syncthreads();
+    bitonic_sort(keys, n2);
+    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) {
+        const unsigned long long key = j < n2 ? keys[j] : kNoKey;
+        const bool have = key != kNoKey;
+        ids_out[(size_t)q * k + j] = have ? (int64_t)(uint32_t)key : (int64_t)-1;
+        dists_out[(size_t)q * k + j] = have ? __uint_as_float((uint32_t)(key >> 32)) : FLT_MAX;
+    }
+}
+
+#ifndef CPB_HOST_EMULATION
+cudaError_t launch_merge_candidates(const unsigned long long* keys, const float* dists, uint32_t lists, uint32_t nq, uint32_t kprime,
+                                    uint32_t k, int64_t* ids_out, float* dists_out, float* tau_out, cudaStream_t stream) {
+    if (nq == 0 || kprime == 0) return cudaSuccess;
+    uint32_t sort_n = 1;
+    while (sort_n < lists * kprime) sort_n <<= 1;
+    if (sort_n < 2) sort_n = 2;
+    const size_t smem = (size_t)sort_n * 8;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(merge_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    merge_candidates_kernel<<<nq, kExThreads, smem, stream>>>(keys, dists, lists, nq, kprime, k, sort_n, ids_out, dists_out, tau_out);
+    return cudaGetLastError();
+}
 #endif
 
 }  // namespace cpb

@@ -485,6 +485,14 @@ __global__ void __launch_bounds__(128) t16_tau_from_partial_kernel(const unsigne
     if (lane == 0 && cur < 0x7F000000u) atomicMin(taug + q, cur);
 }
 
+// thresholds handed in by the caller (other pieces of the scan, other shards): taug = min(taug, tau_in)
+__global__ void t16_seed_tau_kernel(uint32_t* __restrict__ taug, const float* __restrict__ tau_in, uint32_t nq) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const float t = tau_in[q];
+    if (t >= 0.0f && t < kTcTauInf) atomicMin(taug + q, __float_as_uint(t));
+}
+
 bool exhaustive_tc16_applicable(const DevIndex& ix, uint32_t kprime) {
     return kprime <= kTcMaxKPrime && ix.nch == 1 && ix.calib.affine_a > 0.0f;
 }
@@ -494,8 +502,9 @@ cudaError_t launch_exhaustive_scan_tc16(const DevIndex& ix, const ExhaustiveArgs
     const TcWorkspace w = tc_workspace(partial, a.nq, a.kprime, num_sms);
     const uint64_t m = a.id_end - a.id_begin;
     cudaError_t e;
-    // thresholds first: the i8 form over a prefix of the range (its candidate lists are not kept)
-    const uint64_t prefix = m < 65536 ? m : 65536;
+    // thresholds first: the caller's, or the i8 form over a prefix of the range (its candidate lists are not kept)
+    const bool seeded = a.tau_in != nullptr;
+    const uint64_t prefix = seeded ? 0 : (m < 65536 ? m : 65536);
     if (a.kprime && prefix) {
         e = launch_exhaustive_tc_prepare(ix, a.id_begin, a.id_begin + prefix, a.nq, w.vstat, w.taug, true, num_sms, stream);
         if (e != cudaSuccess) return e;
@@ -511,6 +520,11 @@ cudaError_t launch_exhaustive_scan_tc16(const DevIndex& ix, const ExhaustiveArgs
     }
     e = launch_exhaustive_tc_prepare(ix, a.id_begin, a.id_end, a.nq, w.vstat, w.taug, !(a.kprime && prefix), num_sms, stream);
     if (e != cudaSuccess) return e;
+    if (seeded && a.kprime) {
+        t16_seed_tau_kernel<<<(a.nq + 255) / 256, 256, 0, stream>>>(w.taug, a.tau_in, a.nq);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
     const TcSplit sp = tc_split(m, a.nq, a.kprime, num_sms);
     *nseg = sp.nseg;
     if (a.kprime) {

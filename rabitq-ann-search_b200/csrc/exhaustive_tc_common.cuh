@@ -183,8 +183,9 @@ inline TcSplit tc_split(uint64_t m, uint32_t nq, uint32_t kprime, int num_sms) {
     s.ngroups = (nq + kTcNQ - 1) / kTcNQ;
     s.tiles = (uint32_t)((m + kTcM - 1) / kTcM);
     const uint64_t units = (uint64_t)s.ngroups * s.tiles;
-    uint64_t maxseg = kprime ? 16384 / (uint64_t)kprime : 64;
+    uint64_t maxseg = kprime ? 16384 / (uint64_t)kprime - 1 : 64;   // - 1: the merge may take one more list (earlier pieces' candidates)
     if (maxseg > 64) maxseg = 64;
+    if (maxseg < 1) maxseg = 1;
     uint64_t W = (units + num_sms - 1) / num_sms;
     if (maxseg > 1) { const uint64_t wmin = (s.tiles + maxseg - 2) / (maxseg - 1); if (W < wmin) W = wmin; }
     else W = s.tiles;

@@ -94,7 +94,22 @@ struct ExhaustiveArgs {
     void* workspace; size_t workspace_bytes;
     int use_tensor_cores;             // 2: tcgen05 kind::f16 scan with the screen folded in, 1: tcgen05 kind::i8 scan (each where
                                       // applicable, else the next), 0: popcount scan
+    // ---- candidate mode (database sharded over GPUs, or a range scanned piece by piece): instead of the top-k, the k' best
+    //      (estimate, id) keys of  prior_keys U [id_begin, id_end)  are written, ascending, to cand_keys ----
+    const unsigned long long* prior_keys;  // [nq][kprime] keys of earlier pieces (ids of this index), kNoKey-padded; may be NULL
+    const float* tau_in;                   // [nq] upper bounds of the final k'-th estimate known so far (from other pieces /
+                                           // other shards): pairs above them are dropped.  NULL, or FLT_MAX entries = none
+    unsigned long long* cand_keys;         // [nq][kprime] out; NULL = not candidate mode
+    float* cand_dists;                     // [nq][kprime] out, exact distances of cand_keys (the last piece asks for them); may be NULL
+    float* tau_out;                        // [nq] out: estimate of the k'-th key of cand_keys (FLT_MAX while there are fewer); may be NULL
+    uint64_t id_offset;                    // added to the ids in cand_keys when cand_dists is written (shard-local -> global)
 };
+
+// k-way merge of candidate lists (one per shard): keys [lists][nq][kprime] ascending with their exact distances -> the k'
+// smallest keys overall -> the k smallest (distance, id) of those.  Any of the outputs may be NULL; tau_out = estimate of the
+// k'-th smallest key (FLT_MAX if the lists hold fewer), for which dists may be NULL.
+cudaError_t launch_merge_candidates(const unsigned long long* keys, const float* dists, uint32_t lists, uint32_t nq, uint32_t kprime,
+                                    uint32_t k, int64_t* ids_out, float* dists_out, float* tau_out, cudaStream_t stream);
 size_t exhaustive_workspace_bytes(const DevIndex& ix, uint32_t nq, uint64_t m, uint32_t kprime, int num_sms);
 cudaError_t launch_exhaustive(const DevIndex& ix, const ExhaustiveArgs& a, int num_sms, cudaStream_t stream);
 // tensor-core form of the scan stage (exhaustive_tc.cu)

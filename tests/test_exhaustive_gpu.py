@@ -144,31 +144,81 @@ def test_golden_reference_composition(tc):
             assert np.array_equal(_bits(dists[i]), _bits(g[f"dists_{i}_k{k}_kp{kp}"])), (i, k, kp)
 
 
-def test_database_shards_merge_to_the_unsharded_answer(oracle):
-    """DB-sharded mode on one device: each shard scans its id range, the k-way merge of the shards' top-k
-    (by (distance, id)) equals what the oracle gives shard by shard merged the same way."""
+def _sharded_on_one_device(ix, q, k, kp, n, world, prefix, growth):
+    """exhaustive_search_db_sharded with `world` virtual ranks on one device (the shards are id ranges of one index), the
+    collectives done by hand: the same calls, in the same order, as the NCCL path makes."""
     from cphnsw_b200 import hooks, sharding
 
     torch = _torch()
-    fab = common.fabricate(9000, 128, 1, seed=4)
+    shards = [sharding.db_shard(n, r, world) for r in range(world)]
+    plans = [sharding.scan_pieces(e - b, world, n, prefix, growth) for b, e in shards]
+    assert len({len(p) for p in plans}) == 1, "every rank must make the same number of exchanges"
+    keys, dists, tau = [None] * world, [None] * world, None
+    for c in range(len(plans[0])):
+        last = c == len(plans[0]) - 1
+        tl = []
+        for r, (B, _) in enumerate(shards):
+            pb, pe = plans[r][c]
+            keys[r], dists[r], t = hooks.exhaustive_candidates(ix, q, kp, B + pb, B + pe, 0, keys[r], tau, last)
+            tl.append(t)
+        if last:
+            break
+        if c == 0:
+            tau = hooks.merge_candidates(ix, torch.stack(keys), None, 0)[2]      # all-gather of the first pieces' keys
+        else:
+            tau = torch.stack(tl).min(0).values                                  # all-reduce(min)
+    return hooks.merge_candidates(ix, torch.stack(keys), torch.stack(dists), k)[:2]
+
+
+@pytest.mark.parametrize("tc", [2, 1, 0])
+@pytest.mark.parametrize("dim,n,k,kp,world,prefix,growth", [
+    (128, 150_000, 10, 100, 4, 65536, 4),      # the f16 form seeded with the exchanged thresholds, several pieces per shard
+    (96, 70_001, 10, 100, 3, 8192, 3),         # ragged shards, many small pieces
+    (128, 9_000, 10, 64, 4, 65536, 4),         # shards smaller than the prefix: one piece each
+    (64, 30_000, 100, 256, 8, 4096, 2),        # the tensor-core forms' largest k'
+    (96, 20_000, 10, 1000, 2, 4096, 4),        # k' beyond them: popcount form
+    (960, 3_000, 20, 60, 2, 1024, 2),          # D > 256: popcount form
+    (32, 300, 10, 512, 4, 65536, 4),           # fewer vertices than k' in a shard
+])
+def test_database_shards_merge_to_the_unsharded_answer(dim, n, k, kp, world, prefix, growth, tc):
+    """DB-sharded scan = ONE scan of the whole database: the k' best estimates overall, exact re-rank, top-k by (distance,
+    id) -- ids and distance bits -- whatever the number of shards, the piece plan and the scan form."""
+    from cphnsw_b200 import hooks
+
+    torch = _torch()
+    fab = common.fabricate(n, dim, 1, seed=n % 97 + kp, degenerate=True)
+    ix = common.gpu_index_from(fab)
+    ix.set_option("exhaustive_tensor_cores", tc)
+    q = torch.from_numpy(np.random.default_rng(3).standard_normal((37, dim)).astype(np.float32))
+    full_i, full_d = hooks.exhaustive_search(ix, q, k, kp, 0, n)
+    got_i, got_d = _sharded_on_one_device(ix, q, k, kp, n, world, prefix, growth)
+    assert np.array_equal(got_i.cpu().numpy(), full_i.cpu().numpy())
+    assert np.array_equal(_bits(got_d.cpu().numpy()), _bits(full_d.cpu().numpy()))
+
+
+def test_single_scan_in_pieces_against_the_oracle(oracle):
+    """The candidate interface against the oracle directly: keys (estimate bits, ids), thresholds and exact distances."""
+    from cphnsw_b200 import hooks
+
+    torch = _torch()
+    fab = common.fabricate(5000, 96, 1, seed=8, degenerate=True)
     ix = common.gpu_index_from(fab)
     view = oracle.index_view(fab)
-    q = np.random.default_rng(3).standard_normal((16, 128)).astype(np.float32)
-    k, kp, world = 10, 64, 4
-    parts_i, parts_d = [], []
-    for r in range(world):
-        b, e = sharding.db_shard(fab.n, r, world)
-        i_, d_ = hooks.exhaustive_search(ix, torch.from_numpy(q), k, kp, b, e)
-        parts_i.append(i_.cpu().numpy()); parts_d.append(d_.cpu().numpy())
-        for qi in range(len(q)):
-            oi, od, _, _ = oracle.exhaustive(view, fab, q[qi], k, kp, b, e)
-            assert np.array_equal(parts_i[-1][qi, :len(oi)], oi.astype(np.int64))
-            assert np.array_equal(_bits(parts_d[-1][qi, :len(oi)]), _bits(od))
-    mi, md = sharding.merge_topk(np.stack(parts_i), np.stack(parts_d), k)
-    # with k' >= shard size the sharded answer is the exact top-k of the whole database
-    full_i, full_d = hooks.exhaustive_search(ix, torch.from_numpy(q), k, 1024, 0, fab.n)
-    assert mi.shape == (16, k) and np.all(np.diff(md, axis=1) >= 0)
-    del full_i, full_d
+    qn = np.random.default_rng(4).standard_normal((9, 96)).astype(np.float32)
+    q = torch.from_numpy(qn)
+    kp = 50
+    k1, _, t1 = hooks.exhaustive_candidates(ix, q, kp, 0, 2000)
+    k2, d2, t2 = hooks.exhaustive_candidates(ix, q, kp, 2000, 5000, 7, k1, t1, True)
+    k2, d2, t1, t2 = k2.cpu().numpy(), d2.cpu().numpy(), t1.cpu().numpy(), t2.cpu().numpy()
+    for i in range(len(qn)):
+        ids_all, dist_all, _, est = oracle.exhaustive(view, fab, qn[i], 5000, 5000)
+        dist_of = dict(zip(ids_all.tolist(), dist_all.tolist()))
+        order = np.lexsort((np.arange(5000), _bits(est)))[:kp]
+        want_keys = (_bits(est)[order].astype(np.uint64) << np.uint64(32)) | (order.astype(np.uint64) + np.uint64(7))
+        assert np.array_equal(k2[i].view(np.uint64), want_keys)
+        assert np.array_equal(_bits(d2[i]), _bits(np.float32([dist_of[int(v)] for v in order])))
+        first = np.sort(_bits(est[:2000]))[kp - 1]
+        assert _bits(t1[i:i + 1])[0] == first and _bits(t2[i:i + 1])[0] == _bits(est)[order[-1]]
 
 
 def test_rejects_what_it_cannot_do(oracle):

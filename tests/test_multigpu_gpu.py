@@ -1,6 +1,7 @@
 """GPU, world_size 2 over NCCL (skipped on a 1-GPU box): both multi-GPU modes against the single-GPU
 answer -- query-sharded graph search (index replicated, no data-path collective) and DB-sharded
-exhaustive scan (per-shard top-k, NCCL all-gather, k-way merge)."""
+exhaustive scan (per-shard candidates, thresholds exchanged by all-reduce, NCCL all-gather, merge) -- which must equal ONE
+scan of the whole database."""
 import os
 import sys
 
@@ -48,16 +49,22 @@ def _worker(rank, world, port, out):
     ix4, ix1 = make(fab4), make(fab1)
     gi, gd = sharding.search_batch_query_sharded(lambda qs, k: ix4.search_batch(qs, k), q4, 10)
 
-    def scan(qs, k, kp, b, e):
-        i_, d_ = hooks.exhaustive_search(ix1, torch.from_numpy(qs), k, kp, b, e)
-        return i_.cpu().numpy(), d_.cpu().numpy()
+    # DB-sharded scan: every rank holds the whole index here and scans only its id range (ids are global already)
+    B, E = sharding.db_shard(fab1.n, rank, world)
+    q1d = torch.from_numpy(q1).cuda()
 
-    ei, ed = sharding.exhaustive_search_db_sharded(scan, fab1.n, q1, 10, 64)
+    def cand(qs, kp, b, e, off, prior, tau, want):
+        return hooks.exhaustive_candidates(ix1, qs, kp, B + b, B + e, 0, prior, tau, want)
+
+    def merge(keys, dists, k):
+        return hooks.merge_candidates(ix1, keys, dists, k)
+
+    ei, ed = sharding.exhaustive_search_db_sharded(cand, merge, E - B, fab1.n, 0, q1d, 10, 64, None, prefix=2048, growth=2)
+    ei, ed = ei.cpu().numpy(), ed.cpu().numpy()
     if rank == 0:
         si, sd = ix4.search_batch(q4, 10)
-        parts = [scan(q1, 10, 64, *sharding.db_shard(fab1.n, r, world)) for r in range(world)]
-        mi, md = sharding.merge_topk(np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]), 10)
-        np.savez(out, gi=gi, gd=gd, si=si, sd=sd, ei=ei, ed=ed, mi=mi, md=md)
+        mi, md = hooks.exhaustive_search(ix1, q1d, 10, 64, 0, fab1.n)       # ONE scan of the whole database
+        np.savez(out, gi=gi, gd=gd, si=si, sd=sd, ei=ei, ed=ed, mi=mi.cpu().numpy(), md=md.cpu().numpy())
     dist.barrier()
     dist.destroy_process_group()
 

@@ -21,19 +21,66 @@ def _worker(rank, world, port, mode, out):
     from cphnsw_b200 import sharding
 
     o = co.Oracle()
-    fab = common.fabricate(600, 32, 1, seed=3, layers=1)
+    fab = common.fabricate(6000, 32, 1, seed=3, layers=1)
     view = o.index_view(fab)
     q = np.random.default_rng(2).standard_normal((21, 32)).astype(np.float32)
     if mode == "query":
         ids, d = sharding.search_batch_query_sharded(lambda qs, k: o.search_batch(view, qs, k)[:2], q, 10)
     else:
-        def scan(qs, k, kp, b, e):
-            ii = np.full((len(qs), k), -1, np.int64); dd = np.full((len(qs), k), np.finfo(np.float32).max, np.float32)
-            for i, qq in enumerate(qs):
-                a, b_, _, _ = o.exhaustive(view, fab, qq, k, kp, b, e)
-                ii[i, :len(a)] = a; dd[i, :len(a)] = b_
-            return ii, dd
-        ids, d = sharding.exhaustive_search_db_sharded(scan, fab.n, q, 5, 5000, None)
+        import torch
+
+        # CPU stand-ins for the two C-ABI calls of the sharded scan (hooks.exhaustive_candidates / merge_candidates), built
+        # on the oracle's estimates and exact distances of this rank's shard; the flow, the piece plan and the collectives
+        # are the product's
+        B, E = sharding.db_shard(fab.n, rank, world)
+        FMAX = np.finfo(np.float32).max
+        est, dist_of = [], []
+        for qq in q:
+            ia, da, _, e_ = o.exhaustive(view, fab, qq, fab.n, fab.n)
+            est.append(e_.view(np.uint32).astype(np.uint64))
+            dd = np.empty(fab.n, np.float32); dd[ia] = da
+            dist_of.append(dd)
+
+        def cand(queries, kp, b, e, off, prior, tau, want):
+            keys = np.full((len(q), kp), np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64)
+            dists = np.full((len(q), kp), FMAX, np.float32)
+            tout = np.full(len(q), FMAX, np.float32)
+            for i in range(len(q)):
+                loc = np.arange(b, e, dtype=np.uint64)
+                kk = (est[i][B + b:B + e] << np.uint64(32)) | loc
+                if tau is not None:
+                    kk = kk[est[i][B + b:B + e].astype(np.uint32).view(np.float32) <= tau[i].item()]
+                if prior is not None:
+                    pk = prior[i].numpy().view(np.uint64)
+                    kk = np.concatenate([kk, pk[pk != np.uint64(0xFFFFFFFFFFFFFFFF)]])
+                kk = np.sort(kk)[:kp]
+                if len(kk) == kp:
+                    tout[i] = np.uint32(kk[-1] >> np.uint64(32)).view(np.float32)
+                if want:
+                    dists[i, :len(kk)] = dist_of[i][B + (kk & np.uint64(0xFFFFFFFF)).astype(np.int64)]
+                    kk = kk + np.uint64(off)
+                keys[i, :len(kk)] = kk
+            return torch.from_numpy(keys.view(np.int64)), torch.from_numpy(dists) if want else None, torch.from_numpy(tout)
+
+        def merge(keys, dists, k):
+            kk = keys.numpy().view(np.uint64)
+            lists, nq, kp = kk.shape
+            ids = np.full((nq, max(k, 1)), -1, np.int64); dd = np.full((nq, max(k, 1)), FMAX, np.float32); tout = np.full(nq, FMAX, np.float32)
+            for i in range(nq):
+                flat = kk[:, i, :].reshape(-1)
+                order = np.argsort(flat, kind="stable")[:kp]
+                order = order[flat[order] != np.uint64(0xFFFFFFFFFFFFFFFF)]
+                if len(order) == kp:
+                    tout[i] = np.uint32(flat[order[-1]] >> np.uint64(32)).view(np.float32)
+                if dists is not None and k:
+                    fd = dists.numpy()[:, i, :].reshape(-1)[order]
+                    fi = (flat[order] & np.uint64(0xFFFFFFFF)).astype(np.int64)
+                    o2 = np.lexsort((fi, fd))[:k]
+                    ids[i, :len(o2)] = fi[o2]; dd[i, :len(o2)] = fd[o2]
+            return torch.from_numpy(ids), torch.from_numpy(dd), torch.from_numpy(tout)
+
+        ids, d = sharding.exhaustive_search_db_sharded(cand, merge, E - B, fab.n, B, torch.from_numpy(q), 5, 40, None, prefix=128, growth=2)
+        ids, d = ids.numpy(), d.numpy()
     if rank == 0:
         np.savez(out, ids=ids, d=d)
     dist.destroy_process_group()
@@ -46,15 +93,15 @@ def test_two_ranks_match_one(tmp_path, mode):
     mp.spawn(_worker, args=(2, port, mode, out), nprocs=2, join=True)
     got = np.load(out)
     o = co.Oracle()
-    fab = common.fabricate(600, 32, 1, seed=3, layers=1)
+    fab = common.fabricate(6000, 32, 1, seed=3, layers=1)
     view = o.index_view(fab)
     q = np.random.default_rng(2).standard_normal((21, 32)).astype(np.float32)
     if mode == "query":
         ids, d, _ = o.search_batch(view, q, 10)
         assert np.array_equal(got["ids"], ids) and np.array_equal(got["d"], d)
     else:
-        for i in range(len(q)):
-            a, b, _, _ = o.exhaustive(view, fab, q[i], 5, 5000)
+        for i in range(len(q)):      # what ONE scan of the whole database returns with the same k' (not with a larger one)
+            a, b, _, _ = o.exhaustive(view, fab, q[i], 5, 40)
             assert np.array_equal(got["ids"][i, :len(a)], a.astype(np.int64))
             assert np.array_equal(got["d"][i, :len(a)], b)
 
