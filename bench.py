@@ -470,7 +470,7 @@ def run_c4(args, rank, world, local):
 
     def step_dev(q, kp_=None):
         kp_ = kp if kp_ is None else kp_
-        if world == 1:
+        if world == 1 and not args.c4_pieces:
             return hooks.exhaustive_search(ix, q, k, kp_)           # one scan of the whole database
         # shards scan their ranges in pieces, exchange thresholds (all-reduce(min) of nq floats), all-gather their k' candidates
         # (key + exact distance) and merge: the same result as the single scan (tests/test_exhaustive_gpu.py, test_multigpu_gpu.py)
@@ -593,6 +593,7 @@ def main():
     ap.add_argument("--c4-n", type=int, default=10_000_000, help="database size of the c4 sub-run of the default workload")
     ap.add_argument("--c4-prefix", type=int, default=65536, help="c4, N > 1: vertices (over all shards) scanned before the first threshold exchange")
     ap.add_argument("--c4-growth", type=int, default=4, help="c4, N > 1: each later scan piece covers growth - 1 times what has been scanned")
+    ap.add_argument("--c4-pieces", action="store_true", help="c4, N = 1: scan in pieces like a shard does (same result)")
     ap.add_argument("--no-c4", action="store_true", help="default workload: skip the c4 (exhaustive scan, DB-sharded) sub-run")
     ap.add_argument("--scan-form", type=int, default=2, choices=[0, 1, 2],
                     help="c4: 2 = tcgen05 kind::f16 scan with the candidate screen folded into the contraction (default), "

@@ -973,12 +973,44 @@ static int run_exhaustive(cphnsw_b200_index* ix, Lane& L, const float* d_queries
         a.prior_keys = cand->prior_keys; a.tau_in = cand->tau_in; a.cand_keys = cand->keys; a.cand_dists = cand->dists;
         a.tau_out = cand->tau_out; a.id_offset = cand->id_offset;
     }
-    const size_t wb = exhaustive_workspace_bytes(d, (uint32_t)nq, id_end - id_begin, (uint32_t)kprime, ix->num_sms);
-    rc = ensure_buffer(ix, &L.scratch, &L.scratch_bytes, wb + 256, false);
+    const uint64_t m = id_end - id_begin;
+    const size_t wb = (exhaustive_workspace_bytes(d, (uint32_t)nq, m, (uint32_t)kprime, ix->num_sms) + 255) & ~(size_t)255;
+    // A long range is scanned in pieces (64K vertices, then each piece three times what came before): after a piece the
+    // candidates are merged and the thresholds are the exact k'-th estimates so far, which keeps the per-CTA candidate lists
+    // of the next piece short -- measured on 10M x 10k: 38.4 -> 32.4 ms at k' = 100, 185 -> 47 ms at k' = 256.  The result is
+    // the single scan's (the candidate interface is the one the multi-GPU path uses: sharding.py).
+    const bool pieces = !cand && !d_sums && !d_est && k > 0 && kprime > 0 && m > 4 * 65536;
+    const size_t kb = ((size_t)nq * kprime * 8 + 255) & ~(size_t)255, tb = ((size_t)nq * 4 + 255) & ~(size_t)255,
+                 db = ((size_t)nq * kprime * 4 + 255) & ~(size_t)255;
+    rc = ensure_buffer(ix, &L.scratch, &L.scratch_bytes, wb + (pieces ? 2 * kb + tb + db : 0) + 256, false);
     if (rc) return rc;
     a.workspace = L.scratch; a.workspace_bytes = wb;
-    CUDA_TRY(ix, launch_exhaustive(d, a, ix->num_sms, st));
-    return 0;
+    if (!pieces) {
+        CUDA_TRY(ix, launch_exhaustive(d, a, ix->num_sms, st));
+        return 0;
+    }
+    uint8_t* extra = static_cast<uint8_t*>(L.scratch) + wb;
+    unsigned long long* keys[2] = {reinterpret_cast<unsigned long long*>(extra), reinterpret_cast<unsigned long long*>(extra + kb)};
+    float* tau = reinterpret_cast<float*>(extra + 2 * kb);
+    float* cd = reinterpret_cast<float*>(extra + 2 * kb + tb);
+    uint64_t b = 0, size = 65536;
+    for (int c = 0;; ++c) {
+        uint64_t e = std::min<uint64_t>(m, b + size);
+        if (m - e < size / 2) e = m;     // no sliver at the end
+        const bool last = e >= m;
+        ExhaustiveArgs p = a;
+        p.id_begin = id_begin + b; p.id_end = id_begin + e; p.k = 0; p.ids = nullptr; p.dists = nullptr;
+        p.prior_keys = c ? keys[(c - 1) & 1] : nullptr;
+        p.tau_in = c ? tau : nullptr;
+        p.cand_keys = keys[c & 1]; p.tau_out = tau; p.cand_dists = last ? cd : nullptr; p.id_offset = 0;
+        CUDA_TRY(ix, launch_exhaustive(d, p, ix->num_sms, st));
+        if (last) {
+            CUDA_TRY(ix, launch_merge_candidates(keys[c & 1], cd, 1, (uint32_t)nq, (uint32_t)kprime, (uint32_t)k, d_ids, d_dists, nullptr, st));
+            return 0;
+        }
+        size = e * 3;
+        b = e;
+    }
 }
 
 static int check_exhaustive(cphnsw_b200_index* ix, uint64_t nq, uint64_t k, uint64_t kprime, uint64_t id_begin, uint64_t id_end) {

@@ -49,7 +49,10 @@ __global__ void __launch_bounds__(kExThreads) exhaustive_scan_kernel(const DevIn
         const float* cf = a.coeffs + (size_t)(q0 + i) * kCoeffStride;
         par[4 * i + 0] = cf[0]; par[4 * i + 1] = cf[1]; par[4 * i + 2] = cf[2]; par[4 * i + 3] = cf[4];   // A, Bc, C, |qc|^2
     }
-    if (threadIdx.x < kQT) { cnt[threadIdx.x] = 0; tau[threadIdx.x] = FLT_MAX; }
+    if (threadIdx.x < kQT) {   // thresholds handed in by the caller (earlier pieces, other shards), else none yet
+        cnt[threadIdx.x] = 0;
+        tau[threadIdx.x] = (a.tau_in && threadIdx.x < nqt && a.tau_in[q0 + threadIdx.x] >= 0.0f) ? a.tau_in[q0 + threadIdx.x] : FLT_MAX;
+    }
     if (threadIdx.x == 0) need_compact = 0;
     __syncthreads();
 

@@ -449,6 +449,10 @@ cudaError_t launch_exhaustive_scan_tc(const DevIndex& ix, const ExhaustiveArgs& 
     const TcWorkspace w = tc_workspace(partial, a.nq, a.kprime, num_sms);
     cudaError_t e = launch_exhaustive_tc_prepare(ix, a.id_begin, a.id_end, a.nq, w.vstat, w.taug, true, num_sms, stream);
     if (e != cudaSuccess) return e;
+    if (a.tau_in && a.kprime) {
+        e = launch_seed_tau(w.taug, a.tau_in, a.nq, stream);
+        if (e != cudaSuccess) return e;
+    }
     return launch_exhaustive_scan_tc_core(ix, a, num_sms, partial, w, nseg, stream);
 }
 

@@ -493,6 +493,11 @@ __global__ void t16_seed_tau_kernel(uint32_t* __restrict__ taug, const float* __
     if (t >= 0.0f && t < kTcTauInf) atomicMin(taug + q, __float_as_uint(t));
 }
 
+cudaError_t launch_seed_tau(uint32_t* taug, const float* tau_in, uint32_t nq, cudaStream_t stream) {
+    t16_seed_tau_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(taug, tau_in, nq);
+    return cudaGetLastError();
+}
+
 bool exhaustive_tc16_applicable(const DevIndex& ix, uint32_t kprime) {
     return kprime <= kTcMaxKPrime && ix.nch == 1 && ix.calib.affine_a > 0.0f;
 }
@@ -521,8 +526,7 @@ cudaError_t launch_exhaustive_scan_tc16(const DevIndex& ix, const ExhaustiveArgs
     e = launch_exhaustive_tc_prepare(ix, a.id_begin, a.id_end, a.nq, w.vstat, w.taug, !(a.kprime && prefix), num_sms, stream);
     if (e != cudaSuccess) return e;
     if (seeded && a.kprime) {
-        t16_seed_tau_kernel<<<(a.nq + 255) / 256, 256, 0, stream>>>(w.taug, a.tau_in, a.nq);
-        e = cudaGetLastError();
+        e = launch_seed_tau(w.taug, a.tau_in, a.nq, stream);
         if (e != cudaSuccess) return e;
     }
     const TcSplit sp = tc_split(m, a.nq, a.kprime, num_sms);

@@ -199,6 +199,8 @@ inline TcSplit tc_split(uint64_t m, uint32_t nq, uint32_t kprime, int num_sms) {
 // (exhaustive_tc.cu) limits for the screen over [id_begin, id_end) into vstat; optionally resets the shared thresholds
 cudaError_t launch_exhaustive_tc_prepare(const DevIndex& ix, uint64_t id_begin, uint64_t id_end, uint32_t nq, float* vstat, uint32_t* taug,
                                          bool reset_tau, int num_sms, cudaStream_t stream);
+// (exhaustive_tc16.cu) thresholds handed in by the caller: taug = min(taug, tau_in)
+cudaError_t launch_seed_tau(uint32_t* taug, const float* tau_in, uint32_t nq, cudaStream_t stream);
 // (exhaustive_tc.cu) the kind::i8 scan alone, limits and thresholds as they stand
 cudaError_t launch_exhaustive_scan_tc_core(const DevIndex& ix, const ExhaustiveArgs& a, int num_sms, unsigned long long* partial,
                                            const TcWorkspace& w, uint32_t* nseg, cudaStream_t stream);

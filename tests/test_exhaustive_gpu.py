@@ -196,6 +196,29 @@ def test_database_shards_merge_to_the_unsharded_answer(dim, n, k, kp, world, pre
     assert np.array_equal(_bits(got_d.cpu().numpy()), _bits(full_d.cpu().numpy()))
 
 
+@pytest.mark.parametrize("tc", [2, 1, 0])
+@pytest.mark.parametrize("kp", [100, 256])
+def test_long_ranges_are_scanned_in_pieces_with_the_single_scan_result(oracle, tc, kp):
+    """cphnsw_b200_exhaustive_search on a range past 4 x 64K vertices scans it in pieces (candidates merged and thresholds
+    made exact after each): same ids and distance bits as the oracle's single pass; also on a sub-range with an offset."""
+    from cphnsw_b200 import hooks
+
+    torch = _torch()
+    n = 300_000
+    fab = common.fabricate(n, 96, 1, seed=kp, degenerate=True)
+    ix = common.gpu_index_from(fab)
+    ix.set_option("exhaustive_tensor_cores", tc)
+    view = oracle.index_view(fab)
+    qn = np.random.default_rng(5).standard_normal((6, 96)).astype(np.float32)
+    for b, e in ((0, n), (1234, n - 7)):
+        ids, dists = hooks.exhaustive_search(ix, torch.from_numpy(qn), 10, kp, b, e)
+        ids, dists = ids.cpu().numpy(), dists.cpu().numpy()
+        for i in range(len(qn)):
+            oi, od, _, _ = oracle.exhaustive(view, fab, qn[i], 10, kp, b, e)
+            assert np.array_equal(ids[i], oi.astype(np.int64))
+            assert np.array_equal(_bits(dists[i]), _bits(od))
+
+
 def test_single_scan_in_pieces_against_the_oracle(oracle):
     """The candidate interface against the oracle directly: keys (estimate bits, ids), thresholds and exact distances."""
     from cphnsw_b200 import hooks
