@@ -147,15 +147,30 @@ __global__ void __launch_bounds__(kExThreads) exhaustive_select_rerank_kernel(co
     float* qs = reinterpret_cast<float*>(smem_raw + (((size_t)sort_n * 8 + 15) & ~(size_t)15));   // query, accumulator-major, padded rows
     const uint32_t q = blockIdx.x, kp = a.kprime, k = a.k;
     const uint32_t total = nslices * kp;
-    for (uint32_t i = threadIdx.x; i < sort_n; i += blockDim.x) {
+    // the slices' lists are mostly padding once the thresholds are tight: only the keys that exist are gathered (in any
+    // order) and sorted -- a power of two just above their number instead of slices x k'
+    CPB_BLOCK_SHARED uint32_t nvalid;
+    if (threadIdx.x == 0) nvalid = 0;
+    __syncthreads();
+    const uint32_t ntot = total + (a.prior_keys ? kp : 0u);
+    for (uint32_t i0 = 0; i0 < ntot; i0 += blockDim.x) {
+        const uint32_t i = i0 + threadIdx.x;
         unsigned long long key = kNoKey;
         if (i < total) { const uint32_t s = i / kp, j = i % kp; key = partial[((size_t)s * a.nq + q) * kp + j]; }
-        else if (a.prior_keys && i < total + kp) key = a.prior_keys[(size_t)q * kp + (i - total)];   // one more "slice": earlier pieces
-        keys[i] = key;
+        else if (i < ntot) key = a.prior_keys[(size_t)q * kp + (i - total)];   // one more "slice": earlier pieces
+        const unsigned have = __ballot_sync(kFull, key != kNoKey);
+        uint32_t base = 0;
+        if ((threadIdx.x & 31u) == 0 && have) base = atomicAdd(&nvalid, (uint32_t)__popc(have));
+        base = __shfl_sync(kFull, base, 0);
+        if (key != kNoKey) keys[base + __popc(have & ((1u << (threadIdx.x & 31u)) - 1u))] = key;
     }
+    __syncthreads();
+    uint32_t nsort = 2;
+    while (nsort < nvalid || nsort < kp) nsort <<= 1;     // <= sort_n; the first k' slots are read below whatever exists
+    for (uint32_t i = nvalid + threadIdx.x; i < nsort; i += blockDim.x) keys[i] = kNoKey;
     for (uint32_t i = threadIdx.x; i < D; i += blockDim.x) qs[(i / T) * Tp + (i % T)] = a.qT[(size_t)q * D + i];
     __syncthreads();
-    bitonic_sort(keys, sort_n);
+    bitonic_sort(keys, nsort);
     if (a.cand_keys) {   // candidate mode: the k' best keys themselves (ascending), the threshold they imply
         const bool final_piece = a.cand_dists != nullptr;
         for (uint32_t j = threadIdx.x; j < kp; j += blockDim.x) {
@@ -185,7 +200,7 @@ __global__ void __launch_bounds__(kExThreads) exhaustive_select_rerank_kernel(co
     }
     if (a.cand_keys) return;
     // re-sort the first k' by (distance, id); entries beyond k' are not results
-    for (uint32_t i = kp + threadIdx.x; i < sort_n; i += blockDim.x) keys[i] = kNoKey;
+    for (uint32_t i = kp + threadIdx.x; i < nsort; i += blockDim.x) keys[i] = kNoKey;
     __syncthreads();
     uint32_t n2 = 1;
     while (n2 < kp) n2 <<= 1;
