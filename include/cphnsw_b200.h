@@ -164,7 +164,8 @@ int cphnsw_b200_exhaustive_search(cphnsw_b200_index* ix, const float* d_queries,
                                   uint64_t k, uint64_t kprime, uint64_t id_begin, uint64_t id_end,
                                   int64_t* d_ids, float* d_dists, void* stream);
 /* The scan in pieces -- a database sharded over GPUs, each shard scanned range by range -- with the single-scan result:
- * writes to d_keys_out [nq][kprime] the kprime smallest keys (estimate bits << 32 | id, ascending, 0xFF..FF padding) of
+ * writes to d_keys_out [nq][kprime] the kprime smallest keys (estimate bits << 32 | id, 0xFF..FF padding; ascending on
+ * the last piece, in no particular order before) of
  * d_prior_keys (the keys_out of earlier ranges of this index; may be NULL) and the vertices of [id_begin, id_end).
  * d_tau_in [nq] (may be NULL; FLT_MAX = none): upper bounds of the final kprime-th estimate learnt elsewhere (other
  * shards, through an all-reduce(min) of d_tau_out) -- pairs above them are dropped early, which is what keeps a shard's

@@ -213,6 +213,103 @@ __global__ void __launch_bounds__(kExThreads) exhaustive_select_rerank_kernel(co
     }
 }
 
+// Intermediate pieces of a scan done in pieces need no order and no exact distances: only WHICH k' keys are the smallest
+// so far and the estimate of the k'-th.  One warp per query: the keys that exist (the slices' lists are mostly padding once
+// thresholds are tight) are gathered into the warp's buffer, kSelCap at a time, and reduced to the k' smallest by a bitwise
+// search on register-resident keys (16 per lane); more keys than one buffer holds are folded in round by round.
+constexpr uint32_t kSelCap = 512;      // keys per round = 16 per lane
+constexpr int kSelWarps = 8;
+
+__device__ __forceinline__ uint32_t warp_select_smallest(unsigned long long* __restrict__ lst, uint32_t c, uint32_t kp, uint32_t lane,
+                                                         uint32_t& tau_bits) {
+    constexpr int KPL = kSelCap / 32;
+    uint32_t hi[KPL], lo[KPL];
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+        const uint32_t idx = (uint32_t)i * 32 + lane;
+        const unsigned long long key = idx < c ? lst[idx] : kNoKey;
+        hi[i] = (uint32_t)(key >> 32); lo[i] = (uint32_t)key;
+    }
+    uint32_t cur = 0;
+    for (int bit = 30; bit >= 0; --bit) {   // estimates are non-negative floats: bit 31 is clear
+        const uint32_t t = cur | (1u << bit);
+        uint32_t nl = 0;
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) nl += hi[i] < t ? 1u : 0u;
+        nl = __reduce_add_sync(kFull, nl);
+        if (nl < kp) cur = t;
+    }
+    uint32_t nlt = 0, neq = 0;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) { nlt += hi[i] < cur ? 1u : 0u; neq += hi[i] == cur ? 1u : 0u; }
+    nlt = __reduce_add_sync(kFull, nlt); neq = __reduce_add_sync(kFull, neq);
+    const uint32_t r = kp - nlt;   // 1 <= r <= neq of the keys with this estimate stay: those with the smallest ids
+    uint32_t cutlo = 0xFFFFFFFFu;
+    if (neq != r) {
+        uint32_t cl = 0;
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t t = cl | (1u << bit);
+            uint32_t nl = 0;
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) nl += (hi[i] == cur && lo[i] < t) ? 1u : 0u;
+            nl = __reduce_add_sync(kFull, nl);
+            if (nl < r) cl = t;
+        }
+        cutlo = cl;
+    }
+    uint32_t mine = 0;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) mine += (hi[i] < cur || (hi[i] == cur && lo[i] <= cutlo)) ? 1u : 0u;
+    uint32_t pos = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(kFull, pos, o); if (lane >= (uint32_t)o) pos += t; }
+    pos -= mine;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < KPL; ++i)
+        if (hi[i] < cur || (hi[i] == cur && lo[i] <= cutlo)) lst[pos++] = ((unsigned long long)hi[i] << 32) | lo[i];
+    __syncwarp();
+    tau_bits = cur;
+    return kp;
+}
+
+__global__ void __launch_bounds__(kSelWarps * 32) exhaustive_select_keys_kernel(const ExhaustiveArgs a, uint32_t nslices,
+                                                                                const unsigned long long* __restrict__ partial) {
+    CPB_BLOCK_SHARED unsigned long long bufs[kSelWarps][kSelCap];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t q = blockIdx.x * kSelWarps + warp;
+    if (q >= a.nq) return;
+    unsigned long long* buf = bufs[warp];
+    const uint32_t kp = a.kprime, total = nslices * kp, ntot = total + (a.prior_keys ? kp : 0u);
+    uint32_t c = 0, tau_bits = 0x7F7FFFFFu;   // FLT_MAX
+    bool full = false;
+    for (uint32_t i0 = 0; i0 < ntot; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        unsigned long long key = kNoKey;
+        if (i < total) { const uint32_t s = i / kp, j = i % kp; key = partial[((size_t)s * a.nq + q) * kp + j]; }
+        else if (i < ntot) key = a.prior_keys[(size_t)q * kp + (i - total)];
+        const unsigned have = __ballot_sync(kFull, key != kNoKey);
+        if (c + (uint32_t)__popc(have) > kSelCap) {   // the buffer cannot take this row: reduce it to the k' smallest first
+            __syncwarp();
+            c = warp_select_smallest(buf, c, kp, lane, tau_bits);
+            full = true;
+        }
+        if (key != kNoKey) buf[c + __popc(have & ((1u << lane) - 1u))] = key;
+        c += (uint32_t)__popc(have);
+        __syncwarp();
+    }
+    if (c > kp) { c = warp_select_smallest(buf, c, kp, lane, tau_bits); full = true; }
+    else if (c == kp) {   // exactly k' keys: the threshold is their largest estimate
+        uint32_t mx = 0;
+        for (uint32_t i = lane; i < c; i += 32) { const uint32_t e = (uint32_t)(buf[i] >> 32); mx = e > mx ? e : mx; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const uint32_t e = __shfl_xor_sync(kFull, mx, o); mx = e > mx ? e : mx; }
+        tau_bits = mx; full = true;
+    }
+    for (uint32_t j = lane; j < kp; j += 32) a.cand_keys[(size_t)q * kp + j] = j < c ? buf[j] : kNoKey;
+    if (a.tau_out && lane == 0) a.tau_out[q] = full ? __uint_as_float(tau_bits) : FLT_MAX;
+}
+
 #ifndef CPB_HOST_EMULATION   // tests/native/ compiles the kernels above for the host (no PTX)
 // Vertex slices per query tile.  Every (slice, query tile) CTA pays a fixed price in list compactions and a
 // final sort, so slices should be long (>= 64 K vertices) -- but the grid still has to fill the GPU when there
@@ -258,6 +355,10 @@ cudaError_t launch_exhaustive(const DevIndex& ix, const ExhaustiveArgs& a, int n
         exhaustive_scan_kernel<<<grid, kExThreads, smem, stream>>>(ix, a, nslices, slice_len, cap, partial);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
+    }
+    if (a.cand_keys && !a.cand_dists && a.kprime && 2 * a.kprime <= kSelCap) {   // an intermediate piece: which keys, not in which order
+        exhaustive_select_keys_kernel<<<(a.nq + kSelWarps - 1) / kSelWarps, kSelWarps * 32, 0, stream>>>(a, nslices, partial);
+        return cudaGetLastError();
     }
     if (a.kprime && (a.k || a.cand_keys)) {
         uint32_t sort_n = 1;

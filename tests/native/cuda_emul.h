@@ -76,6 +76,15 @@ inline T __shfl_sync(unsigned, T v, int src) {
 
 template <typename T>
 inline T __shfl_xor_sync(unsigned m, T v, int lane_mask) { return __shfl_sync(m, v, (int)(threadIdx.x & 31) ^ lane_mask); }
+inline unsigned __reduce_add_sync(unsigned, unsigned v) {
+    cuda_emul::Warp* w = cuda_emul::t_warp;
+    w->slot[threadIdx.x & 31] = v;
+    w->bar.arrive_and_wait();
+    unsigned s = 0;
+    for (int l = 0; l < 32; ++l) s += w->slot[l];
+    w->bar.arrive_and_wait();
+    return s;
+}
 // shfl.up: lanes below delta keep their own value
 template <typename T>
 inline T __shfl_up_sync(unsigned m, T v, unsigned delta) {
