@@ -224,6 +224,19 @@ int cphnsw_b200_neighbor_codes(cphnsw_b200_index* ix, uint32_t dim, uint32_t bit
                                uint8_t* d_codes, float* d_aux, uint8_t* d_blocks, uint64_t block_stride,
                                void* stream);
 
+/* ---- calibration side: the sample loop of Index::calibrate_estimator -------------------------- */
+/* What the lambda process_query (api/hnsw_index.hpp:786-866) records for each sampled query: d_queries [ns][dim] (a
+ * database vector or the reference's synthetic perturbation of one -- the caller draws them, the reference's RNG being the
+ * host library's) and d_start_ids [ns] (sample_ids[parent_cursor % n]).  Per sample: d_parent (the start vertex or the
+ * closest of its neighbours, l2_distance_simd, strict <, stored order), d_nn_dist_sq = d_dist_qp_sq = that distance; per
+ * neighbour slot of the parent's block, [ns][32]: d_nop = max(nop, 1e-12), d_ip_corrected = ip_approx - ip_cp,
+ * d_ip_qo_denom = max(|ip_qo|, 1e-10), d_true_ip = <q - p, o - p> / nop, d_neighbor = the neighbour's id; slots from the
+ * first empty one on hold 0 / 0xFFFFFFFF.  The index must be loaded (the graph is complete when calibration runs). */
+int cphnsw_b200_calibration_samples(cphnsw_b200_index* ix, const float* d_queries, const uint32_t* d_start_ids, uint64_t ns,
+                                    uint32_t* d_parent, float* d_nn_dist_sq, float* d_dist_qp_sq, float* d_nop,
+                                    float* d_ip_corrected, float* d_ip_qo_denom, float* d_true_ip, uint32_t* d_neighbor,
+                                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,9 @@ void cpo_fht(float* x, uint32_t D) {
  * Fused ops as compiled: u = (int)fma(x - vl, inv_delta, 0.5f);
  *                        C = (-(fma(vl, D, delta*sum_qu))) * inv_sqrt_d.
  * ==================================================================================== */
+static int cpo_encode_variant = 0;
+void cpo_set_encode_variant(int v) { cpo_encode_variant = v; }
+
 void cpo_encode_query(uint32_t dim, uint32_t D, const float* signs, const float* q,
                       uint8_t* lut, float coeffs[3], float* rotated) {
     float* buf = (float*)malloc(sizeof(float) * D);
@@ -126,8 +129,11 @@ void cpo_encode_query(uint32_t dim, uint32_t D, const float* signs, const float*
     }
     coeffs[0] = (2.0f * delta) * inv_sqrt_d;
     coeffs[1] = (2.0f * vl) * inv_sqrt_d;
-    float ds = delta * sum_qu;
-    coeffs[2] = (-fmaf(vl, Df, ds)) * inv_sqrt_d;
+    /* C = -(Df*vl + delta*sum_qu) * inv_sqrt_d: which product GCC fuses depends on the code around the inlined call.  The
+     * reference module's search path (pinned by tests/golden/k1_golden.npz and every end-to-end test) has variant 0; the
+     * calibration loop composed in oracle/refshim.cpp compiles to variant 1 (tests/test_oracle_calibration.py). */
+    if (cpo_encode_variant == 1) coeffs[2] = (-fmaf(delta, sum_qu, Df * vl)) * inv_sqrt_d;
+    else { float ds = delta * sum_qu; coeffs[2] = (-fmaf(vl, Df, ds)) * inv_sqrt_d; }
     free(buf);
     free(u8);
 }
@@ -978,3 +984,72 @@ int cpo_exhaustive_search(const cpo_index* ix, const cpo_flat_view* fv, const fl
     free(qc); free(qpad); free(lut); free(cand); free(packed);
     return (int)nout;
 }
+
+/* ======================================================================================
+ * Calibration sampling: the lambda process_query of Index::calibrate_estimator,
+ * api/hnsw_index.hpp:786-866 -- for one query and a start vertex: the closer of the start vertex and
+ * its neighbours (strict <, stored order, stop at the first empty slot) becomes the parent; for every
+ * neighbour of the parent: nop (floored at 1e-12), ip_corrected = ip_approx - ip_cp, the denominator
+ * max(|ip_qo|, 1e-10) and the true inner product <q - p, o - p> / nop.
+ * How GCC 13.3 -O3 -mfma contracts the two scalar expressions is not visible in the source; `flags`
+ * carries the candidates and tests/test_oracle_calibration.py finds the one the compiled reference
+ * uses (same method as probe_contraction.c):
+ *   bit 0: ip_approx = fma(A', fs, Bc' * pc) + C   instead of   fma(Bc', pc, A' * fs) + C
+ *   bit 1: true_ip accumulates with a separate multiply and add instead of one fma per dimension
+ *   bit 2: ip_approx with no fused multiply-add at all: (A' * fs + Bc' * pc) + C
+ * Outputs are [32] per query; slots past the block's end keep 0 / 0xFFFFFFFF.
+ * ==================================================================================== */
+void cpo_calibration_sample(const cpo_index* ix, const float* query_padded, uint32_t start_id, uint32_t flags, uint32_t* parent_out,
+                            float* nn_dist_sq, float* dist_qp_sq, float* nop_out, float* ip_corrected, float* ip_qo_denom, float* true_ip,
+                            uint32_t* neighbor) {
+    const uint32_t D = ix->D, B = ix->B;
+    uint32_t parent = start_id;
+    float best = cpo_l2(D, query_padded, ix->raw + (size_t)parent * D);
+    nb_view nb = get_nb(ix, parent);
+    for (uint32_t i = 0; i < nb.count; ++i) {
+        const uint32_t nid = nb.ids[i];
+        if (nid == 0xFFFFFFFFu) break;
+        const float d = cpo_l2(D, query_padded, ix->raw + (size_t)nid * D);
+        if (d < best) { best = d; parent = nid; }
+    }
+    *nn_dist_sq = best;
+    *parent_out = parent;
+    *dist_qp_sq = cpo_l2(D, query_padded, ix->raw + (size_t)parent * D);
+    uint8_t* lut = (uint8_t*)malloc((size_t)D * 4);
+    float co[3];
+    cpo_encode_query(D, D, ix->signs, query_padded, lut, co, NULL);
+    nb_view pnb = get_nb(ix, parent);
+    uint32_t nbit[32], msb[32], msb2[32];
+    cpo_fastscan(D, B, lut, pnb.planes, nbit, msb, msb2);
+    free(lut);
+    for (uint32_t j = 0; j < 32; ++j) { nop_out[j] = 0.0f; ip_corrected[j] = 0.0f; ip_qo_denom[j] = 0.0f; true_ip[j] = 0.0f; neighbor[j] = 0xFFFFFFFFu; }
+    const float inv_K = 1.0f / (float)((1u << B) - 1u);
+    const float* p = ix->raw + (size_t)parent * D;
+    for (uint32_t j = 0; j < pnb.count; ++j) {
+        const uint32_t o_id = pnb.ids[j];
+        if (o_id == 0xFFFFFFFFu) break;
+        const float ipqo = pnb.ip_qo[j];
+        const float nop = pnb.nop[j] > 1e-12f ? pnb.nop[j] : 1e-12f;   /* std::max(nop, kSmall) */
+        const float fs = (float)nbit[j];
+        const float pc = B == 1 ? (float)pnb.pop[j] : (float)pnb.wpop[j];
+        const float Ae = B == 1 ? co[0] : co[0] * inv_K, Be = B == 1 ? co[1] : co[1] * inv_K;
+        float t;
+        if (flags & 4u) { const float m1 = Ae * fs, m2 = Be * pc; t = m1 + m2; }
+        else if (flags & 1u) t = fmaf(Ae, fs, Be * pc);
+        else t = fmaf(Be, pc, Ae * fs);
+        const float ip_approx = t + co[2];
+        ip_corrected[j] = ip_approx - pnb.ip_cp[j];
+        const float a = fabsf(ipqo);
+        ip_qo_denom[j] = a > 1e-10f ? a : 1e-10f;
+        const float* o = ix->raw + (size_t)o_id * D;
+        float acc = 0.0f;
+        for (uint32_t d = 0; d < D; ++d) {
+            const float x = query_padded[d] - p[d], y = o[d] - p[d];
+            if (flags & 2u) { const float m = x * y; acc = acc + m; } else acc = fmaf(x, y, acc);
+        }
+        true_ip[j] = acc / nop;
+        nop_out[j] = nop;
+        neighbor[j] = o_id;
+    }
+}
+

@@ -25,6 +25,7 @@ extern "C" {
 void cpo_rotation_signs(uint32_t D, uint64_t seed, float* signs /* [3][D] */);
 void cpo_fht(float* x, uint32_t D);
 /* rotated (optional, may be NULL) receives the rotated, norm_factor-scaled query (D floats) */
+void cpo_set_encode_variant(int v);   /* contraction variant of coeff_constant, see cpo_encode_query (test use only; default 0) */
 void cpo_encode_query(uint32_t dim, uint32_t D, const float* signs, const float* q,
                       uint8_t* lut /* [D/4][16] */, float coeffs[3], float* rotated);
 
@@ -111,6 +112,12 @@ int cpo_exhaustive_search(const cpo_index* ix, const cpo_flat_view* fv, const fl
                           uint64_t k, uint64_t kprime, uint64_t id_begin, uint64_t id_end,
                           uint32_t* ids, float* dists, uint32_t* est_sums /* optional [id_end-id_begin] */,
                           float* est_out /* optional */);
+
+/* Calibration sampling (N4): process_query of Index::calibrate_estimator (api/hnsw_index.hpp:786-866); outputs [32] per query.
+ * flags: see the definition (contraction candidates of the two scalar expressions). */
+void cpo_calibration_sample(const cpo_index* ix, const float* query_padded, uint32_t start_id, uint32_t flags, uint32_t* parent_out,
+                            float* nn_dist_sq, float* dist_qp_sq, float* nop_out, float* ip_corrected, float* ip_qo_denom, float* true_ip,
+                            uint32_t* neighbor);
 
 #ifdef __cplusplus
 }

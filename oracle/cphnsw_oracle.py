@@ -379,6 +379,46 @@ class Oracle:
         ix._keep = keep
         return ix
 
+    # ---- calibration sampling (N4) -----------------------------------------------------------
+    CALIB_FLAGS = 3   # contraction of the two scalar expressions as the compiled reference has it (tests/test_oracle_calibration.py)
+
+    @staticmethod
+    def _calib_out(ns):
+        return {"parent": np.empty(ns, np.uint32), "nn_dist_sq": np.empty(ns, np.float32), "dist_qp_sq": np.empty(ns, np.float32),
+                "nop": np.empty((ns, 32), np.float32), "ip_corrected": np.empty((ns, 32), np.float32),
+                "ip_qo_denom": np.empty((ns, 32), np.float32), "true_ip": np.empty((ns, 32), np.float32),
+                "neighbor": np.empty((ns, 32), np.uint32)}
+
+    def calibration_samples(self, ix, queries_padded, start_ids, flags=None):
+        """C restatement of process_query (api/hnsw_index.hpp:786-866) per (query [D], start vertex)."""
+        flags = self.CALIB_FLAGS if flags is None else flags
+        q = np.ascontiguousarray(queries_padded, np.float32)
+        st = np.ascontiguousarray(start_ids, np.uint32)
+        assert q.shape == (len(st), ix.D)
+        o = self._calib_out(len(st))
+        for i in range(len(st)):
+            par = C.c_uint32(0); nn = C.c_float(0); dq = C.c_float(0)
+            self.lib.cpo_calibration_sample(C.byref(ix), _ptr(q[i], c_f32p), C.c_uint32(int(st[i])), C.c_uint32(flags), C.byref(par), C.byref(nn),
+                                            C.byref(dq), _ptr(o["nop"][i], c_f32p), _ptr(o["ip_corrected"][i], c_f32p),
+                                            _ptr(o["ip_qo_denom"][i], c_f32p), _ptr(o["true_ip"][i], c_f32p), _ptr(o["neighbor"][i], c_u32p))
+            o["parent"][i] = par.value; o["nn_dist_sq"][i] = nn.value; o["dist_qp_sq"][i] = dq.value
+        return o
+
+    def ref_calibration_samples(self, sf, queries_padded, start_ids):
+        """The same loop composed from the unmodified reference's primitives and block types (oracle/refshim.cpp)."""
+        assert self.shim is not None
+        q = np.ascontiguousarray(queries_padded, np.float32)
+        st = np.ascontiguousarray(start_ids, np.uint32)
+        sd = np.ascontiguousarray(sf.search_data); raw = np.ascontiguousarray(sf.raw, np.float32)
+        o = self._calib_out(len(st))
+        rc = self.shim.refshim_calib_samples(C.c_uint32(sf.D), C.c_uint32(sf.B), C.c_uint32(sf.D), C.c_uint64(len(st)), _ptr(q, c_f32p), _ptr(st, c_u32p),
+                                             _ptr(raw, c_f32p), _ptr(sd, c_u8p), C.c_uint64(sf.rec_size), C.c_uint32(sf.nb_off), _ptr(o["parent"], c_u32p),
+                                             _ptr(o["nn_dist_sq"], c_f32p), _ptr(o["dist_qp_sq"], c_f32p), _ptr(o["nop"], c_f32p),
+                                             _ptr(o["ip_corrected"], c_f32p), _ptr(o["ip_qo_denom"], c_f32p), _ptr(o["true_ip"], c_f32p),
+                                             _ptr(o["neighbor"], c_u32p))
+        assert rc == 0, "the shim is built for padded dims 32, 128 and 1024"
+        return o
+
     def search_batch(self, ix, queries, k, threads=0):
         q = np.ascontiguousarray(queries, np.float32)
         nq = q.shape[0]

@@ -20,6 +20,7 @@
 // Built by oracle/Makefile into oracle/_ref/libcphnsw_refshim.so (git-ignored).
 #include <cphnsw/core/codes.hpp>
 #include <cphnsw/core/memory.hpp>
+#include <cphnsw/core/types.hpp>
 #include <cphnsw/core/util.hpp>
 #include <cphnsw/distance/fastscan_kernel.hpp>
 #include <cphnsw/distance/fastscan_layout.hpp>
@@ -27,6 +28,7 @@
 
 #include <cstdint>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 using namespace cphnsw;
@@ -128,9 +130,105 @@ int neighbor_aux_nbit_t(uint32_t dim, uint64_t n, const float* parent, const flo
     return 0;
 }
 
+// The sample loop of Index::calibrate_estimator (api/hnsw_index.hpp:786-866, the lambda process_query) composed from the
+// reference's own types and primitives -- l2_distance_simd, encode_query_raw, fastscan::compute_*_inner_products, the
+// neighbour-block members -- with the scalar expressions written as the reference writes them and compiled with its flags.
+// (The loop itself is a lambda over locals of a private member function and cannot be called; this is the same kind of
+// composition as the exhaustive-scan oracle)  records: VertexSearchData<D,32,B>[n], raw: f32 [n][D].
+template <size_t D, size_t B>
+int calib_samples_t(uint32_t dim, uint64_t ns, const float* queries /* [ns][D], padded */, const uint32_t* start_ids, const float* raw,
+                    const uint8_t* records, uint64_t rec_size, uint32_t nb_off, uint32_t* parent_out, float* nn_dist_sq, float* dist_qp_sq_out,
+                    float* nop_out, float* ip_corrected_out, float* ip_qo_denom_out, float* true_ip_out, uint32_t* neighbor_out) {
+    using NB = std::conditional_t<B == 1, FastScanNeighborBlock<D, 32>, NbitFastScanNeighborBlock<D, 32, B>>;
+    using Enc = std::conditional_t<B == 1, RaBitQEncoder<D>, NbitRaBitQEncoder<D, B>>;
+    Enc encoder_(dim, constants::kDefaultRotationSeed);
+    auto get_vector = [&](uint32_t id) { return raw + (size_t)id * D; };
+    auto get_neighbors = [&](uint32_t id) -> const NB& { return *reinterpret_cast<const NB*>(records + (size_t)id * rec_size + nb_off); };
+    for (uint64_t s = 0; s < ns; ++s) {
+        const float* query_vec = queries + s * D;
+        uint32_t parent = start_ids[s];
+        float best_dist = l2_distance_simd<D>(query_vec, get_vector(parent));
+        const auto& nb = get_neighbors(parent);
+        for (size_t i = 0; i < nb.size(); ++i) {
+            uint32_t nid = nb.neighbor_ids[i];
+            if (nid == INVALID_NODE) break;
+            float d = l2_distance_simd<D>(query_vec, get_vector(nid));
+            if (d < best_dist) {
+                best_dist = d;
+                parent = nid;
+            }
+        }
+        nn_dist_sq[s] = best_dist;
+        parent_out[s] = parent;
+        const auto& pnb = get_neighbors(parent);
+        auto encoded = encoder_.encode_query_raw(query_vec);
+        float dist_qp_sq = l2_distance_simd<D>(query_vec, get_vector(parent));
+        dist_qp_sq_out[s] = dist_qp_sq;
+        for (size_t j = 0; j < 32; ++j) {
+            nop_out[s * 32 + j] = 0.0f; ip_corrected_out[s * 32 + j] = 0.0f; ip_qo_denom_out[s * 32 + j] = 0.0f;
+            true_ip_out[s * 32 + j] = 0.0f; neighbor_out[s * 32 + j] = INVALID_NODE;
+        }
+        size_t num_batches = (pnb.size() + constants::kFastScanBatch - 1) / constants::kFastScanBatch;
+        for (size_t batch = 0; batch < num_batches; ++batch) {
+            size_t batch_start = batch * constants::kFastScanBatch;
+            size_t batch_count = std::min(constants::kFastScanBatch, pnb.size() - batch_start);
+            alignas(64) uint32_t fastscan_sums[constants::kFastScanBatch];
+            if constexpr (B == 1) {
+                fastscan::compute_inner_products(encoded.lut, pnb.code_blocks[batch], fastscan_sums);
+            } else {
+                alignas(64) uint32_t msb_sums[constants::kFastScanBatch];
+                fastscan::compute_nbit_inner_products<D, B>(encoded.lut, pnb.code_blocks[batch], fastscan_sums, msb_sums);
+            }
+            for (size_t j = 0; j < batch_count; ++j) {
+                size_t ni = batch_start + j;
+                uint32_t neighbor = pnb.neighbor_ids[ni];
+                if (neighbor == INVALID_NODE) break;
+                float ip_qo = pnb.ip_qo[ni];
+                float nop = std::max(pnb.nop[ni], constants::eps::kSmall);
+                float A = encoded.coeff_fastscan;
+                float Bc = encoded.coeff_popcount;
+                float C = encoded.coeff_constant;
+                float ip_approx;
+                if constexpr (B == 1) {
+                    ip_approx = A * static_cast<float>(fastscan_sums[j]) + Bc * static_cast<float>(pnb.popcounts[ni]) + C;
+                } else {
+                    constexpr float K = static_cast<float>((1u << B) - 1);
+                    constexpr float inv_K = 1.0f / K;
+                    ip_approx = A * inv_K * static_cast<float>(fastscan_sums[j]) + Bc * inv_K * static_cast<float>(pnb.weighted_popcounts[ni]) + C;
+                }
+                float ip_corrected = ip_approx - pnb.ip_cp[ni];
+                float ip_qo_denom = std::max(std::abs(ip_qo), constants::eps::kMedium);
+                const float* p_vec = get_vector(parent);
+                const float* o_vec = get_vector(neighbor);
+                float true_ip = 0.0f;
+                for (size_t d = 0; d < D; ++d) {
+                    true_ip += (query_vec[d] - p_vec[d]) * (o_vec[d] - p_vec[d]);
+                }
+                true_ip /= nop;
+                nop_out[s * 32 + ni] = nop; ip_corrected_out[s * 32 + ni] = ip_corrected; ip_qo_denom_out[s * 32 + ni] = ip_qo_denom;
+                true_ip_out[s * 32 + ni] = true_ip; neighbor_out[s * 32 + ni] = neighbor;
+            }
+        }
+    }
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
+
+int refshim_calib_samples(uint32_t D, uint32_t B, uint32_t dim, uint64_t ns, const float* queries, const uint32_t* start_ids, const float* raw,
+                          const uint8_t* records, uint64_t rec_size, uint32_t nb_off, uint32_t* parent, float* nn_dist_sq, float* dist_qp_sq,
+                          float* nop, float* ip_corrected, float* ip_qo_denom, float* true_ip, uint32_t* neighbor) {
+#define CALIB_CASE(DD) if (D == DD) { \
+        if (B == 1) return calib_samples_t<DD, 1>(dim, ns, queries, start_ids, raw, records, rec_size, nb_off, parent, nn_dist_sq, dist_qp_sq, nop, ip_corrected, ip_qo_denom, true_ip, neighbor); \
+        if (B == 2) return calib_samples_t<DD, 2>(dim, ns, queries, start_ids, raw, records, rec_size, nb_off, parent, nn_dist_sq, dist_qp_sq, nop, ip_corrected, ip_qo_denom, true_ip, neighbor); \
+        if (B == 4) return calib_samples_t<DD, 4>(dim, ns, queries, start_ids, raw, records, rec_size, nb_off, parent, nn_dist_sq, dist_qp_sq, nop, ip_corrected, ip_qo_denom, true_ip, neighbor); }
+    CALIB_CASE(32) CALIB_CASE(128) CALIB_CASE(1024)
+#undef CALIB_CASE
+    return -1;
+}
+
 
 int refshim_encode_queries(uint32_t dim, uint64_t nq, const float* q, uint8_t* lut, float* coeffs) {
     size_t pd = next_power_of_two(dim);

@@ -17,7 +17,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "cphnsw_b200" / "libcphnsw_b200.so"
 OBJ = HERE / "build"
-SOURCES = ["capi.cu", "query_prep.cu", "fastscan_blocks.cu", "search.cu", "relayout.cu", "exhaustive.cu", "exhaustive_tc.cu", "exhaustive_tc16.cu", "postprocess.cu", "neighbor_codes.cu"]
+SOURCES = ["capi.cu", "query_prep.cu", "fastscan_blocks.cu", "search.cu", "relayout.cu", "exhaustive.cu", "exhaustive_tc.cu", "exhaustive_tc16.cu", "postprocess.cu", "neighbor_codes.cu", "calibration.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-Xptxas", "-v",

@@ -75,6 +75,7 @@ SYMBOLS = {
     "cphnsw_b200_merge_candidates": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P, _P, _P]),
     "cphnsw_b200_exhaustive_estimates": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P, _P]),
     "cphnsw_b200_unique_topk": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_uint64, _P, C.c_uint64, _P, _P, _P]),
+    "cphnsw_b200_calibration_samples": (C.c_int, [_P, _P, _P, C.c_uint64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cphnsw_b200_neighbor_codes": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint64, _P, C.c_uint64, C.c_uint64, _P, _P,
                                              C.c_uint64, _P, _P, _P, C.c_uint64, _P]),
 }

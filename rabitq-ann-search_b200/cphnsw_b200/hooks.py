@@ -177,6 +177,27 @@ def merge_candidates(ix, keys: torch.Tensor, dists: torch.Tensor | None, k: int)
     return ids, out, tau
 
 
+def calibration_samples(ix, queries: torch.Tensor, start_ids: torch.Tensor):
+    """N4: the sample loop of Index::calibrate_estimator (cphnsw_b200_calibration_samples).  queries f32 [ns, dim], start_ids
+    i32 [ns] -> dict of parent i32 [ns], nn_dist_sq / dist_qp_sq f32 [ns], nop / ip_corrected / ip_qo_denom / true_ip f32
+    [ns, 32], neighbor i32 [ns, 32] (-1 past the parent's last neighbour)."""
+    dev = _dev(ix)
+    q = queries.to(dev, torch.float32).contiguous()
+    st = start_ids.to(dev, torch.int32).contiguous()
+    ns = q.shape[0]
+    assert tuple(st.shape) == (ns,) and q.shape[1] == ix.dim
+    o = {"parent": torch.empty((ns,), dtype=torch.int32, device=dev), "nn_dist_sq": torch.empty((ns,), dtype=torch.float32, device=dev),
+         "dist_qp_sq": torch.empty((ns,), dtype=torch.float32, device=dev)}
+    for name in ("nop", "ip_corrected", "ip_qo_denom", "true_ip"):
+        o[name] = torch.empty((ns, 32), dtype=torch.float32, device=dev)
+    o["neighbor"] = torch.empty((ns, 32), dtype=torch.int32, device=dev)
+    _capi.check(ix.handle, ix._lib.cphnsw_b200_calibration_samples(
+        ix.handle, q.data_ptr(), st.data_ptr(), ns, o["parent"].data_ptr(), o["nn_dist_sq"].data_ptr(), o["dist_qp_sq"].data_ptr(),
+        o["nop"].data_ptr(), o["ip_corrected"].data_ptr(), o["ip_qo_denom"].data_ptr(), o["true_ip"].data_ptr(), o["neighbor"].data_ptr(),
+        _stream(ix)))
+    return o
+
+
 def upload_arrays(ix, *, D, bits, dim, search_data, raw, norm_sq, calibration, centroid=None, max_level=0,
                   entry_point=0, graph_entry_point=0, rotation_seed=42, layers=()):
     """cphnsw_b200_upload from numpy arrays laid out like the reference's in-memory index.

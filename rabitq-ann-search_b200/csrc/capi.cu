@@ -930,6 +930,33 @@ int cphnsw_b200_exact_l2(cphnsw_b200_index* ix, const float* d_queries, uint64_t
     });
 }
 
+int cphnsw_b200_calibration_samples(cphnsw_b200_index* ix, const float* d_queries, const uint32_t* d_start_ids, uint64_t ns,
+                                    uint32_t* d_parent, float* d_nn_dist_sq, float* d_dist_qp_sq, float* d_nop, float* d_ip_corrected,
+                                    float* d_ip_qo_denom, float* d_true_ip, uint32_t* d_neighbor, void* stream) {
+    int rc = require_loaded(ix);
+    if (rc) return rc;
+    if (ns == 0) return 0;
+    if (!d_queries || !d_start_ids || !d_parent || !d_nn_dist_sq || !d_dist_qp_sq || !d_nop || !d_ip_corrected || !d_ip_qo_denom ||
+        !d_true_ip || !d_neighbor)
+        return fail(ix, CPHNSW_B200_EINVAL, "null buffer");
+    if (ns > 0x7FFFFFFFull) return fail(ix, CPHNSW_B200_EINVAL, "too many samples in one call");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return with_lane(ix, st, false, [&](Lane& L) -> int {
+        QStateView qs;
+        int r = ensure_qstate(ix, L, ns, &qs);
+        if (r) return r;
+        PrepOut po{};
+        po.coeffs = qs.coeffs; po.uplanes = qs.uplanes; po.qT = qs.qT;
+        CUDA_TRY(ix, launch_query_prep(ix->dev, d_queries, (uint32_t)ns, 0, po, st));
+        CalibrationArgs a{};
+        a.queries = d_queries; a.start_ids = d_start_ids; a.ns = ns; a.qT = qs.qT; a.uplanes = qs.uplanes; a.coeffs = qs.coeffs;
+        a.parent = d_parent; a.nn_dist_sq = d_nn_dist_sq; a.dist_qp_sq = d_dist_qp_sq; a.nop = d_nop; a.ip_corrected = d_ip_corrected;
+        a.ip_qo_denom = d_ip_qo_denom; a.true_ip = d_true_ip; a.neighbor = d_neighbor;
+        CUDA_TRY(ix, launch_calibration_samples(ix->dev, a, st));
+        return 0;
+    });
+}
+
 int cphnsw_b200_greedy_descent(cphnsw_b200_index* ix, const float* d_queries, uint64_t nq, uint32_t* d_entry,
                                void* stream) {
     int rc = require_loaded(ix);

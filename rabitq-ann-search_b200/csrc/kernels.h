@@ -122,6 +122,22 @@ cudaError_t launch_exhaustive_scan_tc16(const DevIndex& ix, const ExhaustiveArgs
 cudaError_t launch_exhaustive_scan_tc(const DevIndex& ix, const ExhaustiveArgs& a, int num_sms, unsigned long long* partial,
                                       uint32_t* nseg, cudaStream_t stream);
 
+// ---- N4 calibration sampling (calibration.cu) -------------------------------------------------------------------
+struct CalibrationArgs {
+    const float* queries;        // [ns][dim] the sampled queries as given
+    const uint32_t* start_ids;   // [ns] start vertex of each sample
+    uint64_t ns;
+    const float* qT;             // K1 outputs for the same queries (no centring)
+    const uint32_t* uplanes;
+    const float* coeffs;
+    uint32_t* parent;            // [ns]
+    float* nn_dist_sq;           // [ns]
+    float* dist_qp_sq;           // [ns]
+    float *nop, *ip_corrected, *ip_qo_denom, *true_ip;   // [ns][32]; 0 past the parent's last neighbour
+    uint32_t* neighbor;          // [ns][32]; 0xFFFFFFFF past the parent's last neighbour
+};
+cudaError_t launch_calibration_samples(const DevIndex& ix, const CalibrationArgs& a, cudaStream_t stream);
+
 // ---- result post-processing, outside the parity path (postprocess.cu) -----------------------------------
 cudaError_t launch_unique_topk(const int64_t* ids_in, const float* dists_in, uint64_t nq, uint32_t kin, uint32_t kout,
                                const uint32_t* id_map, uint64_t map_size, int64_t* ids_out, float* dists_out, cudaStream_t stream);
