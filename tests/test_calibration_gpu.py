@@ -30,13 +30,10 @@ def _run(ix, q, start):
 @pytest.mark.parametrize("dim,bits", [(24, 1), (64, 2), (100, 2), (128, 4), (128, 1), (960, 2), (1500, 4)])
 def test_samples_match_the_restatement(oracle, dim, bits):
     fab = common.fabricate(3000, dim, bits, seed=dim + bits, counts=(32, 32, 29, 9, 0))
-    ids_off = fab.nb_off + co.nb_layout(fab.D, bits)["ids"]
-    fab.search_data[7, ids_off + 4 * 5:ids_off + 4 * 6] = 0xFF        # a hole: the loop stops at the first empty slot
-    ix = common.gpu_index_from(fab)
+    ix = common.gpu_index_from(fab)      # (a hole inside a block -- covered on the CPU side -- is refused by the index hand-off as corrupt)
     rng = np.random.default_rng(5)
     ns = 777
     start = rng.integers(0, fab.n, ns).astype(np.uint32)
-    start[:4] = 7
     q = np.ascontiguousarray(fab.raw[rng.integers(0, fab.n, ns), :dim])
     q[ns // 2:] += (0.2 * rng.standard_normal((ns - ns // 2, dim))).astype(np.float32)
     got = _run(ix, q, start)
