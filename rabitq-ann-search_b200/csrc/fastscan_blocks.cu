@@ -31,16 +31,12 @@ __device__ __forceinline__ void fs_mbar_init_fence() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-// One block into one stage: the code planes [0, aux_off) and the aux fields behind the neighbour ids
-// [aux_off + 128, bytes) as two bulk copies -- the estimator never reads the 128 bytes of ids between them, so that
-// 128-byte line is not fetched (a block is 21 lines of traffic instead of 22).
-__device__ __forceinline__ void fs_issue(void* dst, const void* src, uint32_t aux_off, uint32_t bytes, uint64_t* bar) {
-    const uint32_t d = fs_smem_u32(dst), b = fs_smem_u32(bar), skip = aux_off + 128u;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes - 128u) : "memory");
+// (Tried and not kept: two bulk copies per block that skip the 128 bytes of neighbour ids the estimator never reads -- 21
+// lines of traffic instead of 22.  The second copy costs more than the line saves: 0.642 of the HBM peak against 0.668.)
+__device__ __forceinline__ void fs_issue(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fs_smem_u32(bar)), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(d), "l"(src), "r"(aux_off), "r"(b) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(d + skip), "l"(static_cast<const uint8_t*>(src) + skip), "r"(bytes - skip), "r"(b) : "memory");
+                 ::"r"(fs_smem_u32(dst)), "l"(src), "r"(bytes), "r"(fs_smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fs_wait(uint64_t* bar, uint32_t phase) {
     uint32_t done;
@@ -54,9 +50,8 @@ __device__ __forceinline__ void fs_wait(uint64_t* bar, uint32_t phase) {
 // phases, and a parity wait returns once the phase of that parity is over -- the same protocol, minus the hardware
 inline void fs_mbar_init(uint64_t* bar) { __atomic_store_n(bar, 0, __ATOMIC_RELEASE); }
 inline void fs_mbar_init_fence() {}
-inline void fs_issue(void* dst, const void* src, uint32_t aux_off, uint32_t bytes, uint64_t* bar) {
-    memcpy(dst, src, aux_off);
-    memcpy(static_cast<uint8_t*>(dst) + aux_off + 128, static_cast<const uint8_t*>(src) + aux_off + 128, bytes - aux_off - 128);
+inline void fs_issue(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    memcpy(dst, src, bytes);
     __atomic_fetch_add(bar, 1, __ATOMIC_RELEASE);
 }
 inline void fs_wait(uint64_t* bar, uint32_t phase) {
@@ -101,7 +96,7 @@ __global__ void __launch_bounds__(kFsMaxWarps * 32) fastscan_blocks_kernel(const
     if (lane == 0)
         for (uint32_t s = 0; s < ns; ++s) {
             const uint64_t i = first + (uint64_t)s * stride;
-            if (i < a.nblocks) fs_issue(stages + (size_t)s * stage_bytes, block_ptr(i), ix.aux_off, copy_bytes, mbar + s);
+            if (i < a.nblocks) fs_issue(stages + (size_t)s * stage_bytes, block_ptr(i), copy_bytes, mbar + s);
         }
 
     // slack level of blocks without an explicit one: looked up once, not per block (a dynamic index into the
@@ -140,7 +135,7 @@ __global__ void __launch_bounds__(kFsMaxWarps * 32) fastscan_blocks_kernel(const
         __syncwarp();   // every lane is done reading this stage: refill it
         if (lane == 0) {
             const uint64_t nxt = i + (uint64_t)ns * stride;
-            if (nxt < a.nblocks) fs_issue(stages + (size_t)s * stage_bytes, block_ptr(nxt), ix.aux_off, copy_bytes, mbar + s);
+            if (nxt < a.nblocks) fs_issue(stages + (size_t)s * stage_bytes, block_ptr(nxt), copy_bytes, mbar + s);
         }
         uint32_t nbit, msb, msb2;
         combine_planes<B>(ps, nbit, msb, msb2);
