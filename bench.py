@@ -468,13 +468,13 @@ def run_c4(args, rank, world, local):
     q_dev = torch.randn((nq, dim), generator=gq, device=dev)
     q_pin = q_dev.cpu().pin_memory()
 
-    def step_dev(q, kp_=None):
+    def step_dev(q, kp_=None, timeline=None):
         kp_ = kp if kp_ is None else kp_
         if world == 1 and not args.c4_pieces:
             return hooks.exhaustive_search(ix, q, k, kp_)           # one scan of the whole database
         # shards scan their ranges in pieces, exchange thresholds (all-reduce(min) of nq floats), all-gather their k' candidates
         # (key + exact distance) and merge: the same result as the single scan (tests/test_exhaustive_gpu.py, test_multigpu_gpu.py)
-        return sharding.exhaustive_search_db_sharded_device(ix, q, k, kp_, m, n, b, prefix=args.c4_prefix, growth=args.c4_growth)
+        return sharding.exhaustive_search_db_sharded_device(ix, q, k, kp_, m, n, b, prefix=args.c4_prefix, growth=args.c4_growth, timeline=timeline)
 
     def barrier():
         if world > 1:
@@ -505,6 +505,12 @@ def run_c4(args, rank, world, local):
         dev_ms, step_ms, (out_i, out_d), t_begin = timed(kp, args.steps, args.warmup)
         clocks.window(t_begin, time.time())
     value = nq * args.steps / (dev_ms / 1e3)
+    phases = None
+    if world > 1 or args.c4_pieces:      # where one step's time goes on this rank (device timeline of one more step)
+        tl = []
+        step_dev(q_dev, kp, tl)
+        torch.cuda.synchronize()
+        phases = [{"phase": name, "ms": round(tl[i - 1][1].elapsed_time(ev), 3)} for i, (name, ev) in enumerate(tl) if i]
     # e2e: queries from pinned host memory, results back to the host, every step
     ids_pin = torch.empty((nq, k), dtype=torch.int64).pin_memory()
     d_pin = torch.empty((nq, k), dtype=torch.float32).pin_memory()
@@ -548,6 +554,8 @@ def run_c4(args, rank, world, local):
                          "note": "whole step timed (K1 + threshold prefix + scan + select / re-rank, and for N > 1 the exchanges and the merge); the scan "
                                  "kernel is ~90% of it at N = 1 (DESIGN.md section 4, K5)"},
             "clocks": clocks.summary(), "step_ms": [round(x, 3) for x in step_ms]}
+    if phases:
+        line["phases_rank0"] = phases
     if rank == 0 and world == 1 and not args.no_recall:
         # recall@10 of (1-bit estimate -> k' candidates -> exact re-rank) against brute force, per re-rank depth k': the
         # operating point is a choice of k' (the scan's tensor-core forms reach k' = 256; beyond, the popcount form)

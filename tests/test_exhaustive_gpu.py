@@ -164,7 +164,7 @@ def _sharded_on_one_device(ix, q, k, kp, n, world, prefix, growth):
         if last:
             break
         if c == 0:
-            tau = hooks.merge_candidates(ix, torch.stack(keys), None, 0)[2]      # all-gather of the first pieces' keys
+            tau = torch.stack([sharding.kth_estimate(kk, -(-kp // world)) for kk in keys]).max(0).values      # all-reduce(max)
         else:
             tau = torch.stack(tl).min(0).values                                  # all-reduce(min)
     return hooks.merge_candidates(ix, torch.stack(keys), torch.stack(dists), k)[:2]
