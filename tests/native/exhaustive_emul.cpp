@@ -1,9 +1,11 @@
 // K5, popcount form: exhaustive_scan_kernel + exhaustive_select_rerank_kernel (exhaustive.cu; the second also ends the
-// two tensor-core forms) with the index hand-off of relayout.cu, compiled for the host over cuda_emul.h.  The prepared
+// two tensor-core forms), and the scan in pieces: candidate mode + exhaustive_select_keys_kernel + merge_candidates_kernel, with the index hand-off of relayout.cu, compiled for the host over cuda_emul.h.  The prepared
 // (centred) queries come from the K1 harness.  Built and called by tests/test_kernels_emulated.py; never part of the product.
 #include "cuda_emul.h"
 
 #include <float.h>
+
+#include <algorithm>
 
 namespace cpb { alignas(128) uint8_t smem_raw[224 * 1024]; }
 
@@ -14,7 +16,8 @@ namespace cpb { alignas(128) uint8_t smem_raw[224 * 1024]; }
 extern "C" int emul_exhaustive(uint32_t dim, const uint8_t* records, uint64_t rec_size, uint32_t nb_off, uint64_t n, const float* raw,
                                const float* norm_sq, const float* calib3 /* affine_a, affine_b, ip_qo_floor */, const float* qT,
                                const uint32_t* uplanes, const float* coeffs, uint32_t nq, uint64_t id_begin, uint64_t id_end,
-                               uint32_t k, uint32_t kprime, uint32_t nslices, uint32_t* sums, float* est, int64_t* ids, float* dists) {
+                               uint32_t k, uint32_t kprime, uint32_t nslices, uint32_t* sums, float* est, int64_t* ids, float* dists,
+                               uint32_t npieces /* > 1: scan [id_begin, id_end) in that many pieces, as run_exhaustive / sharding.py do */) {
     using namespace cpb;
     DevIndex ix{};
     uint32_t D = 16;
@@ -50,6 +53,43 @@ extern "C" int emul_exhaustive(uint32_t dim, const uint8_t* records, uint64_t re
     const uint32_t cap = kprime <= 384 ? 1024u : (uint32_t)kCapMax;
     const size_t smem = (size_t)kQT * cap * 8 + (size_t)kQT * ix.nch * 64 + (size_t)kQT * 16;
     if (smem > sizeof(smem_raw)) return 2;
+    if (npieces > 1 && kprime && k) {
+        // the candidate interface: the k' best keys of (earlier pieces U this piece), thresholds handed on, exact distances on
+        // the last piece, then the merge of the one list -- launch_exhaustive's kernel choices
+        std::vector<unsigned long long> keys[2] = {std::vector<unsigned long long>((size_t)nq * kprime), std::vector<unsigned long long>((size_t)nq * kprime)};
+        std::vector<float> tau(nq, FLT_MAX), cd((size_t)nq * kprime);
+        const uint64_t plen = (m + npieces - 1) / npieces;
+        for (uint32_t c = 0; c < npieces; ++c) {
+            const bool last = c + 1 == npieces;
+            ExhaustiveArgs p = a;
+            p.id_begin = id_begin + std::min<uint64_t>(m, (uint64_t)c * plen); p.id_end = id_begin + std::min<uint64_t>(m, (uint64_t)(c + 1) * plen);
+            p.k = 0; p.ids = nullptr; p.dists = nullptr; p.sums = nullptr; p.est = nullptr;
+            p.prior_keys = c ? keys[(c - 1) & 1].data() : nullptr; p.tau_in = c ? tau.data() : nullptr;
+            p.cand_keys = keys[c & 1].data(); p.tau_out = tau.data(); p.cand_dists = last ? cd.data() : nullptr; p.id_offset = 0;
+            const uint64_t pm = p.id_end - p.id_begin, psl = pm ? (pm + nslices - 1) / nslices : 1;
+            std::fill(partial.begin(), partial.end(), 0xEEEEEEEEEEEEEEEEull);
+            auto scan = [&](int) { exhaustive_scan_kernel(ix, p, nslices, psl, cap, partial.data()); };
+            cuda_emul::launch(scan, dim3(nslices, (nq + kQT - 1) / kQT), kExThreads, smem_raw, smem, 0);
+            if (!last && 2 * kprime <= kSelCap) {
+                auto sel = [&](int) { exhaustive_select_keys_kernel(p, nslices, partial.data()); };
+                cuda_emul::launch(sel, (nq + kSelWarps - 1) / kSelWarps, kSelWarps * 32, smem_raw, 0, 0);
+            } else {
+                uint32_t sort_n = 1;
+                while (sort_n < (nslices + (p.prior_keys ? 1u : 0u)) * kprime) sort_n <<= 1;
+                const size_t smem2 = (((size_t)sort_n * 8 + 15) & ~(size_t)15) + (size_t)8 * (ix.T + 4) * 4;
+                if (smem2 > sizeof(smem_raw)) return 3;
+                auto sel = [&](int) { exhaustive_select_rerank_kernel(ix, p, nslices, sort_n, partial.data()); };
+                cuda_emul::launch(sel, nq, kExThreads, smem_raw, smem2, 0);
+            }
+            if (last) {
+                uint32_t sort_n = 2;
+                while (sort_n < kprime) sort_n <<= 1;
+                auto mrg = [&](int) { merge_candidates_kernel(keys[c & 1].data(), cd.data(), 1, nq, kprime, k, sort_n, ids, dists, nullptr); };
+                cuda_emul::launch(mrg, nq, kExThreads, smem_raw, (size_t)sort_n * 8, 0);
+            }
+        }
+        return 0;
+    }
     if (m > 0 || kprime) {
         auto scan = [&](int) { exhaustive_scan_kernel(ix, a, nslices, slice_len, cap, partial.data()); };
         cuda_emul::launch(scan, dim3(nslices, (nq + kQT - 1) / kQT), kExThreads, smem_raw, smem, 0);

@@ -291,7 +291,7 @@ def k5(tmp_path_factory):
     return _build(tmp_path_factory, "exhaustive_emul")
 
 
-def _exhaustive(k1, k5, oracle, sf, queries, k, kprime, nslices=1, dense=False, id_begin=0, id_end=None):
+def _exhaustive(k1, k5, oracle, sf, queries, k, kprime, nslices=1, dense=False, id_begin=0, id_end=None, pieces=1):
     id_end = sf.n if id_end is None else id_end
     _, coeffs, _, upl, qT = _prepare(k1, oracle, queries, center=True, centroid=sf.centroid)
     nq, m = len(queries), id_end - id_begin
@@ -307,7 +307,7 @@ def _exhaustive(k1, k5, oracle, sf, queries, k, kprime, nslices=1, dense=False, 
                             _p(raw, C.c_float), _p(norm_sq, C.c_float), _p(cal, C.c_float), _p(qT, C.c_float), _p(upl, C.c_uint32),
                             _p(coeffs, C.c_float), C.c_uint32(nq), C.c_uint64(id_begin), C.c_uint64(id_end), C.c_uint32(k),
                             C.c_uint32(kprime), C.c_uint32(nslices), None if sums is None else _p(sums, C.c_uint32),
-                            None if est is None else _p(est, C.c_float), _p(ids, C.c_int64), _p(dists, C.c_float))
+                            None if est is None else _p(est, C.c_float), _p(ids, C.c_int64), _p(dists, C.c_float), C.c_uint32(pieces))
     assert rc == 0, rc
     return sums, est, ids, dists
 
@@ -323,11 +323,13 @@ def test_exhaustive_kernel_sources_reproduce_the_reference_composition(k1, k5, o
     for i in range(len(q)):
         assert np.array_equal(sums[i], g[f"sums_{i}"]), i
         assert np.array_equal(_bits(est[i]), _bits(g[f"est_{i}"])), i
-    for k, kp, nslices in ((10, 100, 1), (10, 100, 3), (1, 1, 1), (5, 32, 3), (10, 300, 1)):
-        _, _, ids, dists = _exhaustive(k1, k5, oracle, sf, q, k, kp, nslices=nslices)
+    # one pass, and the scan in pieces (candidate mode, thresholds handed on, warp key selection / CTA select, merge kernel)
+    for k, kp, nslices, pieces in ((10, 100, 1, 1), (10, 100, 3, 1), (1, 1, 1, 1), (5, 32, 3, 1), (10, 300, 1, 1),
+                                   (10, 100, 2, 3), (5, 32, 1, 4), (10, 300, 2, 2), (1, 1, 1, 3)):
+        _, _, ids, dists = _exhaustive(k1, k5, oracle, sf, q, k, kp, nslices=nslices, pieces=pieces)
         for i in range(len(q)):
-            assert np.array_equal(ids[i], g[f"ids_{i}_k{k}_kp{kp}"]), (i, k, kp, nslices)
-            assert np.array_equal(_bits(dists[i]), _bits(g[f"dists_{i}_k{k}_kp{kp}"])), (i, k, kp, nslices)
+            assert np.array_equal(ids[i], g[f"ids_{i}_k{k}_kp{kp}"]), (i, k, kp, nslices, pieces)
+            assert np.array_equal(_bits(dists[i]), _bits(g[f"dists_{i}_k{k}_kp{kp}"])), (i, k, kp, nslices, pieces)
 
 
 @pytest.mark.parametrize("D", [16, 128, 1024])
@@ -351,3 +353,65 @@ def test_exact_distance_kernel_source_against_the_reference_dot_products(k1, k3,
         for j in range(6):   # the other pairs against the oracle's dot
             w = np.float32(np.float32(qn + norm_sq[j]) - np.float32(np.float32(2.0) * oracle.dot(a[i], b[j])))
             assert _bits(out[i, j:j + 1])[0] == _bits(np.array([max(w, np.float32(0.0))]))[0], (i, j)
+
+
+# ---- N4 (calibration.cu): the sample loop of calibrate_estimator -------------------------------------------------------
+@pytest.fixture(scope="module")
+def n4(tmp_path_factory):
+    return _build(tmp_path_factory, "calibration_emul")
+
+
+def _calibration(k1, n4, oracle, dim, bits, records, rec_size, nb_off, raw, queries, start):
+    ns = len(queries)
+    _, coeffs, _, upl, qT = _prepare(k1, oracle, queries)
+    records = np.ascontiguousarray(records)
+    raw = np.ascontiguousarray(raw, np.float32)
+    q = np.ascontiguousarray(queries, np.float32)
+    st = np.ascontiguousarray(start, np.uint32)
+    o = {"parent": np.full(ns, 0xEEEEEEEE, np.uint32), "nn_dist_sq": np.full(ns, np.nan, np.float32), "dist_qp_sq": np.full(ns, np.nan, np.float32),
+         "neighbor": np.full((ns, 32), 0xEEEEEEEE, np.uint32)}
+    for name in ("nop", "ip_corrected", "ip_qo_denom", "true_ip"):
+        o[name] = np.full((ns, 32), np.nan, np.float32)
+    rc = n4.emul_calibration_samples(C.c_uint32(dim), C.c_uint32(bits), _p(records, C.c_uint8), C.c_uint64(rec_size), C.c_uint32(nb_off),
+                                     C.c_uint64(raw.shape[0]), _p(raw, C.c_float), _p(q, C.c_float), _p(st, C.c_uint32), C.c_uint64(ns),
+                                     _p(qT, C.c_float), _p(upl, C.c_uint32), _p(coeffs, C.c_float), _p(o["parent"], C.c_uint32),
+                                     _p(o["nn_dist_sq"], C.c_float), _p(o["dist_qp_sq"], C.c_float), _p(o["nop"], C.c_float),
+                                     _p(o["ip_corrected"], C.c_float), _p(o["ip_qo_denom"], C.c_float), _p(o["true_ip"], C.c_float),
+                                     _p(o["neighbor"], C.c_uint32))
+    assert rc == 0, rc
+    return o
+
+
+@pytest.mark.parametrize("bits", [1, 2, 4])
+def test_calibration_kernel_source_on_the_reference_index_files(k1, n4, oracle, bits):
+    """calibration.cu on host threads against the composition over the unmodified reference (calib_golden.npz) on the index
+    files the reference built and saved: everything bit for bit, except ip_corrected, which carries coeff_constant -- fused
+    one way in the search path that K1 reproduces and, in the composition's D = 32 instantiation only, the other way (an
+    ulp of a term ~20; tests/test_oracle_calibration.py)."""
+    g = np.load(common.GOLDEN / "calib_golden.npz")
+    sf = co_SaveFile(common.GOLDEN / f"ref_n300_d24_b{bits}.bin")
+    got = _calibration(k1, n4, oracle, sf.dim, bits, sf.search_data, sf.rec_size, sf.nb_off, sf.raw, g[f"queries_b{bits}"], g[f"start_b{bits}"])
+    for k in ("parent", "neighbor"):
+        assert np.array_equal(got[k], g[f"{k}_b{bits}"]), k
+    for k in ("nn_dist_sq", "dist_qp_sq", "nop", "ip_qo_denom", "true_ip"):
+        assert np.array_equal(_bits(got[k]), _bits(g[f"{k}_b{bits}"])), k
+    assert np.allclose(got["ip_corrected"], g[f"ip_corrected_b{bits}"], rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("dim,bits", [(128, 4), (100, 2), (20, 1)])
+def test_calibration_kernel_source_equals_the_restatement(k1, n4, oracle, dim, bits):
+    """Fabricated indexes with partial and empty blocks: every field bit for bit against cpo_calibration_sample."""
+    fab = common.fabricate(300, dim, bits, seed=dim * 3 + bits, counts=(32, 32, 29, 9, 0))
+    rng = np.random.default_rng(8)
+    ns = 40
+    start = rng.integers(0, fab.n, ns).astype(np.uint32)
+    q = np.ascontiguousarray(fab.raw[rng.integers(0, fab.n, ns), :dim])
+    q[ns // 2:] += (0.2 * rng.standard_normal((ns - ns // 2, dim))).astype(np.float32)
+    got = _calibration(k1, n4, oracle, dim, bits, fab.search_data, fab.search_data.shape[1], fab.nb_off, fab.raw, q, start)
+    qp = np.zeros((ns, fab.D), np.float32)
+    qp[:, :dim] = q
+    want = oracle.calibration_samples(oracle.index_view(fab), qp, start)
+    for k in ("parent", "neighbor"):
+        assert np.array_equal(got[k], want[k]), k
+    for k in ("nn_dist_sq", "dist_qp_sq", "nop", "ip_corrected", "ip_qo_denom", "true_ip"):
+        assert np.array_equal(_bits(got[k]), _bits(want[k])), k
