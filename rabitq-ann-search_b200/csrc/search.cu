@@ -557,16 +557,19 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                     const float ipqo = reinterpret_cast<const float*>(aux + 256)[lane];
                     const float ipcp = reinterpret_cast<const float*>(aux + 384)[lane];
                     const uint32_t pops = reinterpret_cast<const uint32_t*>(aux + 512)[lane];
+                    // planes 1 .. B-1, the MSB-pair bound and the full estimate in one go: the estimate is wanted unless EVERY
+                    // neighbour's MSB-pair bound reaches the k-th distance (:178-187) -- which this data never does -- so computing
+                    // it before that vote wastes nothing and lets its popcounts run under the bound's division chain
                     const uint32_t ps1 = plane_sum_one<true>(reinterpret_cast<const uint4*>(stage), 1, nch, lane, w.uq);
-                    const float msb_lower = convert_msb<B>(qp, 2u * ps0 + ps1, nop, ipqo, ipcp, pops & 0xFFFFu, dqp, sq);
-                    const bool any = nn_m < k || __any_sync(kFull, valid && msb_lower < w0);   // :178-187
-                    if (any) {
-                        uint32_t nbit = (ps0 << (B - 1)) + (ps1 << (B - 2));
+                    uint32_t nbit = (ps0 << (B - 1)) + (ps1 << (B - 2));
 #pragma unroll
-                        for (int b = 2; b < B; ++b)
-                            nbit += plane_sum_one<true>(reinterpret_cast<const uint4*>(stage), b, nch, lane, w.uq) << (B - 1 - b);
-                        est = nbit_est<B>(qp, nbit, nop, ipqo, ipcp, pops >> 16, lane, count, dqp);
-                    } else {
+                    for (int b = 2; b < B; ++b)
+                        nbit += plane_sum_one<true>(reinterpret_cast<const uint4*>(stage), b, nch, lane, w.uq) << (B - 1 - b);
+                    const float msb_lower = convert_msb<B>(qp, 2u * ps0 + ps1, nop, ipqo, ipcp, pops & 0xFFFFu, dqp, sq);
+                    const float full_est = nbit_est<B>(qp, nbit, nop, ipqo, ipcp, pops >> 16, lane, count, dqp);
+                    const bool any = nn_m < k || __any_sync(kFull, valid && msb_lower < w0);   // :178-187
+                    if (any) est = full_est;
+                    else {
                         if (STATS) ++st.msb_skipped;
                         est = FLT_MAX;
                         lower = msb_lower;

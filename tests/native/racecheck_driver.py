@@ -52,6 +52,15 @@ elif which == "k5":
     q = g["queries"][:2]
     _, _, ids, _ = T._exhaustive(lib("query_prep_emul"), lib("exhaustive_emul"), oracle, sf, q, 10, 100, nslices=2)
     ok &= all(np.array_equal(ids[i], g[f"ids_{i}_k10_kp100"]) for i in range(len(q)))
+    # the scan in pieces: candidate mode, warp key selection, CTA select with the earlier pieces' list, merge kernel
+    _, _, ids, _ = T._exhaustive(lib("query_prep_emul"), lib("exhaustive_emul"), oracle, sf, q, 10, 100, nslices=2, pieces=3)
+    ok &= all(np.array_equal(ids[i], g[f"ids_{i}_k10_kp100"]) for i in range(len(q)))
+elif which == "n4":
+    g = np.load(common.GOLDEN / "calib_golden.npz")
+    sf = co.SaveFile(common.GOLDEN / "ref_n300_d24_b4.bin")
+    got = T._calibration(lib("query_prep_emul"), lib("calibration_emul"), oracle, sf.dim, 4, sf.search_data, sf.rec_size, sf.nb_off, sf.raw,
+                         g["queries_b4"][:12], g["start_b4"][:12])
+    ok &= np.array_equal(got["neighbor"], g["neighbor_b4"][:12]) and np.array_equal(got["true_ip"].view(np.uint32), g["true_ip_b4"][:12].view(np.uint32))
 elif which == "n3":
     for dim, bits, global_tile in ((128, 4, False), (96, 2, True), (20, 1, True)):
         vec, pids, nbr = common.neighbor_code_case(dim, 5, dim + bits)

@@ -31,7 +31,7 @@ pytestmark = pytest.mark.skipif(os.environ.get("CPHNSW_RACECHECK") != "1" or _li
 @pytest.fixture(scope="module")
 def tsan_libs(tmp_path_factory):
     out = tmp_path_factory.mktemp("tsan")
-    for name in ("race_probe", "query_prep_emul", "fastscan_emul", "search_emul", "exhaustive_emul", "neighbor_codes_emul"):
+    for name in ("race_probe", "query_prep_emul", "fastscan_emul", "search_emul", "exhaustive_emul", "neighbor_codes_emul", "calibration_emul"):
         cmd = ["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
                "-I/usr/local/cuda/include", "-I", str(NATIVE), str(NATIVE / f"{name}.cpp"), "-o", str(out / f"lib{name}.so")]
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -57,7 +57,7 @@ def test_the_check_finds_a_missing_syncwarp(tsan_libs):
     assert any(name == "race_probe.cpp" for name, _ in _races(tsan_libs, "probe", 0))
 
 
-@pytest.mark.parametrize("which", ["k1", "k2", "k5", "n3"])
+@pytest.mark.parametrize("which", ["k1", "k2", "k5", "n3", "n4"])
 def test_kernel_source_has_no_unordered_accesses(tsan_libs, which):
     assert _races(tsan_libs, which) == set()
 
