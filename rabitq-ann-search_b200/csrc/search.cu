@@ -359,6 +359,8 @@ __device__ __forceinline__ uint32_t greedy_descent(const DevIndex& ix, const War
 // (Tried and not kept, again: an L2 prefetch of the block most likely to be expanded next -- the smaller child of the
 // frontier's root -- one expansion ahead: 3 % slower with it on, and its mere presence behind a flag cost 9 %, the register
 // allocation of this kernel being what it is.)
+// (Tried and not kept: fetching the ancestors' keys of the next push right after the pop, so that the push at the end of the
+// expansion does not wait for the arena -- 33 more instructions per expansion and more spills: 0.505 against 0.539.)
 // (Tried and not kept: more registers for fewer warps -- 72 / 79 / 96 registers at 28 / 24 / 20 warps per SM lose 8 - 13 %,
 // while 28 warps at 64 registers run as fast as 32.)
 // (Tried and not kept: instantiations with the CTA shape and the per-warp shared-memory stride as compile-time constants.
