@@ -1,0 +1,12 @@
+#!/bin/bash
+# Final round-2 numbers on one B200: the driver's two bench commands, then ncu of K3 (1M, one batch at a time) and K2.
+mkdir -p gpurun_out
+python bench.py --impl reference --gpus 1 --steps 5 --warmup 2 > gpurun_out/bench_r02_ref.json 2> gpurun_out/bench_r02_ref.err
+S=$(date +%s)
+python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_r02_1gpu.json 2> gpurun_out/bench_r02_1gpu.err
+echo "main arm wall seconds: $(( $(date +%s) - S ))"
+python profiles/pj.py < gpurun_out/bench_r02_1gpu.json
+CMD="python bench.py --steps 2 --warmup 1 --inflight 1 --no-gate --no-stream --no-recall --no-cpu-baseline --no-c4"
+ncu --set full --clock-control none --import-source on -k regex:search_kernel -s 4 -c 1 -f -o gpurun_out/k3_r02_final $CMD > /dev/null 2>&1
+ncu --set full --clock-control none -k regex:fastscan_blocks -s 2 -c 1 -f -o gpurun_out/k2_r02_final python bench.py --steps 2 --warmup 1 --no-gate --no-recall --no-cpu-baseline --no-c4 > /dev/null 2>&1
+ls -la gpurun_out/*_r02_final.ncu-rep
