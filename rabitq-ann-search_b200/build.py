@@ -29,15 +29,23 @@ def _newest_dep() -> float:
     return max(p.stat().st_mtime for p in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, variant: str = "", defines: tuple = ()) -> Path:
+    """variant / defines: an A/B build of the same library with extra -D flags, written to
+    cphnsw_b200/variants/libcphnsw_b200_<variant>.so (load it with CPHNSW_B200_LIB=...)."""
+    global OUT, OBJ
+    if variant:
+        OUT = HERE / "cphnsw_b200" / "variants" / f"libcphnsw_b200_{variant}.so"
+        OBJ = HERE / "build" / f"variant_{variant}"
+        OUT.parent.mkdir(exist_ok=True)
+        force = True
     newest = _newest_dep()
     if not force and OUT.exists() and OUT.stat().st_mtime >= newest:
         return OUT
-    OBJ.mkdir(exist_ok=True)
+    OBJ.mkdir(exist_ok=True, parents=True)
 
     def compile_one(src: str):
         obj = OBJ / (src + ".o")
-        cmd = ["nvcc", *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = ["nvcc", *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", str(CSRC / src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         (OBJ / (src + ".log")).write_text(r.stdout + r.stderr)
         if r.returncode != 0:
@@ -56,4 +64,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:   # build.py --variant NAME [DEFINE[=VALUE] ...]
+        i = sys.argv.index("--variant")
+        print(build(variant=sys.argv[i + 1], defines=tuple(sys.argv[i + 2:])))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -6,10 +6,12 @@ no Python or CPU fallback for the query path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libcphnsw_b200.so"
+# CPHNSW_B200_LIB: another build of the same library (A/B runs of kernel variants, build.py --variant); still native code
+LIB_PATH = Path(os.environ["CPHNSW_B200_LIB"]).resolve() if os.environ.get("CPHNSW_B200_LIB") else HERE / "libcphnsw_b200.so"
 
 OK, EINVAL, ERUNTIME, ECUDA, ENOMEM = 0, -1, -2, -3, -4
 

@@ -608,7 +608,7 @@ static int run_search(cphnsw_b200_index* ix, Lane& L, const float* d_queries, ui
     const bool stats = ix->collect_stats != 0;
     int warps = (int)ix->warps_per_cta;
     const size_t smem_budget = 220 * 1024;
-    const size_t spw = search_smem_per_warp(d, k);
+    const size_t spw = search_smem_per_warp(d, k, stats);
     while (warps > 1 && spw * warps > smem_budget) --warps;
     int per_sm;
     {   // the occupancy query costs tens of microseconds: once per (shared memory per warp, warps, stats)
@@ -626,12 +626,7 @@ static int run_search(cphnsw_b200_index* ix, Lane& L, const float* d_queries, ui
     if (ctas > need) ctas = need;
 
     auto layout = [&](uint32_t cap, SearchArgs& a) {
-        const uint32_t words = (uint32_t)((d.n + 31) / 32);
-        uint32_t chunk = 32, shift = 10;         // 32 chunks (one dirty bit each in a lane register),
-        while (chunk * 32 < words) { chunk <<= 1; ++shift; }   // power-of-two sized so id -> chunk is a shift
-        a.chunk_words = chunk;
-        a.chunk_shift = shift;
-        a.bitmap_words = chunk * 32;
+        a.bitmap_words = (uint32_t)(((d.n + 31) / 32 + 31) & ~(uint64_t)31);   // one bit per vertex, whole 128-byte lines per slot
         size_t off = 0;
         a.heap_off = off; off += ((size_t)(cap + 2) * 16 + 127) & ~(size_t)127;
         a.nn_off = off; if (k > 128) off += ((size_t)k * 8 + 127) & ~(size_t)127;

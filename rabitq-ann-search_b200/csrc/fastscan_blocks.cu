@@ -31,6 +31,12 @@ __device__ __forceinline__ void fs_mbar_init_fence() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// (Tried and not kept: warps PULLING blocks from a per-CTA shared-memory counter, one 32-warp CTA per SM, instead of a fixed
+// stride per warp.  With the fixed stride ncu shows 23 of 32 warps active on average, every SM alike -- the schedulers'
+// priorities let some warps finish early -- and the pull does keep all 32 busy to the end (warps active 36.6 % -> 49.7 %), but
+// the issue rate does not follow (70.8 % -> 68.4 %) and the stream is 9 % slower on the same box: with the ALU pipe at 66 %,
+// the XU pipe at 55 % and issue at 71 % the kernel sits on three nearly equal limits at once, and extra resident warps add
+// contention, not throughput.  Staggering the warps' start by fractions of a block's time changes nothing either.)
 // (Tried and not kept: two bulk copies per block that skip the 128 bytes of neighbour ids the estimator never reads -- 21
 // lines of traffic instead of 22.  The second copy costs more than the line saves: 0.642 of the HBM peak against 0.668.)
 __device__ __forceinline__ void fs_issue(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {

@@ -60,15 +60,14 @@ struct SearchArgs {
     size_t heap_off, nn_off;   // inside a slot
     uint32_t beam_capacity;    // frontier entries per slot
     uint32_t* bitmaps;         // per-slot "estimated" bitmaps: all-zero between queries
-    uint32_t bitmap_words, chunk_words;  // 32 chunks of chunk_words (a power of two) words each
-    uint32_t chunk_shift;                // log2(32 * chunk_words): vertex id -> chunk
+    uint32_t bitmap_words;     // words per slot (a multiple of 32), one bit per vertex
     uint32_t* counters;        // [0] work counter, [1] number of overflowed queries
     uint32_t* overflow_list;   // queries whose frontier overflowed (to be re-run)
     Stats* stats;              // may be NULL
     uint32_t* entry_out;       // descent-only mode: layer-0 entry point per query (else NULL)
     uint32_t warp_smem;        // bytes of shared memory per warp (filled in by launch_search)
 };
-size_t search_smem_per_warp(const DevIndex& ix, uint32_t k);
+size_t search_smem_per_warp(const DevIndex& ix, uint32_t k, bool stats);
 int search_max_ctas_per_sm(const DevIndex& ix, uint32_t k, int warps_per_cta, bool stats);
 cudaError_t launch_search(const DevIndex& ix, const SearchArgs& a, int ctas, int warps_per_cta, bool stats,
                           cudaStream_t stream);

@@ -49,13 +49,16 @@ __host__ __device__ inline uint32_t nn_smem_entries(uint32_t k) { return k <= kN
 
 // bytes of a block that an expansion reads (codes + aux + count), rounded for the bulk copy
 __host__ __device__ inline uint32_t block_copy_bytes(uint32_t aux_off) { return (aux_off + 644u + 15u) & ~15u; }
-__host__ __device__ inline uint32_t stage_raw_off(uint32_t aux_off) { return (block_copy_bytes(aux_off) + 127u) & ~127u; }
+// (16-byte granularity everywhere: what the bulk copies and the 128-bit reads need.  Every byte not spent here is L1 for the
+// frontier arena -- the carve-out comes in steps, see launch_search.)
+__host__ __device__ inline uint32_t stage_raw_off(uint32_t aux_off) { return block_copy_bytes(aux_off); }
 
-__host__ __device__ inline size_t smem_per_warp(uint32_t D, uint32_t B, uint32_t k) {
+// nnr: the result list lives in registers (the NNR instantiations), not in shared memory
+__host__ __device__ inline size_t smem_per_warp(uint32_t D, uint32_t B, uint32_t k, bool nnr) {
     const uint32_t T = D / 8, nch = (D > 128 ? D : 128) / 128, aux_off = B * nch * 512;
     size_t s = (size_t)stage_raw_off(aux_off) + (size_t)D * 4 + 16 + 64;   // staged block + raw vector + mbarrier + WarpState
-    s += (size_t)8 * (T + 4) * 4 + (size_t)nch * 64 + (size_t)(kHC + 1) * 16 + (size_t)nn_smem_entries(k) * 8;
-    return (s + 127) & ~(size_t)127;
+    s += (size_t)8 * (T + 4) * 4 + (size_t)nch * 64 + (size_t)(kHC + 1) * 16 + (nnr ? 0 : (size_t)nn_smem_entries(k) * 8);
+    return (s + 15) & ~(size_t)15;
 }
 
 struct WarpCtx {
@@ -72,7 +75,7 @@ struct WarpCtx {
     uint32_t lane;
     uint32_t D, T;    // padded dimension and D/8 (compile-time constants in the D = 128 instantiation)
     struct WarpState* ws;
-    const uint2* walk;  // per-lane constants of the frontier walk (shared by the CTA), see init_walk_table
+    const uint4* walk;  // per-lane constants of the frontier walk (shared by the CTA), see init_walk_table
 };
 
 // Per-query state that is touched rarely or only by uniform reads: kept in shared memory, not in
@@ -80,11 +83,12 @@ struct WarpCtx {
 struct WarpState {
     double ratio_sum, ratio_sq_sum;   // gamma_q adaptation (search/rabitq_search.hpp:255-267)
     float A, Bc, C, qn;               // estimator coefficients of the query, |q|^2
+    uint4 last;                       // the frontier's last entry {key, payload x, payload y, valid}, when known without reading it
+                                      // back: one 16-byte record, written by the push and read by the pop in one access each
     float gamma_q;
     uint32_t ratio_count;
-    float lk;                         // the frontier's last entry, when known without reading it back
-    uint32_t lp_x, lp_y;
-    uint32_t last_valid;
+    float slack;                      // dot_slack of the next non-empty expansion (:141-145)
+    uint32_t pad_;
 };
 static_assert(sizeof(WarpState) <= 64, "WarpState must fit its shared-memory slot");
 
@@ -102,8 +106,8 @@ __device__ __forceinline__ void eset(const WarpCtx& w, uint32_t i, float key, ui
 
 // Lane L < 31 owns sibling pair L of the 5-level subtree under the hole (pair L = the children of subtree
 // node L).  walk[L] = {mask of the pairs above pair L on the way to the subtree root, which child (bit = 1:
-// right) each of them must prefer for the walk to reach pair L}.
-__device__ __forceinline__ void init_walk_table(uint2* tab, uint32_t L) {
+// right) each of them must prefer for the walk to reach pair L, levels below the hole minus one, index of the pair in its level}.
+__device__ __forceinline__ void init_walk_table(uint4* tab, uint32_t L) {
     uint32_t m = 0, need = 0, a = L;
     while (a > 0 && L < 31) {
         const uint32_t p = (a - 1) >> 1, r = (a - 1) & 1u;   // pair a hangs under child r of pair p
@@ -111,7 +115,8 @@ __device__ __forceinline__ void init_walk_table(uint2* tab, uint32_t L) {
         need |= r << p;
         a = p;
     }
-    tab[L] = make_uint2(m, need);
+    const uint32_t dlev = 32u - __clz(L + 1);      // pair L sits dlev levels below the hole, jpair-th in its level
+    tab[L] = make_uint4(m, need, dlev - 1, L + 1 - (1u << (dlev - 1)));
 }
 
 // std::push_heap of (vk, vp) onto a heap of n entries, comp(a,b) = a.est > b.est.  Warp-cooperative.
@@ -126,14 +131,14 @@ __device__ __forceinline__ void heap_push(const WarpCtx& w, uint32_t n, float vk
     const unsigned up = __ballot_sync(kFull, l < depth && ka > vk);
     const uint32_t cnt = __ffs(~up) - 1;           // the new entry passes ancestors 0 .. cnt-1
     if (cnt == 0) {                                 // the common case: it stays a leaf
-        if (l == 0) { eset(w, n, vk, vp); w.ws->lk = vk; w.ws->lp_x = vp.x; w.ws->lp_y = vp.y; w.ws->last_valid = 1u; }
+        if (l == 0) { eset(w, n, vk, vp); w.ws->last = make_uint4(__float_as_uint(vk), vp.x, vp.y, 1u); }
     } else {
         uint2 pa = make_uint2(0, 0);
         if (l < cnt) { float t; eget(w, anc, t, pa); }
         __syncwarp();
         if (l < cnt) eset(w, (m >> l) - 1, ka, pa);    // ancestor l moves to where ancestor l-1 (or the leaf) was
         if (l == cnt) eset(w, (m >> cnt) - 1, vk, vp);
-        if (l == 0) { w.ws->lk = ka; w.ws->lp_x = pa.x; w.ws->lp_y = pa.y; w.ws->last_valid = 1u; }   // the parent now sits in the leaf
+        if (l == 0) w.ws->last = make_uint4(__float_as_uint(ka), pa.x, pa.y, 1u);   // the parent now sits in the leaf
     }
     __syncwarp();
 }
@@ -144,9 +149,8 @@ __device__ __forceinline__ void heap_push(const WarpCtx& w, uint32_t n, float vk
 template <bool SMEM>
 __device__ __forceinline__ uint32_t pop_step(const WarpCtx& w, uint32_t& hole, uint32_t len, float vk) {
     const uint32_t L = w.lane;
-    const uint32_t dlev = 32u - __clz(L + 1);      // pair L sits dlev levels below the hole, jpair-th in its level
-    const uint32_t jpair = L + 1 - (1u << (dlev - 1));
-    const uint32_t p = SMEM ? L : ((hole + 1) << (dlev - 1)) - 1 + jpair;
+    const uint4 wk = w.walk[L];
+    const uint32_t p = SMEM ? L : ((hole + 1) << wk.z) - 1 + wk.w;
     const uint32_t left = 2 * p + 1;
     const bool hl = L < 31 && left < len, hr = L < 31 && left + 1 < len;
     // whole entries, the pair is one aligned 32-byte unit; below a hole outside shared memory every child is in the arena
@@ -159,13 +163,12 @@ __device__ __forceinline__ uint32_t pop_step(const WarpCtx& w, uint32_t& hole, u
     const bool ok = hl && (right ? kr : kl) <= vk;  // the preferred child still moves up
     const unsigned rmask = __ballot_sync(kFull, right);
     const unsigned omask = __ballot_sync(kFull, ok);
-    const uint2 wk = w.walk[L];
     const bool mv = ok && (omask & wk.x) == wk.x && (rmask & wk.x) == wk.y;
     const unsigned M = __ballot_sync(kFull, mv);   // the pairs on the walk: one per level, top down
     const uint32_t src = left + (right ? 1u : 0u);
     __syncwarp();
     if (mv) {
-        const uint4 e = right ? er : el;
+        const uint4 e = make_uint4(right ? er.x : el.x, right ? er.y : el.y, right ? er.z : el.z, 0u);   // (.w is never set)
         if (SMEM) w.hs[p + 1] = e; else *eptr(w, p) = e;
     }
     if (M) hole = __shfl_sync(kFull, src, 31 - __clz(M));
@@ -174,14 +177,15 @@ __device__ __forceinline__ uint32_t pop_step(const WarpCtx& w, uint32_t& hole, u
 
 // std::pop_heap + pop_back on a heap of n >= 1 entries.  Warp-cooperative.
 __device__ __forceinline__ void heap_pop(const WarpCtx& w, uint32_t n) {
-    if (n <= 1) { w.ws->last_valid = 0u; return; }
+    if (n <= 1) { w.ws->last.w = 0u; return; }
     const uint32_t len = n - 1;                    // entries 0 .. len-1 remain, the hole starts at the root
     float vk;
     uint2 vp;
-    if (w.ws->last_valid) { vk = w.ws->lk; vp = make_uint2(w.ws->lp_x, w.ws->lp_y); }   // known from the last push
+    const uint4 last = w.ws->last;
+    if (last.w) { vk = __uint_as_float(last.x); vp = make_uint2(last.y, last.z); }   // known from the last push
     else eget(w, len, vk, vp);
     __syncwarp();
-    w.ws->last_valid = 0u;
+    w.ws->last.w = 0u;
     uint32_t hole = 0;
     uint32_t moved = pop_step<true>(w, hole, len, vk);
     while (moved == 5) {
@@ -207,11 +211,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 // The records an expansion reads (3 KB at a random place of a multi-GB index) are never read again by this query and
 // hardly ever by another before L2 has turned over: they are fetched with an evict-first policy, which leaves L2 to the
 // data that IS re-read -- the "estimated" bitmaps (32 atomics per expansion) and the frontier arenas.
-__device__ __forceinline__ uint64_t l2_evict_first_policy() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
+// (The policy word is what `createpolicy.fractional.L2::evict_first.b64 p, 1.0` returns on sm_100a -- ptxas folds that
+// instruction into seven uniform-datapath instructions per use; as a literal it is an operand.)
+__device__ __forceinline__ uint64_t l2_evict_first_policy() { return 0x12F0000000000000ull; }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
@@ -367,6 +369,12 @@ __device__ __forceinline__ uint32_t greedy_descent(const DevIndex& ix, const War
 // They remove the ~60 instructions per expansion that re-derive lane / warp / base from the thread id -- the kernel lives
 // at the 64-register cap -- but run slower: 788 instead of 820 instructions per expansion, 66 % instead of 71 % issue
 // utilisation, 3 % fewer QPS.  The kernel is bound by the latency of its dependent chain, not by issue slots.)
+// (Tried and not kept, on one box against the same build without them, 250k x 128 x 4-bit, 541 k QPS: an L1 prefetch of the
+// ancestors of the leaf the expansion's push will write, issued right after the pop with no register held -- the push's wait
+// for those keys is the kernel's largest long-scoreboard stall, 7.4 % of warp time -- 530 k; plain popcounts instead of the
+// carry-save compression, 12 issue slots and 33 ALU-pipe instructions fewer per expansion for 21 more POPC: 518 k; a larger L1
+// (shared-memory carve-out 164 KB instead of 196 KB, which the trimmed per-warp footprint allows at 30 or 28 warps per SM):
+// 540 k / 538 k.  The kernel sits on the issue, ALU and XU limits at once; none of them can be traded for another.)
 template <int B, bool STATS, int DT, bool NNR>
 __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const SearchArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -382,7 +390,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
     WarpCtx w;
     w.lane = lane;
     w.D = D; w.T = T;
-    CPB_BLOCK_SHARED uint2 walk_tab[32];
+    CPB_BLOCK_SHARED uint4 walk_tab[32];
     if (warp == 0) init_walk_table(walk_tab, lane);
     w.walk = walk_tab;
     __syncthreads();
@@ -436,7 +444,8 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             ws->A = cf[0]; ws->Bc = cf[1]; ws->C = cf[2]; ws->qn = cf[3];
             ws->gamma_q = cal.gamma;
             ws->ratio_sum = 0.0; ws->ratio_sq_sum = 0.0; ws->ratio_count = 0u;
-            ws->last_valid = 0u;
+            ws->last = make_uint4(0u, 0u, 0u, 0u);
+            ws->slack = cal.slack[0];
         }
         __syncwarp();
         const float qn = ws->qn;
@@ -451,7 +460,6 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
         int slack_batch_count = 0;
         bool overflow = false;
         uint32_t max_beam = 0;
-        uint32_t dirty = 0;   // this lane's share of the 32 bitmap chunks it has set bits in
 
         {
             const float d0 = exact_group(ix, w, ep, true, qn);
@@ -459,7 +467,6 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             if (lane == 0) {
                 w.hs[1] = make_uint4(__float_as_uint(d0), __float_as_uint(0.0f), ep, 0u);
                 atomicOr(&w.bitmap[ep >> 5], 1u << (ep & 31));
-                dirty |= 1u << (ep >> a.chunk_shift);
             }
             heap_n = 1;
             __syncwarp();
@@ -491,7 +498,8 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             phase ^= 1u;
 
             // neighbour ids first: their "estimated" probes travel while the distances are computed
-            const uint32_t count = *reinterpret_cast<const uint32_t*>(aux + 640);
+            const uint2 count_norm = *reinterpret_cast<const uint2*>(aux + 640);   // count, and the vertex's norm_sq riding in the block
+            const uint32_t count = count_norm.x;
             const uint32_t nid = reinterpret_cast<const uint32_t*>(aux)[lane];
             const bool valid = lane < count;
             // ---- check_and_mark_estimated for all slots at once (:227); slots are distinct ids unless
@@ -501,6 +509,11 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                 const unsigned peers = __match_any_sync(kFull, valid ? nid : (kInvalid - lane));
                 leader = valid && (uint32_t)(__ffs(peers) - 1) == lane;
             }
+            // (Tried and not kept: the bitmap belongs to this warp alone, so the probe could be a plain load here and a plain store
+            // of the new bits where the result is first needed, with a __match_any_sync for the one expansion in sixty whose slots
+            // share a word.  profiles/micro/random_records.cu has L2 executing 32 scattered atomics per record at about half the
+            // rate of 32 loads plus stores -- but in the kernel the loads fetch two sectors per miss where the atomics fetch one
+            // (DRAM reads per expansion 2 635 -> 2 994 bytes at 250k) and the time follows the DRAM bytes: 546 k -> 474 k QPS.)
             uint32_t old = 0xFFFFFFFFu;
             if (leader) old = atomicOr(&w.bitmap[nid >> 5], 1u << (nid & 31));
 
@@ -512,7 +525,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             {
                 const float dot = group_chain<false, true>(reinterpret_cast<const float*>(stage + raw_off) + (size_t)(lane & 7u) * T,
                                                            w.qrow, T, true);
-                exact_dist = exact_from_dot(ws->qn, *reinterpret_cast<const float*>(aux + 644), dot);   // norm_sq rides in the block
+                exact_dist = exact_from_dot(ws->qn, __uint_as_float(count_norm.y), dot);
             }
             if (NNR) nn_push_reg(nnr_d, nnr_i, nnr_worst, nn_m, k, lane, cur, exact_dist);
             else nn_push(w, nn_m, k, cur, exact_dist);
@@ -522,11 +535,14 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             QParams qp;
             qp.A = ws->A; qp.Bc = ws->Bc; qp.C = ws->C;
             qp.a = cal.affine_a; qp.b = cal.affine_b; qp.floor_ = cal.ip_qo_floor;
-            {   // :141-145: the slack level of this expansion (level 0 applies until the first non-empty block)
-                int li = slack_batch_count - (count > 0 ? 0 : 1);
-                li = li < 0 ? 0 : (li < cal.num_slack - 1 ? li : cal.num_slack - 1);
-                qp.slack = cal.num_slack > 0 ? cal.slack[li] : cal.slack[0];
-                if (cal.num_slack > 0 && count > 0) ++slack_batch_count;
+            // :141-145: the slack level of this expansion = min(non-empty expansions so far, num_slack - 1); an empty block reads
+            // no slack at all.  Kept in shared memory and advanced while it still changes, not looked up per expansion.
+            qp.slack = ws->slack;
+            if (count > 0 && slack_batch_count < cal.num_slack - 1) {
+                ++slack_batch_count;
+                __syncwarp();
+                if (lane == 0) ws->slack = cal.slack[slack_batch_count];
+                __syncwarp();
             }
 
             // ---- FastScan over the 32-code block + epilogue (:150-207); lane = neighbour slot -----
@@ -547,7 +563,6 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             }
 
             const bool isnew = leader && !(old & (1u << (nid & 31)));
-            if (isnew) dirty |= 1u << (nid >> a.chunk_shift);
             unsigned rem = __ballot_sync(kFull, isnew);
             if (STATS) st.estimated += __popc(rem);
 
@@ -684,15 +699,13 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
         }
         if (STATS && (unsigned long long)max_beam > st.max_beam) st.max_beam = max_beam;
 
-        // ---- clear the touched chunks of the estimated bitmap (32 chunks; lanes OR their shares) ----------
+        // ---- clear the estimated bitmap.  (Round 1 tracked which of 32 chunks had been touched and cleared only those: two
+        //      instructions and a register per expansion, and after a few hundred marks of random ids every chunk is touched --
+        //      a query marks tens of thousands.  The clear is 1 % of the bytes a query reads.) -----------------------------------
         __syncwarp();
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) dirty |= __shfl_xor_sync(kFull, dirty, o);
-        while (dirty) {
-            const uint32_t ch = __ffs(dirty) - 1;
-            dirty &= dirty - 1;
-            uint4* p = reinterpret_cast<uint4*>(w.bitmap + (size_t)ch * a.chunk_words);
-            for (uint32_t i = lane; i < a.chunk_words / 4; i += 32) p[i] = make_uint4(0, 0, 0, 0);
+        {
+            uint4* p = reinterpret_cast<uint4*>(w.bitmap);
+            for (uint32_t i = lane; i < a.bitmap_words / 4; i += 32) p[i] = make_uint4(0, 0, 0, 0);
         }
         __syncwarp();
     }
@@ -712,7 +725,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
     }
 }
 
-size_t search_smem_per_warp(const DevIndex& ix, uint32_t k) { return smem_per_warp(ix.D, ix.B, k); }
+size_t search_smem_per_warp(const DevIndex& ix, uint32_t k, bool stats) { return smem_per_warp(ix.D, ix.B, k, !stats && k <= 32); }
 
 #ifndef CPB_HOST_EMULATION   // tests/native/ compiles the kernels of this file for the host
 typedef void (*SearchKernel)(const DevIndex, const SearchArgs);
@@ -733,7 +746,7 @@ static SearchKernel pick_kernel(const DevIndex& ix, bool stats, uint32_t k) {
 }
 
 int search_max_ctas_per_sm(const DevIndex& ix, uint32_t k, int warps_per_cta, bool stats) {
-    const size_t smem = search_smem_per_warp(ix, k) * warps_per_cta;
+    const size_t smem = search_smem_per_warp(ix, k, stats) * warps_per_cta;
     SearchKernel kern = pick_kernel(ix, stats, k);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
@@ -749,12 +762,12 @@ int search_max_ctas_per_sm(const DevIndex& ix, uint32_t k, int warps_per_cta, bo
 
 cudaError_t launch_search(const DevIndex& ix, const SearchArgs& a, int ctas, int warps_per_cta, bool stats,
                           cudaStream_t stream) {
-    const size_t smem = search_smem_per_warp(ix, a.k) * warps_per_cta;
+    const size_t smem = search_smem_per_warp(ix, a.k, stats) * warps_per_cta;
     SearchKernel kern = pick_kernel(ix, stats, a.k);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     SearchArgs b = a;
-    b.warp_smem = (uint32_t)search_smem_per_warp(ix, a.k);
+    b.warp_smem = (uint32_t)search_smem_per_warp(ix, a.k, stats);
     kern<<<ctas, warps_per_cta * 32, smem, stream>>>(ix, b);
     return cudaGetLastError();
 }

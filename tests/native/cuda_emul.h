@@ -93,6 +93,10 @@ inline T __shfl_up_sync(unsigned m, T v, unsigned delta) {
 }
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
+template <typename T>
+inline T __ldcg(const T* p) { return *p; }
+template <typename T>
+inline void __stcg(T* p, T v) { *p = v; }
 
 inline unsigned __ballot_sync(unsigned, int pred) {
     cuda_emul::Warp* w = cuda_emul::t_warp;

@@ -61,19 +61,16 @@ extern "C" int emul_search(uint32_t dim, uint32_t bits, const uint8_t* records, 
 
     // run_search's argument layout (capi.cu)
     const uint32_t k = std::max<uint32_t>(k_user, 1);
-    while (warps > 1 && search_smem_per_warp(ix, k) * warps > sizeof(smem_raw)) --warps;
-    const size_t smem = search_smem_per_warp(ix, k) * warps;
+    while (warps > 1 && search_smem_per_warp(ix, k, stats_out != nullptr) * warps > sizeof(smem_raw)) --warps;
+    const size_t smem = search_smem_per_warp(ix, k, stats_out != nullptr) * warps;
     if (smem > sizeof(smem_raw)) return 2;
     const int need = (int)((nq + warps - 1) / warps);
     if (ctas > need) ctas = need;
     SearchArgs a{};
-    a.warp_smem = (uint32_t)search_smem_per_warp(ix, k);
+    a.warp_smem = (uint32_t)search_smem_per_warp(ix, k, stats_out != nullptr);
     a.nq = nq; a.query_list = nullptr; a.k = k; a.kout = k_user; a.ids = ids; a.dists = dists;
     a.qT = qT; a.uplanes = uplanes; a.coeffs = coeffs; a.entry_out = nullptr;
-    const uint32_t words = (uint32_t)((n + 31) / 32);
-    uint32_t chunk = 32, shift = 10;
-    while (chunk * 32 < words) { chunk <<= 1; ++shift; }
-    a.chunk_words = chunk; a.chunk_shift = shift; a.bitmap_words = chunk * 32;
+    a.bitmap_words = (uint32_t)(((n + 31) / 32 + 31) & ~(uint64_t)31);
     const uint32_t cap = beam_capacity ? beam_capacity : (uint32_t)n + 1;
     size_t off = 0;
     a.heap_off = off; off += ((size_t)(cap + 2) * 16 + 127) & ~(size_t)127;
