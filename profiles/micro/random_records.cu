@@ -98,7 +98,10 @@ int main(int argc, char** argv) {
         {32, 1, 0, 1, 1, 4096}, {32, 1, 0, 1, 1, 512}, {32, 1, 4000, 1, 1, 4096}, {32, 1, 4000, 1, 1, 512},
         {32, 1, 0, 2, 1, 32768}, {32, 1, 0, 2, 1, 4096}, {32, 1, 0, 2, 1, 512}, {32, 1, 4000, 2, 1, 32768}, {32, 1, 4000, 2, 1, 512},
     };
+    const int only = argc > 2 ? atoi(argv[2]) : -1;   // one configuration by index (for ncu)
+    int ci = -1;
     for (const Cfg& c : cfgs) {
+        if (++ci != only && only >= 0) continue;
         Args a{};
         a.blocks = blocks; a.raw = raw; a.bitmaps = bitmaps; a.nrec = nrec; a.block_stride = block_stride; a.blk_bytes = blk; a.raw_bytes = rawb;
         a.stages = c.stages; a.think_ns = c.think; a.atomics = c.atomics; a.evict_first = c.ef; a.bitmap_words = c.bw; a.sink = sink;

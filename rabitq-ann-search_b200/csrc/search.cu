@@ -177,7 +177,7 @@ __device__ __forceinline__ uint32_t pop_step(const WarpCtx& w, uint32_t& hole, u
 
 // std::pop_heap + pop_back on a heap of n >= 1 entries.  Warp-cooperative.
 __device__ __forceinline__ void heap_pop(const WarpCtx& w, uint32_t n) {
-    if (n <= 1) { w.ws->last.w = 0u; return; }
+    if (n <= 1) { if (w.lane == 0) w.ws->last.w = 0u; return; }
     const uint32_t len = n - 1;                    // entries 0 .. len-1 remain, the hole starts at the root
     float vk;
     uint2 vp;
@@ -185,7 +185,7 @@ __device__ __forceinline__ void heap_pop(const WarpCtx& w, uint32_t n) {
     if (last.w) { vk = __uint_as_float(last.x); vp = make_uint2(last.y, last.z); }   // known from the last push
     else eget(w, len, vk, vp);
     __syncwarp();
-    w.ws->last.w = 0u;
+    if (w.lane == 0) w.ws->last.w = 0u;
     uint32_t hole = 0;
     uint32_t moved = pop_step<true>(w, hole, len, vk);
     while (moved == 5) {

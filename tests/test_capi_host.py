@@ -61,6 +61,20 @@ def test_no_gpu_means_loud_failure_not_fallback():
         cphnsw_b200.CPIndex(128, 4)
 
 
+def test_a_missing_library_is_an_import_error_not_a_fallback(tmp_path):
+    """CPHNSW_B200_LIB names another build of the native library (A/B runs of kernel variants); a path with nothing behind it
+    must fail as loudly as a missing default build."""
+    import subprocess
+    import sys
+
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from cphnsw_b200 import _capi\n"
+            "try:\n    _capi.lib()\nexcept ImportError as e:\n    print('IMPORT_ERROR', 'no CPU fallback' in str(e))\n") % str(ROOT / "rabitq-ann-search_b200")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
+                       env=dict(__import__("os").environ, CPHNSW_B200_LIB=str(tmp_path / "libnothing.so")))
+    assert "IMPORT_ERROR True" in r.stdout, (r.stdout, r.stderr[-500:])
+
+
 def test_constructor_validation_matches_the_reference_factory():
     import cphnsw_b200
 
