@@ -513,7 +513,8 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             // of the new bits where the result is first needed, with a __match_any_sync for the one expansion in sixty whose slots
             // share a word.  profiles/micro/random_records.cu has L2 executing 32 scattered atomics per record at about half the
             // rate of 32 loads plus stores -- but in the kernel the loads fetch two sectors per miss where the atomics fetch one
-            // (DRAM reads per expansion 2 635 -> 2 994 bytes at 250k) and the time follows the DRAM bytes: 546 k -> 474 k QPS.)
+            // (DRAM reads per expansion 2 635 -> 2 994 bytes at 250k) and the time follows the DRAM bytes: 546 k -> 474 k QPS, with
+            // cudaLimitMaxL2FetchGranularity at 32 bytes as without it.)
             uint32_t old = 0xFFFFFFFFu;
             if (leader) old = atomicOr(&w.bitmap[nid >> 5], 1u << (nid & 31));
 
