@@ -90,7 +90,7 @@ struct WarpState {
     float slack;                      // dot_slack of the next non-empty expansion (:141-145)
     uint32_t pad_;
 };
-static_assert(sizeof(WarpState) <= 64, "WarpState must fit its shared-memory slot");
+static_assert(sizeof(WarpState) == 64, "WarpState must fit its shared-memory slot");
 
 // Entry i wherever it lives: one generic address (the shared window or the arena), so reads and writes of entries are
 // single 16-byte accesses with no branch on the address space.
@@ -123,15 +123,17 @@ __device__ __forceinline__ void init_walk_table(uint4* tab, uint32_t L) {
 // ws->lk/lp track the entry at the last index (what the next pop re-inserts) without reading it back.
 __device__ __forceinline__ void heap_push(const WarpCtx& w, uint32_t n, float vk, uint2 vp) {
     const uint32_t m = n + 1;                      // 1-based index of the new leaf
-    const uint32_t depth = 31u - __clz(m);         // number of ancestors
     const uint32_t l = w.lane;
+    const uint32_t depth = 31u - __clz(m);         // number of ancestors
     const uint32_t anc = l < depth ? (m >> (l + 1)) - 1 : 0u;   // ancestor l (l = 0: parent)
     float ka = 0.0f;
     if (l < depth) ka = kget(w, anc);
     const unsigned up = __ballot_sync(kFull, l < depth && ka > vk);
     const uint32_t cnt = __ffs(~up) - 1;           // the new entry passes ancestors 0 .. cnt-1
     if (cnt == 0) {                                 // the common case: it stays a leaf
-        if (l == 0) { eset(w, n, vk, vp); w.ws->last = make_uint4(__float_as_uint(vk), vp.x, vp.y, 1u); }
+        if (l == 0) {
+            eset(w, n, vk, vp); w.ws->last = make_uint4(__float_as_uint(vk), vp.x, vp.y, 1u);
+        }
     } else {
         uint2 pa = make_uint2(0, 0);
         if (l < cnt) { float t; eget(w, anc, t, pa); }
@@ -316,6 +318,52 @@ __device__ __forceinline__ float exact_for_lanes(const DevIndex& ix, const WarpC
     return mine;
 }
 
+// Planes 1 .. B-1 of a FEW slots of the staged block, evaluated by the whole warp.  Lane = slot (plane_sum_one) spends the
+// same (B-1) x nch x 47 instructions whether one slot needs its other planes or all 32 do, and once the result list is full
+// few do: on the 1M x 128 benchmark index 42 % of the expansions have no new slot under the plane-0 bound, 32 % one, 15 % two,
+// 6 % three, 4.5 % more.  Here the (plane, chunk, word) items of a slot -- W = (B-1) x nch x 4 words, each worth
+// sum_t 2^t popc(word & u_t) -- are dealt to the lanes of a group (16 lanes, two slots per pass, when W <= 16; else the warp,
+// one slot per pass), summed across the group with shuffles and handed to the slot's own lane: the same integers, a
+// quarter of the instructions.  Out, in the lanes named by `slots` (others: 0): p1 = plane 1's sum and
+// rest = sum_{b >= 1} plane_b << (B-1-b), so that nbit = (plane_0 << (B-1)) + rest and msb2 = 2 plane_0 + p1.
+template <int B>
+__device__ __forceinline__ void slot_planes_by_warp(const uint8_t* stage, uint32_t nch, const uint4* uq, uint32_t lane,
+                                                    unsigned slots, uint32_t& p1, uint32_t& rest) {
+    p1 = 0; rest = 0;
+    const uint32_t per_plane = nch * 4u, W = (uint32_t)(B - 1) * per_plane;   // nch is a power of two
+    const uint32_t pshift = 31u - __clz(per_plane);
+    const bool halves = W <= 16u;
+    const uint32_t G = halves ? 16u : 32u, sub = lane & (G - 1u), grp = halves ? (lane >> 4) : 0u;
+    while (slots) {
+        const uint32_t j0 = __ffs(slots) - 1; slots &= slots - 1;
+        uint32_t j1 = 32u;
+        if (halves && slots) { j1 = __ffs(slots) - 1; slots &= slots - 1; }
+        const uint32_t j = grp ? j1 : j0;
+        uint32_t acc1 = 0, accr = 0;
+        if (j < 32u) {
+            for (uint32_t item = sub; item < W; item += G) {
+                const uint32_t b = 1u + (item >> pshift), r = item & (per_plane - 1u), c = r >> 2, wi = r & 3u;
+                const uint32_t word = reinterpret_cast<const uint32_t*>(stage)[(((size_t)b * nch + c) * 32u + j) * 4u + wi];
+                const uint32_t* u = reinterpret_cast<const uint32_t*>(uq) + (size_t)c * 4u + wi;   // uq[t * nch + c], word wi
+                const uint32_t v = __popc(word & u[0]) + 2u * __popc(word & u[(size_t)nch * 4u]) +
+                                   4u * __popc(word & u[(size_t)nch * 8u]) + 8u * __popc(word & u[(size_t)nch * 12u]);
+                accr += v << ((uint32_t)(B - 1) - b);
+                if (b == 1u) acc1 += v;
+            }
+        }
+        // sums over the group (xor shuffles up to G/2 stay inside an aligned group of G lanes)
+        for (uint32_t o = G >> 1; o > 0; o >>= 1) {
+            acc1 += __shfl_xor_sync(kFull, acc1, (int)o);
+            accr += __shfl_xor_sync(kFull, accr, (int)o);
+        }
+        // to the slots' own lanes
+        const uint32_t a1 = __shfl_sync(kFull, acc1, 16), ar = __shfl_sync(kFull, accr, 16);   // the second group's (halves)
+        const uint32_t b1 = __shfl_sync(kFull, acc1, 0), br = __shfl_sync(kFull, accr, 0);     // the first group's
+        if (lane == j0) { p1 = b1; rest = br; }
+        if (lane == j1) { p1 = a1; rest = ar; }
+    }
+}
+
 // greedy_search_layer over levels max_level..1 (api/hnsw_index.hpp:195-202, 617-638)
 template <bool STATS>
 __device__ __forceinline__ uint32_t greedy_descent(const DevIndex& ix, const WarpCtx& w, unsigned long long& ndist) {
@@ -384,6 +432,12 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
     const uint32_t block_stride = DT ? ((aux_off + 644 + 127) & ~127u) : ix.block_stride;
     const uint32_t k = a.k;
     const uint32_t nq_work = a.nq_ptr ? *a.nq_ptr : a.nq;
+    // up to how many slots slot_planes_by_warp is the cheaper way to their other planes (instruction estimates: lane per slot
+    // 47 per plane and chunk; by warp 30 + 10 per item a lane handles, per pass of one or two slots)
+    const uint32_t coop_W = (uint32_t)(B > 1 ? B - 1 : 0) * nch * 4u, coop_G = coop_W <= 16u ? 16u : 32u;
+    const uint32_t coop_pass = 30u + 10u * ((coop_W + coop_G - 1u) / coop_G);
+    const uint32_t coop_passes = (3u * (uint32_t)(B > 1 ? B - 1 : 0) * nch * 47u / 4u) / coop_pass;
+    const uint32_t coop_max = min(8u, coop_passes * (coop_W <= 16u ? 2u : 1u));
 
     // ---- carve shared memory -------------------------------------------------------------------
     uint8_t* sm = smem_raw + warp * a.warp_smem;   // smem_per_warp(D, B, k), computed by the launcher
@@ -563,34 +617,58 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                 else lower = nbit_lower<B>(qp, ps0, nop, ipqo, ipcp, pops & 0xFFFFu, lane, count, dqp, sq);
             }
 
+            // planes 1 .. B-1, the MSB-pair bound (:170-187) and the full estimate (:189-200) in one go: the estimate is wanted unless
+            // EVERY neighbour's MSB-pair bound reaches the k-th distance -- which this data never does -- so computing it before
+            // that vote wastes nothing and lets its popcounts run under the bound's division chain
+            float full_est = FLT_MAX, msb_lower = 0.0f;
+            auto rest_of_estimate = [&]() {
+                const float nop = reinterpret_cast<const float*>(aux + 128)[lane];
+                const float ipqo = reinterpret_cast<const float*>(aux + 256)[lane];
+                const float ipcp = reinterpret_cast<const float*>(aux + 384)[lane];
+                const uint32_t pops = reinterpret_cast<const uint32_t*>(aux + 512)[lane];
+                const uint32_t ps1 = plane_sum_one<true>(reinterpret_cast<const uint4*>(stage), 1, nch, lane, w.uq);
+                uint32_t nbit = (ps0 << (B - 1)) + (ps1 << (B - 2));
+#pragma unroll
+                for (int b = 2; b < B; ++b)
+                    nbit += plane_sum_one<true>(reinterpret_cast<const uint4*>(stage), b, nch, lane, w.uq) << (B - 1 - b);
+                msb_lower = convert_msb<B>(qp, 2u * ps0 + ps1, nop, ipqo, ipcp, pops & 0xFFFFu, dqp, sq);
+                full_est = nbit_est<B>(qp, nbit, nop, ipqo, ipcp, pops >> 16, lane, count, dqp);
+            };
+            const bool nbit_stage = B > 1 && count > 0 && (STATS || !warmup);
+            const float w0 = nbit_stage ? (NNR ? nnr_worst : w.nn_d[nn_m - 1]) : 0.0f;   // nn.worst_distance() (:179), the k-th distance when nn is full
+
             const bool isnew = leader && !(old & (1u << (nid & 31)));
             unsigned rem = __ballot_sync(kFull, isnew);
             if (STATS) st.estimated += __popc(rem);
 
-            if (B > 1 && count > 0 && (STATS || (!warmup && rem))) {
-                const float w0 = NNR ? nnr_worst : w.nn_d[nn_m - 1];   // nn.worst_distance() (:179), the k-th distance when nn is full
+            if (nbit_stage && (STATS || rem)) {
                 const unsigned cand = __ballot_sync(kFull, isnew && !(lower >= w0));
                 if (STATS || cand) {
-                    const float nop = reinterpret_cast<const float*>(aux + 128)[lane];
-                    const float ipqo = reinterpret_cast<const float*>(aux + 256)[lane];
-                    const float ipcp = reinterpret_cast<const float*>(aux + 384)[lane];
-                    const uint32_t pops = reinterpret_cast<const uint32_t*>(aux + 512)[lane];
-                    // planes 1 .. B-1, the MSB-pair bound and the full estimate in one go: the estimate is wanted unless EVERY
-                    // neighbour's MSB-pair bound reaches the k-th distance (:178-187) -- which this data never does -- so computing
-                    // it before that vote wastes nothing and lets its popcounts run under the bound's division chain
-                    const uint32_t ps1 = plane_sum_one<true>(reinterpret_cast<const uint4*>(stage), 1, nch, lane, w.uq);
-                    uint32_t nbit = (ps0 << (B - 1)) + (ps1 << (B - 2));
-#pragma unroll
-                    for (int b = 2; b < B; ++b)
-                        nbit += plane_sum_one<true>(reinterpret_cast<const uint4*>(stage), b, nch, lane, w.uq) << (B - 1 - b);
-                    const float msb_lower = convert_msb<B>(qp, 2u * ps0 + ps1, nop, ipqo, ipcp, pops & 0xFFFFu, dqp, sq);
-                    const float full_est = nbit_est<B>(qp, nbit, nop, ipqo, ipcp, pops >> 16, lane, count, dqp);
-                    const bool any = nn_m < k || __any_sync(kFull, valid && msb_lower < w0);   // :178-187
-                    if (any) est = full_est;
-                    else {
-                        if (STATS) ++st.msb_skipped;
-                        est = FLT_MAX;
-                        lower = msb_lower;
+                    bool done = false;
+                    if (!STATS && (uint32_t)__popc(cand) <= coop_max) {
+                        // few slots want their other planes: the warp evaluates just those (slot_planes_by_warp).  est is only
+                        // ever read for new slots under the bound (a subset of cand: the k-th distance only shrinks), and the
+                        // MSB-pair vote (:178-187) is decided as soon as ONE slot is under it -- if none of these is, the vote
+                        // needs every slot's bound and the lane-per-slot evaluation below provides it.
+                        uint32_t p1, rest;
+                        slot_planes_by_warp<B>(stage, nch, w.uq, lane, cand, p1, rest);
+                        const float nop = reinterpret_cast<const float*>(aux + 128)[lane];
+                        const float ipqo = reinterpret_cast<const float*>(aux + 256)[lane];
+                        const float ipcp = reinterpret_cast<const float*>(aux + 384)[lane];
+                        const uint32_t pops = reinterpret_cast<const uint32_t*>(aux + 512)[lane];
+                        const float ml = convert_msb<B>(qp, 2u * ps0 + p1, nop, ipqo, ipcp, pops & 0xFFFFu, dqp, sq);
+                        const float fe = nbit_est<B>(qp, (ps0 << (B - 1)) + rest, nop, ipqo, ipcp, pops >> 16, lane, count, dqp);
+                        if (__any_sync(kFull, ((cand >> lane) & 1u) && ml < w0)) { est = fe; done = true; }
+                    }
+                    if (!done) {
+                        rest_of_estimate();
+                        const bool any = nn_m < k || __any_sync(kFull, valid && msb_lower < w0);   // :178-187
+                        if (any) est = full_est;
+                        else {
+                            if (STATS) ++st.msb_skipped;
+                            est = FLT_MAX;
+                            lower = msb_lower;
+                        }
                     }
                 }
                 if (!warmup && !cand) rem = 0;   // no new slot passes :246 -- nothing in the neighbour loop can act

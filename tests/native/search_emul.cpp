@@ -128,3 +128,27 @@ extern "C" int emul_exact_l2(uint32_t dim, uint64_t n, const float* raw, const f
     cuda_emul::launch(kern, (nq + warps - 1) / warps, warps * 32, smem_raw, smem, 0);
     return 0;
 }
+
+// slot_planes_by_warp against the lane-per-slot evaluation it replaces for a few slots: one warp, a block's code planes
+// ([plane][chunk][slot] uint4) and the query's bit-planes ([t][chunk] uint4) as given.  Out, per lane: plane 1's sum and
+// sum_{b >= 1} plane_b << (B-1-b) both ways (the warp's way only in the lanes named by `slots`).
+extern "C" int emul_slot_planes(uint32_t bits, uint32_t nch, const uint8_t* planes, const uint32_t* uq, uint32_t slots,
+                                uint32_t* p1_warp, uint32_t* rest_warp, uint32_t* p1_lane, uint32_t* rest_lane) {
+    using namespace cpb;
+    if (bits != 2 && bits != 4) return 1;
+    auto kern = [&](int) {
+        const uint32_t lane = threadIdx.x & 31;
+        const uint4* u4 = reinterpret_cast<const uint4*>(uq);
+        uint32_t p1 = 0, rest = 0, q1 = 0, qr = 0;
+        if (bits == 4) slot_planes_by_warp<4>(planes, nch, u4, lane, slots, p1, rest);
+        else slot_planes_by_warp<2>(planes, nch, u4, lane, slots, p1, rest);
+        for (uint32_t b = 1; b < bits; ++b) {
+            const uint32_t s = plane_sum_one<true>(reinterpret_cast<const uint4*>(planes), b, nch, lane, u4);
+            if (b == 1) q1 = s;
+            qr += s << (bits - 1 - b);
+        }
+        p1_warp[lane] = p1; rest_warp[lane] = rest; p1_lane[lane] = q1; rest_lane[lane] = qr;
+    };
+    cuda_emul::launch(kern, 1, 32, smem_raw, 0, 0);
+    return 0;
+}

@@ -8,6 +8,8 @@ import subprocess
 import numpy as np
 import pytest
 
+import os
+
 import common
 
 NATIVE = common.ROOT / "tests" / "native"
@@ -15,7 +17,9 @@ NATIVE = common.ROOT / "tests" / "native"
 
 def _build(tmp_path_factory, name):
     out = tmp_path_factory.mktemp("emul") / f"lib{name}.so"
-    cmd = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I/usr/local/cuda/include",
+    # CPHNSW_EMUL_DEFINES: the -D flags of a kernel variant under test (build.py --variant), space separated
+    defines = [f"-D{d}" for d in os.environ.get("CPHNSW_EMUL_DEFINES", "").split()]
+    cmd = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I/usr/local/cuda/include", *defines,
            str(NATIVE / f"{name}.cpp"), "-o", str(out)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
@@ -415,3 +419,36 @@ def test_calibration_kernel_source_equals_the_restatement(k1, n4, oracle, dim, b
         assert np.array_equal(got[k], want[k]), k
     for k in ("nn_dist_sq", "dist_qp_sq", "nop", "ip_corrected", "ip_qo_denom", "true_ip"):
         assert np.array_equal(_bits(got[k]), _bits(want[k])), k
+
+
+@pytest.mark.parametrize("dim,bits,k", [(128, 4, 10), (300, 4, 10), (960, 2, 20), (200, 2, 5)])
+def test_fast_search_kernel_source_equals_the_oracle_on_fabricated_indexes(k1, k3, oracle, dim, bits, k):
+    """The non-counting instantiations (result list in registers; the other planes of the few slots that want them evaluated by
+    the whole warp, in groups of 16 lanes at D = 128 / 256 and by the warp beyond) against the C restatement: ids and distance bits."""
+    fab = common.fabricate(300, dim, bits, seed=2 * dim + bits, counts=(32, 32, 30, 17, 8, 0), degenerate=True, layers=1,
+                           gamma=1.05, gamma_max=1.8, gamma_beta=0.8, gamma_warmup=4, floor=0.35, slacks=(0.05, 0.08, 0.1))
+    q = np.random.default_rng(5).standard_normal((6, dim)).astype(np.float32)
+    ids, dists, over, _ = _search(k1, k3, oracle, dim, bits, fab.search_data, fab.search_data.shape[1], fab.nb_off, fab.raw, fab.norm_sq,
+                                  fab.calibration, fab.max_level, fab.entry_point, fab.layers, q, k)
+    assert over == 0
+    oid, od, _ = oracle.search_batch(oracle.index_view(fab), q, k)
+    gi, gd = common.sorted_rows(ids, dists)
+    wi, wd = common.sorted_rows(oid, od)
+    assert np.array_equal(gi, wi) and np.array_equal(_bits(gd), _bits(wd))
+
+
+@pytest.mark.parametrize("bits,nch", [(4, 1), (2, 1), (2, 2), (4, 2), (2, 8), (4, 8), (4, 16)])
+def test_slot_planes_by_warp_equals_the_lane_per_slot_sums(k3, bits, nch):
+    """The warp-cooperative evaluation of a few slots' other planes (search.cu: slot_planes_by_warp; 16-lane groups up to 16
+    words per slot, the whole warp beyond) gives the integers plane_sum_one gives, for every choice of slots."""
+    rng = np.random.default_rng(100 * bits + nch)
+    planes = rng.integers(0, 256, bits * nch * 32 * 16, dtype=np.uint8)
+    uq = rng.integers(0, 2**32, 4 * nch * 4, dtype=np.uint32)
+    for slots in (0x1, 0x80000000, 0x00010002, 0x80000001, 0x00F00000, 0x12345678, 0xFFFFFFFF, 0x0000A005, 0x40000000):
+        out = [np.zeros(32, np.uint32) for _ in range(4)]
+        rc = k3.emul_slot_planes(C.c_uint32(bits), C.c_uint32(nch), _p(planes, C.c_uint8), _p(uq, C.c_uint32), C.c_uint32(slots),
+                                 *[_p(o, C.c_uint32) for o in out])
+        assert rc == 0
+        sel = np.array([(slots >> l) & 1 for l in range(32)], bool)
+        assert np.array_equal(out[0][sel], out[2][sel]) and np.array_equal(out[1][sel], out[3][sel]), hex(slots)
+        assert not out[0][~sel].any() and not out[1][~sel].any()
