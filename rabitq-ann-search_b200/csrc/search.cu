@@ -53,11 +53,10 @@ __host__ __device__ inline uint32_t block_copy_bytes(uint32_t aux_off) { return 
 // frontier arena -- the carve-out comes in steps, see launch_search.)
 __host__ __device__ inline uint32_t stage_raw_off(uint32_t aux_off) { return block_copy_bytes(aux_off); }
 
-// nnr: the result list lives in registers (the NNR instantiations), not in shared memory
-__host__ __device__ inline size_t smem_per_warp(uint32_t D, uint32_t B, uint32_t k, bool nnr) {
+__host__ __device__ inline size_t smem_per_warp(uint32_t D, uint32_t B, uint32_t k) {
     const uint32_t T = D / 8, nch = (D > 128 ? D : 128) / 128, aux_off = B * nch * 512;
     size_t s = (size_t)stage_raw_off(aux_off) + (size_t)D * 4 + 16 + 64;   // staged block + raw vector + mbarrier + WarpState
-    s += (size_t)8 * (T + 4) * 4 + (size_t)nch * 64 + (size_t)(kHC + 1) * 16 + (nnr ? 0 : (size_t)nn_smem_entries(k) * 8);
+    s += (size_t)8 * (T + 4) * 4 + (size_t)nch * 64 + (size_t)(kHC + 1) * 16 + (size_t)nn_smem_entries(k) * 8;
     return (s + 15) & ~(size_t)15;
 }
 
@@ -245,45 +244,57 @@ inline void mbar_wait(uint64_t* bar, uint32_t phase) {
 inline void prefetch_l2(const void*) {}
 #endif
 
-// BoundedMaxHeap::push (search/rabitq_search.hpp:26-35) on an ascending list: accept while not
-// full, else replace the worst iff strictly closer.  No de-duplication.  Equal
-// distances keep arrival order.  Warp-cooperative; all arguments warp-uniform.
-__device__ __forceinline__ void nn_push(const WarpCtx& w, uint32_t& m, uint32_t k, uint32_t id, float dist) {
-    if (m == k && !(dist < w.nn_d[k - 1])) return;
-    const uint32_t newm = m < k ? m + 1 : k;
-    for (int c = (int)((newm - 1) >> 5); c >= 0; --c) {
-        const uint32_t i = (uint32_t)c * 32 + w.lane;
-        float d0 = 0.0f, dm = 0.0f;
-        uint32_t im = 0;
-        const bool have0 = i < m, havem = i >= 1 && (i - 1) < m;
-        if (have0) d0 = w.nn_d[i];
-        if (havem) { dm = w.nn_d[i - 1]; im = w.nn_i[i - 1]; }
-        const bool le0 = have0 && d0 <= dist;              // old[i] stays in place
-        const bool lem = i == 0 || (havem && dm <= dist);  // old[i-1] stays in place
-        __syncwarp();
-        if (i < newm && !le0) {
-            if (lem) { w.nn_d[i] = dist; w.nn_i[i] = id; }
-            else { w.nn_d[i] = dm; w.nn_i[i] = im; }
-        }
-        __syncwarp();
-        if (__all_sync(kFull, le0 || i >= newm)) break;         // nothing below this chunk moves
-        if (__any_sync(kFull, i < newm && !le0 && lem)) break;  // insertion point passed
+// BoundedMaxHeap (search/rabitq_search.hpp:17-49), node for node: the result set is libstdc++'s binary max-heap over
+// (distance, id) entries compared by distance alone, filled with std::push_heap, and once full an entry strictly closer than
+// front() replaces it through std::pop_heap / back() = v / std::push_heap.  No de-duplication.  WHICH of two entries
+// of equal distance sits at the front -- and is the one evicted -- is a matter of the heap's layout, and with distinct ids of
+// bit-equal distance (one query in ten thousand on the 250k benchmark index) it decides which id is in the answer; an
+// ascending list that evicts its last entry, as rounds 1 and 2 had it, returns the other one.  So the heap is kept as the
+// reference keeps it, by lane 0 alone: pushes that are accepted are rare once the set is full (the test against front() is
+// warp-uniform and comes first), and the algorithms are sequential by nature.  d / id: shared memory up to k = 128, else
+// the slot's arena.
+__device__ __forceinline__ void nnh_push_heap(float* d, uint32_t* id, uint32_t hole, float vd, uint32_t vi) {   // std::__push_heap, top = 0
+    while (hole > 0) {
+        const uint32_t parent = (hole - 1) >> 1;
+        if (!(d[parent] < vd)) break;
+        d[hole] = d[parent]; id[hole] = id[parent];
+        hole = parent;
     }
-    m = newm;
+    d[hole] = vd; id[hole] = vi;
 }
-
-// The same list with entry j in lane j's registers (k <= 32): one ballot finds the insertion point, one shuffle moves
-// the tail up.  `worst` = distance of the last entry (warp-uniform), i.e. nn.worst_distance().
-__device__ __forceinline__ void nn_push_reg(float& d, uint32_t& id, float& worst, uint32_t& m, uint32_t k, uint32_t lane,
-                                            uint32_t nid, float dist) {
-    if (m == k && !(dist < worst)) return;
-    const uint32_t pos = __popc(__ballot_sync(kFull, lane < m && d <= dist));   // the entries that stay are a prefix
-    const float du = __shfl_up_sync(kFull, d, 1);
-    const uint32_t iu = __shfl_up_sync(kFull, id, 1);
-    if (lane > pos) { d = du; id = iu; }
-    else if (lane == pos) { d = dist; id = nid; }
-    m = m < k ? m + 1 : k;
-    worst = __shfl_sync(kFull, d, m - 1);
+__device__ __forceinline__ void nnh_pop_heap(float* d, uint32_t* id, uint32_t len) {   // std::pop_heap(first, first + len)
+    if (len <= 1) return;
+    const uint32_t n = len - 1;                    // __adjust_heap(first, 0, n, value = the former last entry)
+    const float vd = d[n]; const uint32_t vi = id[n];
+    d[n] = d[0]; id[n] = id[0];
+    uint32_t hole = 0, child = 0;
+    while ((int)child < ((int)n - 1) / 2) {
+        child = 2 * (child + 1);
+        if (d[child] < d[child - 1]) --child;      // the larger child; the right one when equal
+        d[hole] = d[child]; id[hole] = id[child];
+        hole = child;
+    }
+    if ((n & 1u) == 0 && (int)child == ((int)n - 2) / 2) {
+        child = 2 * (child + 1);
+        d[hole] = d[child - 1]; id[hole] = id[child - 1];
+        hole = child - 1;
+    }
+    nnh_push_heap(d, id, hole, vd, vi);
+}
+// BoundedMaxHeap::push.  m = entries held, front = front().distance (FLT_MAX while empty) -- both warp-uniform registers.
+__device__ __forceinline__ void nn_push(const WarpCtx& w, uint32_t& m, uint32_t k, uint32_t id, float dist, float& front) {
+    if (m == k && !(dist < front)) return;         // :31
+    __syncwarp();
+    if (w.lane == 0) {
+        if (m < k) nnh_push_heap(w.nn_d, w.nn_i, m, dist, id);
+        else {
+            nnh_pop_heap(w.nn_d, w.nn_i, k);
+            nnh_push_heap(w.nn_d, w.nn_i, k - 1, dist, id);
+        }
+    }
+    if (m < k) ++m;
+    __syncwarp();
+    front = w.nn_d[0];
 }
 
 __device__ __forceinline__ float exact_group(const DevIndex& ix, const WarpCtx& w, uint32_t id, bool active,
@@ -405,7 +416,6 @@ __device__ __forceinline__ uint32_t greedy_descent(const DevIndex& ix, const War
 
 // DT = 128: the padded dimension is the compile-time constant 128 (SIFT/Deep shapes: one 128-dim chunk per
 // code plane, 16-step distance chains, constant shared-memory offsets); DT = 0: any supported dimension.
-// NNR: the result list lives in registers (lane j = entry j; k <= 32) instead of shared memory.
 // (Tried and not kept, again: an L2 prefetch of the block most likely to be expanded next -- the smaller child of the
 // frontier's root -- one expansion ahead: 3 % slower with it on, and its mere presence behind a flag cost 9 %, the register
 // allocation of this kernel being what it is.)
@@ -423,7 +433,7 @@ __device__ __forceinline__ uint32_t greedy_descent(const DevIndex& ix, const War
 // carry-save compression, 12 issue slots and 33 ALU-pipe instructions fewer per expansion for 21 more POPC: 518 k; a larger L1
 // (shared-memory carve-out 164 KB instead of 196 KB, which the trimmed per-warp footprint allows at 30 or 28 warps per SM):
 // 540 k / 538 k.  The kernel sits on the issue, ALU and XU limits at once; none of them can be traded for another.)
-template <int B, bool STATS, int DT, bool NNR>
+template <int B, bool STATS, int DT>
 __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const SearchArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -462,9 +472,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
     uint8_t* arena = a.scratch + (size_t)slot * a.slot_stride;
     w.hg = reinterpret_cast<uint4*>(arena + a.heap_off);
     w.bitmap = a.bitmaps + (size_t)slot * a.bitmap_words;
-    if (NNR) {
-        w.nn_d = nullptr; w.nn_i = nullptr;
-    } else if (k <= kNNSmem) {
+    if (k <= kNNSmem) {
         w.nn_d = reinterpret_cast<float*>(sm);
         w.nn_i = reinterpret_cast<uint32_t*>(sm + (size_t)nn_smem_entries(k) * 4);
     } else {
@@ -509,8 +517,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
 
         // ---- layer-0 search state (search/rabitq_search.hpp:77-97) ----------------------------
         uint32_t heap_n = 0, nn_m = 0;
-        float nnr_d = 0.0f, nnr_worst = FLT_MAX;   // NNR: this lane's entry, and the last entry's distance
-        uint32_t nnr_i = 0;
+        float nn_front = FLT_MAX;   // front().distance of the result heap: the largest distance held (the k-th, once it is full)
         int slack_batch_count = 0;
         bool overflow = false;
         uint32_t max_beam = 0;
@@ -532,7 +539,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
             const float cur_est = __uint_as_float(top.x), cur_lower = __uint_as_float(top.y);
             const uint32_t cur = top.z;
             const bool full0 = nn_m >= k;
-            float worst = full0 ? (NNR ? nnr_worst : w.nn_d[k - 1]) : FLT_MAX;
+            float worst = full0 ? nn_front : FLT_MAX;
             const bool terminate = full0 && cur_est >= __fmul_rn(ws->gamma_q, worst);   // :120
             const bool lbskip = full0 && cur_lower > worst;                          // :122
             const bool expand = !terminate && !lbskip;
@@ -582,8 +589,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                                                            w.qrow, T, true);
                 exact_dist = exact_from_dot(ws->qn, __uint_as_float(count_norm.y), dot);
             }
-            if (NNR) nn_push_reg(nnr_d, nnr_i, nnr_worst, nn_m, k, lane, cur, exact_dist);
-            else nn_push(w, nn_m, k, cur, exact_dist);
+            nn_push(w, nn_m, k, cur, exact_dist, nn_front);
             if (STATS) { ++st.exact_calls; ++st.nn_pushes; ++st.expansions; }
             // (count == 0 -> `continue` in the reference: no lane is valid, nothing below acts)
             const float dqp = exact_dist;
@@ -635,7 +641,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                 full_est = nbit_est<B>(qp, nbit, nop, ipqo, ipcp, pops >> 16, lane, count, dqp);
             };
             const bool nbit_stage = B > 1 && count > 0 && (STATS || !warmup);
-            const float w0 = nbit_stage ? (NNR ? nnr_worst : w.nn_d[nn_m - 1]) : 0.0f;   // nn.worst_distance() (:179), the k-th distance when nn is full
+            const float w0 = nn_front;   // nn.worst_distance() (:179), the k-th distance when nn is full
 
             const bool isnew = leader && !(old & (1u << (nid & 31)));
             unsigned rem = __ballot_sync(kFull, isnew);
@@ -683,9 +689,8 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                     rem &= rem - 1;
                     const float ex = __shfl_sync(kFull, myex, j);
                     const uint32_t id = __shfl_sync(kFull, nid, j);
-                    const float dabs = nn_m >= k ? __fmul_rn(ws->gamma_q, NNR ? nnr_worst : w.nn_d[k - 1]) : FLT_MAX;   // :230-232
-                    if (NNR) nn_push_reg(nnr_d, nnr_i, nnr_worst, nn_m, k, lane, id, ex);
-                    else nn_push(w, nn_m, k, id, ex);
+                    const float dabs = nn_m >= k ? __fmul_rn(ws->gamma_q, nn_front) : FLT_MAX;   // :230-232
+                    nn_push(w, nn_m, k, id, ex, nn_front);
                     if (STATS) ++st.nn_pushes;
                     if (ex < dabs) {
                         if (heap_n >= a.beam_capacity) { overflow = true; break; }
@@ -695,7 +700,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                     }
                 }
             } else if (rem) {
-                worst = NNR ? nnr_worst : w.nn_d[k - 1];
+                worst = nn_front;
                 // distances that may be needed: every new slot that passes both tests under the
                 // current k-th distance (the k-th distance only shrinks, so this is a superset)
                 const unsigned spec = __ballot_sync(kFull, isnew && !(lower >= worst) && est < worst);
@@ -725,8 +730,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                         const float ex = __shfl_sync(kFull, myex, first), ed = __shfl_sync(kFull, est, first);
                         const float lo = __shfl_sync(kFull, lower, first);
                         const uint32_t id = __shfl_sync(kFull, nid, first);
-                        if (NNR) nn_push_reg(nnr_d, nnr_i, nnr_worst, nn_m, k, lane, id, ex);
-                        else nn_push(w, nn_m, k, id, ex);
+                        nn_push(w, nn_m, k, id, ex, nn_front);
                         if (STATS) ++st.nn_pushes;
                         if (ex < dabs) {
                             if (heap_n >= a.beam_capacity) { overflow = true; break; }
@@ -751,7 +755,7 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
                             if (lane == 0) { ws->ratio_sum = rs; ws->ratio_sq_sum = rq; ws->ratio_count = rc; ws->gamma_q = gq; }
                             __syncwarp();
                         }
-                        worst = NNR ? nnr_worst : w.nn_d[k - 1];
+                        worst = nn_front;
                     }
                 }
             }
@@ -763,13 +767,10 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
         __syncwarp();
         if (overflow) {
             if (lane == 0) { const uint32_t o = atomicAdd(a.counters + 1, 1u); a.overflow_list[o] = q; }
-        } else if (NNR) {
-            if (lane < a.kout) {
-                const bool have = lane < nn_m;
-                a.ids[(size_t)q * a.kout + lane] = have ? (int64_t)nnr_i : (int64_t)-1;
-                a.dists[(size_t)q * a.kout + lane] = have ? nnr_d : FLT_MAX;
-            }
         } else if (a.kout > 0) {
+            if (lane == 0)
+                for (uint32_t len = nn_m; len > 1; --len) nnh_pop_heap(w.nn_d, w.nn_i, len);   // std::sort_heap: ascending
+            __syncwarp();
             for (uint32_t j = lane; j < a.kout; j += 32) {
                 const bool have = j < nn_m;
                 a.ids[(size_t)q * a.kout + j] = have ? (int64_t)w.nn_i[j] : (int64_t)-1;
@@ -804,24 +805,21 @@ __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const
     }
 }
 
-size_t search_smem_per_warp(const DevIndex& ix, uint32_t k, bool stats) { return smem_per_warp(ix.D, ix.B, k, !stats && k <= 32); }
+size_t search_smem_per_warp(const DevIndex& ix, uint32_t k, bool) { return smem_per_warp(ix.D, ix.B, k); }
 
 #ifndef CPB_HOST_EMULATION   // tests/native/ compiles the kernels of this file for the host
 typedef void (*SearchKernel)(const DevIndex, const SearchArgs);
 
-template <int DT, bool ST, bool NN>
+template <int DT, bool ST>
 static SearchKernel pick_kernel_b(uint32_t B) {
-    return B == 1 ? search_kernel<1, ST, DT, NN> : B == 2 ? search_kernel<2, ST, DT, NN> : search_kernel<4, ST, DT, NN>;
+    return B == 1 ? search_kernel<1, ST, DT> : B == 2 ? search_kernel<2, ST, DT> : search_kernel<4, ST, DT>;
 }
 template <int DT>
-static SearchKernel pick_kernel_d(uint32_t B, bool stats, bool nnr) {
-    if (stats) return pick_kernel_b<DT, true, false>(B);
-    return nnr ? pick_kernel_b<DT, false, true>(B) : pick_kernel_b<DT, false, false>(B);
+static SearchKernel pick_kernel_d(uint32_t B, bool stats) {
+    return stats ? pick_kernel_b<DT, true>(B) : pick_kernel_b<DT, false>(B);
 }
-// the result list is held in registers when it fits one entry per lane (the counting build keeps the shared-memory list)
-static SearchKernel pick_kernel(const DevIndex& ix, bool stats, uint32_t k) {
-    const bool nnr = k <= 32;
-    return ix.D == 128 ? pick_kernel_d<128>(ix.B, stats, nnr) : pick_kernel_d<0>(ix.B, stats, nnr);
+static SearchKernel pick_kernel(const DevIndex& ix, bool stats, uint32_t) {
+    return ix.D == 128 ? pick_kernel_d<128>(ix.B, stats) : pick_kernel_d<0>(ix.B, stats);
 }
 
 int search_max_ctas_per_sm(const DevIndex& ix, uint32_t k, int warps_per_cta, bool stats) {

@@ -84,20 +84,16 @@ extern "C" int emul_search(uint32_t dim, uint32_t bits, const uint8_t* records, 
     a.scratch = scratch.data() + (128 - reinterpret_cast<uintptr_t>(scratch.data()) % 128) % 128;
     a.bitmaps = bitmaps.data(); a.overflow_list = over.data(); a.counters = counters; a.stats = &st;
     const bool stats = stats_out != nullptr;
-    // the same selection as the launcher's pick_kernel: counting build keeps the shared-memory result list, otherwise the
-    // list lives in registers when k <= 32
-    const bool nnr = !stats && k <= 32;
+    // the same selection as the launcher's pick_kernel
     auto kern = [&](int) {
-#define CPB_EMUL_PICK(BITS, ST, DTV, NN) search_kernel<BITS, ST, DTV, NN>(ix, a)
-#define CPB_EMUL_BITS(ST, DTV, NN) do { if (bits == 1) CPB_EMUL_PICK(1, ST, DTV, NN); else if (bits == 2) CPB_EMUL_PICK(2, ST, DTV, NN); else CPB_EMUL_PICK(4, ST, DTV, NN); } while (0)
+#define CPB_EMUL_PICK(BITS, ST, DTV) search_kernel<BITS, ST, DTV>(ix, a)
+#define CPB_EMUL_BITS(ST, DTV) do { if (bits == 1) CPB_EMUL_PICK(1, ST, DTV); else if (bits == 2) CPB_EMUL_PICK(2, ST, DTV); else CPB_EMUL_PICK(4, ST, DTV); } while (0)
         if (D == 128) {
-            if (stats) CPB_EMUL_BITS(true, 128, false);
-            else if (nnr) CPB_EMUL_BITS(false, 128, true);
-            else CPB_EMUL_BITS(false, 128, false);
+            if (stats) CPB_EMUL_BITS(true, 128);
+            else CPB_EMUL_BITS(false, 128);
         } else {
-            if (stats) CPB_EMUL_BITS(true, 0, false);
-            else if (nnr) CPB_EMUL_BITS(false, 0, true);
-            else CPB_EMUL_BITS(false, 0, false);
+            if (stats) CPB_EMUL_BITS(true, 0);
+            else CPB_EMUL_BITS(false, 0);
         }
 #undef CPB_EMUL_BITS
 #undef CPB_EMUL_PICK

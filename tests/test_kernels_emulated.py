@@ -452,3 +452,21 @@ def test_slot_planes_by_warp_equals_the_lane_per_slot_sums(k3, bits, nch):
         sel = np.array([(slots >> l) & 1 for l in range(32)], bool)
         assert np.array_equal(out[0][sel], out[2][sel]) and np.array_equal(out[1][sel], out[3][sel]), hex(slots)
         assert not out[0][~sel].any() and not out[1][~sel].any()
+
+
+@pytest.mark.parametrize("dim,bits,k,stats", [(128, 4, 10, False), (64, 4, 10, True), (96, 2, 5, False), (32, 1, 7, False), (128, 4, 40, False)])
+def test_result_set_follows_the_reference_heap_where_distinct_ids_tie(k1, k3, oracle, dim, bits, k, stats):
+    """Forty vectors stored under fifteen ids each: distinct ids of bit-equal distance meet at the result set's eviction boundary
+    all the time, and which of them BoundedMaxHeap lets go is a matter of its heap layout (search/rabitq_search.hpp:26-35); an
+    ascending list that evicts its last entry differs from it in a quarter of these rows."""
+    fab = common.fabricate(600, dim, bits, seed=7 + dim, counts=(32, 32, 30, 12), layers=1)
+    fab.raw[:] = fab.raw[np.arange(600) % 40]
+    fab.norm_sq[:] = fab.norm_sq[np.arange(600) % 40]
+    q = np.random.default_rng(3).standard_normal((16, dim)).astype(np.float32)
+    ids, dists, over, _ = _search(k1, k3, oracle, dim, bits, fab.search_data, fab.search_data.shape[1], fab.nb_off, fab.raw, fab.norm_sq,
+                                  fab.calibration, fab.max_level, fab.entry_point, fab.layers, q, k, want_stats=stats)
+    assert over == 0
+    oid, od, _ = oracle.search_batch(oracle.index_view(fab), q, k)
+    gi, gd = common.sorted_rows(ids, dists)
+    wi, wd = common.sorted_rows(oid, od)
+    assert np.array_equal(gi, wi) and np.array_equal(_bits(gd), _bits(wd))

@@ -509,3 +509,23 @@ def test_fastscan_streaming_specialisation_equals_the_general_kernel(dim, bits):
     full = hooks.fastscan_blocks(ix, prep["uplanes"], prep["coeffs"], dqp, first_vertex=0, nblocks=fab.n)
     for name in ("est", "lower"):
         assert np.array_equal(_bits(lean[name].cpu().numpy()), _bits(full[name].cpu().numpy())), name
+
+
+@pytest.mark.parametrize("dim,bits,k", [(64, 4, 10), (128, 4, 10), (96, 2, 5), (32, 1, 7), (128, 4, 40)])
+def test_result_set_follows_the_reference_heap_where_distinct_ids_tie(oracle, dim, bits, k):
+    """Forty vectors stored under fifteen ids each: distinct ids of bit-equal distance meet at the result set's eviction boundary
+    all the time, and WHICH of them BoundedMaxHeap lets go is a matter of its heap layout (search/rabitq_search.hpp:26-35).  An
+    ascending list that evicts its last entry differs from it in a quarter of these rows."""
+    fab = common.fabricate(600, dim, bits, seed=7 + dim, counts=(32, 32, 30, 12), layers=1)
+    fab.raw[:] = fab.raw[np.arange(600) % 40]
+    fab.norm_sq[:] = fab.norm_sq[np.arange(600) % 40]
+    ix = common.gpu_index_from(fab)
+    view = oracle.index_view(fab)
+    q = np.random.default_rng(3).standard_normal((40, dim)).astype(np.float32)
+    _check_search(oracle, ix, view, q, k)                      # the counting build
+    ix.set_option("collect_stats", 0)                          # the fast one
+    ids, dists = ix.search_batch(q, k)
+    oid, od, _ = oracle.search_batch(view, q, k)
+    gi, gd = common.sorted_rows(ids, dists)
+    wi, wd = common.sorted_rows(oid, od)
+    assert np.array_equal(gi, wi) and np.array_equal(_bits(gd), _bits(wd))
