@@ -140,6 +140,27 @@ def test_search_vs_reference_module(oracle, bits):
         assert np.array_equal(rid, oid) and np.array_equal(_bits(rd), _bits(od))
 
 
+@needs_ref
+def test_search_vs_reference_module_where_distinct_ids_tie(oracle, tmp_path):
+    """Sixty vectors stored twenty times each, index built by the unmodified reference: every result row holds distinct ids of
+    bit-equal distance, and which of them survive an eviction is a matter of BoundedMaxHeap's layout (search/rabitq_search.hpp:
+    26-35).  The restatement must return the reference's rows entry for entry -- this pins the heap the kernels are held to
+    (tests/test_parity_gpu.py, tests/test_kernels_emulated.py: ..._where_distinct_ids_tie)."""
+    rng = np.random.default_rng(5)
+    base = np.tile(rng.standard_normal((60, 32)).astype(np.float32), (20, 1))
+    rng.shuffle(base)
+    path = tmp_path / "dup.bin"
+    ref = co.build_reference_index(base, 4, path, threads=4)
+    q = rng.standard_normal((300, 32)).astype(np.float32)
+    view = oracle.index_view(co.SaveFile(path))
+    for k in (10, 3, 25):
+        rid, rd = ref.search_batch(q, k)
+        oid, od, _ = oracle.search_batch(view, q, k)
+        assert np.array_equal(rid, oid) and np.array_equal(_bits(rd), _bits(od))
+        tied = sum(any(rd[r, a] == rd[r, b] and rid[r, a] != rid[r, b] for a in range(k) for b in range(a + 1, k)) for r in range(300))
+        assert tied > 250   # the situation the test is about does occur
+
+
 def test_exhaustive_restatement_against_the_reference_composition(oracle):
     """cpo_exhaustive_search against tests/golden/exhaustive_golden.npz, which was composed in Python from primitives
     executed by the unmodified reference (tests/golden/make_exhaustive_golden.py): integer sums, estimate bits, and the
