@@ -526,6 +526,24 @@ def test_result_set_follows_the_reference_heap_where_distinct_ids_tie(oracle, di
     ix.set_option("collect_stats", 0)                          # the fast one
     ids, dists = ix.search_batch(q, k)
     oid, od, _ = oracle.search_batch(view, q, k)
-    gi, gd = common.sorted_rows(ids, dists)
-    wi, wd = common.sorted_rows(oid, od)
-    assert np.array_equal(gi, wi) and np.array_equal(_bits(gd), _bits(wd))
+    assert np.array_equal(ids, oid) and np.array_equal(_bits(dists), _bits(od))   # entry for entry: sort_heap's order of equal distances too
+
+
+@pytest.mark.skipif(not co.have_ref(), reason="oracle/_ref (compiled reference) not present")
+def test_rows_equal_the_reference_modules_where_distinct_ids_tie(tmp_path):
+    """The same situation on an index the unmodified reference built and searched itself (sixty vectors stored twenty times
+    each): its rows, entry for entry."""
+    import cphnsw_b200
+
+    rng = np.random.default_rng(5)
+    base = np.tile(rng.standard_normal((60, 32)).astype(np.float32), (20, 1))
+    rng.shuffle(base)
+    path = tmp_path / "dup.bin"
+    ref = co.build_reference_index(base, 4, path, threads=4)
+    q = rng.standard_normal((300, 32)).astype(np.float32)
+    ix = cphnsw_b200.CPIndex(32, 4)
+    ix.load(str(path))
+    for k in (10, 3, 25, 40):
+        rid, rd = ref.search_batch(q, k)
+        ids, dists = ix.search_batch(q, k)
+        assert np.array_equal(ids, rid) and np.array_equal(_bits(dists), _bits(rd))
