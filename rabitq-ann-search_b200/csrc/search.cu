@@ -433,6 +433,11 @@ __device__ __forceinline__ uint32_t greedy_descent(const DevIndex& ix, const War
 // carry-save compression, 12 issue slots and 33 ALU-pipe instructions fewer per expansion for 21 more POPC: 518 k; a larger L1
 // (shared-memory carve-out 164 KB instead of 196 KB, which the trimmed per-warp footprint allows at 30 or 28 warps per SM):
 // 540 k / 538 k.  The kernel sits on the issue, ALU and XU limits at once; none of them can be traded for another.)
+// (Tried and not kept: the other planes evaluated BEFORE the probes' answers are back, i.e. whenever any slot, new or not, is
+// under the plane-0 bound -- 98 % of the expansions instead of 58 %: -11 %.  The kernel does feel its ALU / XU instructions,
+// which is what slot_planes_by_warp then saved.  A shared-memory cache of the key at the parent position of the leaf the last
+// push wrote -- pushes and pops alternate, so push after push lands under the same parent, and a push that finds the key and
+// stays a leaf needs neither the arena nor a ballot: -2 %.)
 template <int B, bool STATS, int DT>
 __global__ void __launch_bounds__(256, 4) search_kernel(const DevIndex ix, const SearchArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
